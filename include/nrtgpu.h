@@ -1,0 +1,176 @@
+/*
+ * nrtgpu.h -- C ABI of the B200-native query-execution engine that drops in behind nrtsearch's
+ * SearchHandler / SearchRequestProcessor (reference = Yelp/nrtsearch @ 59c38655, Lucene 10.4.0).
+ *
+ * The reference has NO native seam for query execution (it is pure Java over lucene-core); the
+ * entry points below are what a JNI shim would bind at the three Lucene API call sites that bound the
+ * hot path:
+ *
+ *   nrtgpu_index_build / _close   <->  ShardSearcherFactory.newSearcher(reader, previous)
+ *                                      src/main/java/com/yelp/nrtsearch/server/index/ShardState.java:506-526
+ *                                      (one device image per reader version; freed after the last
+ *                                      ShardState.release, :406-425)
+ *   nrtgpu_search_bool            <->  searcher.search(query, collectorManager)
+ *                                      src/main/java/com/yelp/nrtsearch/server/handler/SearchHandler.java:1412-1413, :556
+ *                                      (BooleanQuery of TermQuery / range / match-all clauses built at
+ *                                      .../query/QueryNodeMapper.java:257-283; collector config from
+ *                                      .../search/collectors/RelevanceCollector.java:42-69)
+ *   nrtgpu_search_knn             <->  knnQuery.rewrite(searcher)   .../search/KnnUtils.java:56
+ *                                      and ExactVectorQuery          .../query/vector/ExactVectorQuery.java:137-173
+ *   nrtgpu_merge_topk             <->  TopDocs.merge(0, numHits, perSlice[])
+ *                                      src/main/java/org/apache/lucene/search/LazyQueueTopScoreDocCollectorManager.java:137-144
+ *   nrtgpu_blend_rrf              <->  BlenderOperation.blend (weighted RRF)
+ *                                      .../search/multiretriever/blender/BlenderOperation.java:76-87
+ *   nrtgpu_rescore_combine        <->  RescoreOperation.rescore / QueryRescore.combine
+ *                                      .../rescore/QueryRescore.java:39-57
+ *
+ * Conventions: every function returns 0 on success, non-zero nrtgpu_status otherwise; the message is
+ * available from nrtgpu_last_error() (thread-local). Handles are opaque; output buffers are caller
+ * allocated (Java direct ByteBuffers); the library never frees caller memory. All entry points are
+ * re-entrant (called concurrently from the reference's SERVER / SEARCH / RETRIEVER pools).
+ * There is NO CPU fallback: without a CUDA device every call fails with NRTGPU_ERR_CUDA.
+ */
+#ifndef NRTGPU_H
+#define NRTGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NRTGPU_OK = 0,
+  NRTGPU_ERR_INVALID = 1,      /* IllegalArgumentException on the Java side */
+  NRTGPU_ERR_CUDA = 2,         /* -> Status.INTERNAL (SearchHandler.java:136-145) */
+  NRTGPU_ERR_UNSUPPORTED = 3,  /* query shape outside the GPU path: caller falls through to Lucene */
+  NRTGPU_ERR_OOM = 4
+} nrtgpu_status;
+
+typedef struct nrtgpu_ctx nrtgpu_ctx;     /* one per (process, device) */
+typedef struct nrtgpu_index nrtgpu_index; /* device image of one shard at one reader version */
+typedef struct nrtgpu_batch nrtgpu_batch; /* a compiled query batch resident on the device */
+
+const char* nrtgpu_last_error(void);
+int nrtgpu_version(void);
+
+/* device_id: CUDA ordinal (one shard group per GPU; one process per GPU). */
+int nrtgpu_init(int device_id, nrtgpu_ctx** out);
+void nrtgpu_shutdown(nrtgpu_ctx* ctx);
+
+/* BooleanClause.Occur and leaf kinds */
+enum { NRTGPU_SHOULD = 0, NRTGPU_MUST = 1, NRTGPU_FILTER = 2, NRTGPU_MUST_NOT = 3 };
+enum { NRTGPU_TERM = 0, NRTGPU_RANGE_I64 = 1, NRTGPU_MATCH_ALL = 2 };
+/* VectorSimilarityFunction (reference VectorFieldDef.java:77-88) */
+enum { NRTGPU_SIM_L2 = 0, NRTGPU_SIM_DOT = 1, NRTGPU_SIM_COSINE = 2, NRTGPU_SIM_MIP = 3 };
+
+/* Host-side description of one shard, i.e. what the adaptor reads out of the LeafReaders
+ * (terms()/postings()/getNormValues()/getNumericDocValues()/getFloatVectorValues()). Term ids are the
+ * adaptor's dense numbering of (field, term); doc ids are shard-local, results carry doc_base + local. */
+typedef struct {
+  int32_t n_docs;
+  int32_t doc_base;
+  int32_t n_terms;
+  const int64_t* term_off;          /* [n_terms+1] CSR offsets into post_* */
+  const int32_t* post_docs;         /* ascending per term */
+  const int32_t* post_freqs;        /* >= 1 */
+  const int32_t* term_field;        /* [n_terms] text-field id, NULL = all field 0 */
+  const int64_t* term_df;           /* [n_terms] INDEX-WIDE docFreq (termStatistics), NULL = CSR length */
+  int32_t n_fields;
+  const uint8_t* const* norms;      /* [n_fields] -> [n_docs] SmallFloat norm bytes, NULL entry = omitNorms */
+  const int64_t* field_doc_count;   /* [n_fields] INDEX-WIDE collectionStatistics.docCount */
+  const int64_t* field_sum_ttf;     /* [n_fields] INDEX-WIDE sumTotalTermFreq */
+  const float* field_k1;            /* [n_fields] or NULL => 1.2 */
+  const float* field_b;             /* [n_fields] or NULL => 0.75 */
+  int32_t n_columns;
+  const int64_t* const* columns;    /* [n_columns] -> [n_docs] numeric doc values (sortable-long domain) */
+  const uint8_t* const* column_has; /* [n_columns] -> [n_docs] 0/1, NULL entry = every doc has a value */
+  const uint8_t* live_docs;         /* [n_docs] 0/1 or NULL */
+  /* one float vector field (more via nrtgpu_index_add_vectors) */
+  int32_t vec_dims;                 /* 0 = none */
+  int32_t vec_similarity;
+  int32_t vec_count;                /* number of vectors (ord -> doc via vec_docs, NULL = identity) */
+  const float* vectors;             /* [vec_count * vec_dims] */
+  const int32_t* vec_docs;
+} nrtgpu_shard_desc;
+
+int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* desc, nrtgpu_index** out);
+int nrtgpu_index_close(nrtgpu_index* ix);
+/* bytes of device memory held by the image */
+int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix);
+
+typedef struct {
+  int32_t occur;  /* NRTGPU_SHOULD.. */
+  int32_t kind;   /* NRTGPU_TERM.. */
+  int32_t id;     /* term id or column id */
+  float boost;    /* product of enclosing BoostQuery boosts (weight = boost * idf) */
+  int64_t lo, hi; /* inclusive range bounds */
+} nrtgpu_clause;
+
+typedef struct {
+  int32_t clause_begin, clause_end; /* flat BooleanQuery = clauses[clause_begin:clause_end] */
+  int32_t min_should_match;
+  int32_t has_after;                /* searchAfter (LazyQueueTopScoreDocCollector.java:112) */
+  int32_t after_doc;
+  float after_score;
+} nrtgpu_query;
+
+/* flags */
+enum {
+  NRTGPU_FLAG_NONE = 0,
+  NRTGPU_FLAG_NO_PRUNING = 1 /* force exhaustive evaluation even when total_hits_threshold allows pruning */
+};
+
+/* One-shot search with HOST buffers (the JNI entry point): uploads the batch, runs, copies results
+ * back, synchronises `stream` (a cudaStream_t, NULL = default stream).
+ *   out_docs/out_scores [nq*top_k] (score desc, doc asc), out_counts [nq],
+ *   out_total_hits [nq], out_relation [nq] (0 = EQUAL_TO, 1 = GREATER_THAN_OR_EQUAL_TO).
+ * total_hits_threshold == INT32_MAX <=> ScoreMode.COMPLETE (exact counts, no pruning). */
+int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                       const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                       int32_t total_hits_threshold, int32_t flags, void* stream, int32_t* out_docs,
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
+                       uint8_t* out_relation);
+
+/* Split form: compile+upload once, launch many times with everything resident in HBM. */
+int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                         int32_t total_hits_threshold, int32_t flags, nrtgpu_batch** out);
+int nrtgpu_batch_run(nrtgpu_batch* b, void* stream);   /* asynchronous: kernels only */
+int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream, int32_t* out_docs, float* out_scores,
+                       int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation);
+/* device pointers of the last run's results: uint64 keys are not exposed; these are the final arrays */
+int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts);
+/* stats of the compiled batch: algorithmic postings (sum of df over all term clauses), kernel launches per run */
+int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run,
+                       int64_t* work_items);
+/* duration (ms) of stage `stage` in the most recent run (events recorded on the run's stream;
+ * the stream must have been synchronised). stage 0 = posting traversal kernel, 1 = slice merge. */
+int nrtgpu_batch_stage_ms(nrtgpu_batch* b, int32_t stage, float* ms);
+int nrtgpu_batch_free(nrtgpu_batch* b);
+
+/* Exact kNN (ExactVectorQuery / KnnFloatVectorQuery with exact semantics): HOST buffers. */
+int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k,
+                      const float* boosts /*[nq] or NULL*/, const uint8_t* filter /*[n_docs] 0/1 or NULL*/,
+                      void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts);
+
+/* TopDocs.merge over `n_lists` per-shard lists resident on the DEVICE (the receive buffer of the NCCL
+ * all-gather): docs/scores [n_lists][nq][top_k], counts [n_lists][nq]; outputs on the device. */
+int nrtgpu_merge_topk_device(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k,
+                             const int32_t* d_docs, const float* d_scores, const int32_t* d_counts,
+                             int32_t* d_out_docs, float* d_out_scores, int32_t* d_out_counts, void* stream);
+
+/* Weighted RRF blend of R retrievers' lists for nq queries (HOST buffers):
+ * docs [R][nq][top_in], counts [R][nq], boosts [R]; out [nq][top_out]. */
+int nrtgpu_blend_rrf(nrtgpu_ctx* ctx, int32_t n_retrievers, int32_t nq, int32_t top_in,
+                     const int32_t* docs, const int32_t* counts, const float* boosts,
+                     int32_t rank_constant, int32_t top_out, int32_t* out_docs, float* out_scores,
+                     int32_t* out_counts, int32_t* out_total);
+
+/* QueryRescore.combine + re-sort for nq hit lists (HOST buffers, in place): [nq][n_hits]. */
+int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const int32_t* counts,
+                           int32_t* docs, float* scores, const uint8_t* second_matches,
+                           const float* second_scores, double query_weight, double rescore_weight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

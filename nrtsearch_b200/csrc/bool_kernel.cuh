@@ -1,0 +1,473 @@
+// Batched BooleanQuery execution over HBM-resident postings: window engine + slice merge.
+//
+// Replaces, for a whole batch of queries at once, the per-query chain
+//   IndexSearcher.search -> BooleanWeight.bulkScorer -> (MaxScoreBulkScorer | ConjunctionDISI) ->
+//   TermScorer/BM25Scorer -> TopScoreDocCollector
+// that the reference drives from src/main/java/com/yelp/nrtsearch/server/handler/SearchHandler.java:1412.
+//
+// Work item = (doc slice, query). A CTA sweeps its slice in windows of W docs:
+//   pass 1 (scatter): every posting of every term clause in the window stores its saturated tf byte
+//                     into byte `slot` of a W-entry shared-memory word array (no atomics: doc ids
+//                     are unique inside one posting list and the passes are barrier separated);
+//   pass 2 (emit):    the postings of the DRIVER clauses are re-read; the lowest driver clause present
+//                     in a doc's word "owns" the doc, clears the word, evaluates the boolean
+//                     constraints, scores the matched clauses with Lucene's BM25 float formula, sums
+//                     in double in clause order, and offers (score, doc) to the CTA's candidate
+//                     buffer if it beats the query's running threshold theta;
+//   pass 3 (clean):   non-driver clauses clear the words pass 2 did not visit.
+// Smem cost is proportional to postings, not to W. theta is a 64-bit (score, ~doc) key shared by all
+// slices of a query through one global atomicMax word -- the device analogue of the reference's
+// LazyMaxScoreAccumulator (src/main/java/org/apache/lucene/search/LazyMaxScoreAccumulator.java:21-70),
+// used here only to drop hits that provably cannot enter the top-k (results stay exact).
+#pragma once
+#include "common.cuh"
+
+namespace nrtgpu {
+
+constexpr int kMaxClauses = 16;     // clauses per flat BooleanQuery on the GPU path
+constexpr int kMaxTermSlots = 8;    // term clauses per query (u32 words: 4, u64 words: 8)
+constexpr int kWindowDocs = 16384;  // W
+constexpr int kSliceWindows = 64;   // windows per work item  => 1,048,576 docs per slice
+constexpr int kCandCap = 4096;      // candidate buffer (keys) per CTA, power of two
+constexpr int kThreads = 512;
+constexpr int kMaxTopK = 1024;
+
+struct DevClause {
+  int64_t post_base;  // offset of the term's postings in post_docs / post_f8
+  int32_t n_post;
+  int32_t occur;
+  int32_t kind;
+  int32_t slot;       // byte index inside the window word (term clauses), -1 otherwise
+  int32_t field;      // text field (norms + cache) for term clauses
+  int32_t col;        // doc-value column for range clauses
+  float weight;       // boost*idf (term) or constant score = boost (range / match-all)
+  int32_t scoring;    // 1 if the clause contributes to the score (MUST / SHOULD)
+  int64_t lo, hi;
+};
+
+struct DevQuery {
+  int32_t clause_begin, n_clauses;
+  int32_t n_term;          // number of term clauses (= slots used)
+  int32_t n_req;           // MUST + FILTER clauses (all kinds)
+  int32_t need_should;     // minimum matching SHOULD clauses
+  int32_t msm;             // minimumNumberShouldMatch as given
+  uint32_t req_term_mask;  // bit s set: term slot s is MUST/FILTER
+  uint32_t not_term_mask;  // bit s set: term slot s is MUST_NOT
+  uint32_t driver_mask;    // bit s set: term slot s drives pass 2
+  int32_t dense_driver;    // 1: iterate every doc of the window instead of driver postings
+  int32_t has_non_driver;  // 1: some term slot is not a driver (pass 3 needed)
+  int32_t has_nonterm;     // 1: range / match-all clauses present
+  int32_t empty;           // 1: can match nothing
+  int32_t has_after;
+  uint64_t after_key;
+};
+
+struct DevIndexView {
+  int32_t n_docs;
+  int32_t doc_base;
+  const int32_t* post_docs;
+  const uint8_t* post_f8;        // min(freq, 255)
+  const int64_t* exc_pos;        // sorted global posting indices with freq >= 255
+  const int32_t* exc_freq;
+  int32_t n_exc;
+  const uint8_t* const* norms;   // [n_fields] device pointers (NULL = omitNorms)
+  const float* caches;           // [n_fields][256]
+  const int64_t* const* col64;   // [n_columns] (NULL if stored as int32)
+  const int32_t* const* col32;   // [n_columns] (NULL if stored as int64)
+  const uint8_t* const* col_has; // [n_columns] (NULL = all)
+  const uint32_t* live_bits;     // bitmap or NULL
+};
+
+struct BoolLaunch {
+  DevIndexView ix;
+  const DevClause* clauses;
+  const DevQuery* queries;
+  const int32_t* work_query;   // [n_work] query index per work item (slice-major order)
+  const int32_t* work_slice;   // [n_work]
+  int32_t n_work;
+  int32_t n_slices;
+  int32_t top_k;
+  uint64_t* theta;             // [nq] running k-th best key (0 = none yet)
+  unsigned long long* total_hits;  // [nq]
+  uint64_t* slice_keys;        // [nq][n_slices][top_k]
+  int32_t* slice_cnt;          // [nq][n_slices]
+};
+
+template <typename SlotT>
+struct SlotTraits;
+template <> struct SlotTraits<uint32_t> { static constexpr int kSlots = 4; };
+template <> struct SlotTraits<uint64_t> { static constexpr int kSlots = 8; };
+
+template <typename SlotT>
+struct BoolSmem {
+  SlotT slots[kWindowDocs];
+  uint64_t cand[kCandCap];
+  uint32_t bounds[kMaxTermSlots][kSliceWindows + 1];
+  float cache[kMaxTermSlots][256];
+  DevClause cl[kMaxClauses];
+  DevQuery q;
+  int cand_count;
+  unsigned long long theta;
+};
+
+template <typename SlotT>
+__device__ __forceinline__ uint32_t presence_mask(SlotT s) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < SlotTraits<SlotT>::kSlots; ++i) m |= (((s >> (8 * i)) & 0xff) != 0 ? 1u : 0u) << i;
+  return m;
+}
+
+// exact tf of posting (clause c, doc) when the byte saturated: find the posting, then the exception list
+template <typename SlotT>
+__device__ __noinline__ float exact_freq_slow(const DevIndexView& ix, const DevClause& c, int32_t doc) {
+  const int32_t* docs = ix.post_docs + c.post_base;
+  int lo = 0, hi = c.n_post;
+  while (lo < hi) { int m = (lo + hi) >> 1; if (docs[m] < doc) lo = m + 1; else hi = m; }
+  int64_t gp = c.post_base + lo;
+  int a = 0, b = ix.n_exc;
+  while (a < b) { int m = (a + b) >> 1; if (ix.exc_pos[m] < gp) a = m + 1; else b = m; }
+  if (a < ix.n_exc && ix.exc_pos[a] == gp) return (float)ix.exc_freq[a];
+  return 255.0f;
+}
+
+// Evaluate the boolean constraints + score for one candidate doc. Returns false if the doc does not match.
+// Score combination follows Lucene's BooleanScorerSupplier: conjunction / disjunction sums are double,
+// required+optional is ReqOptSumScorer's float add (msm == 0) or ConjunctionScorer's double add (msm > 0).
+template <typename SlotT>
+__device__ __forceinline__ bool evaluate_doc(const DevIndexView& ix, const BoolSmem<SlotT>& sm, int32_t doc,
+                                             SlotT slot, float* out_score) {
+  const DevQuery& q = sm.q;
+  uint32_t m = presence_mask<SlotT>(slot);
+  if ((m & q.req_term_mask) != q.req_term_mask) return false;
+  if (m & q.not_term_mask) return false;
+  if (ix.live_bits && !((ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
+  double must_sum = 0.0, should_sum = 0.0;
+  int n_req = 0, n_should = 0;
+  for (int i = 0; i < q.n_clauses; ++i) {
+    const DevClause& c = sm.cl[i];
+    bool present;
+    float s = 0.0f;
+    if (c.kind == NRTGPU_TERM) {
+      uint32_t b = (uint32_t)((slot >> (8 * c.slot)) & 0xff);
+      present = b != 0;
+      if (present && c.scoring) {
+        float f = (b == 255u) ? exact_freq_slow<SlotT>(ix, c, doc) : (float)b;
+        const uint8_t* nrm = ix.norms[c.field];
+        uint32_t nb = nrm ? (uint32_t)nrm[doc] : 1u;
+        s = bm25_score(c.weight, f, sm.cache[c.slot][nb]);
+      }
+    } else if (c.kind == NRTGPU_RANGE_I64) {
+      const uint8_t* has = ix.col_has[c.col];
+      present = !has || has[doc];
+      if (present) {
+        int64_t v = ix.col32[c.col] ? (int64_t)ix.col32[c.col][doc] : ix.col64[c.col][doc];
+        present = (v >= c.lo) && (v <= c.hi);
+      }
+      s = c.weight;
+    } else {
+      present = true;
+      s = c.weight;
+    }
+    if (!present) {
+      if (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER) return false;
+      continue;
+    }
+    switch (c.occur) {
+      case NRTGPU_MUST: must_sum += (double)s; ++n_req; break;
+      case NRTGPU_FILTER: ++n_req; break;
+      case NRTGPU_SHOULD: should_sum += (double)s; ++n_should; break;
+      default: return false;  // MUST_NOT present
+    }
+  }
+  if (n_should < q.need_should) return false;
+  float score;
+  if (q.n_req == 0) score = (float)should_sum;
+  else {
+    float req = (float)must_sum;
+    if (n_should == 0) score = req;
+    else {
+      float opt = (float)should_sum;
+      score = (q.msm > 0) ? (float)((double)req + (double)opt) : __fadd_rn(req, opt);
+    }
+  }
+  *out_score = score;
+  return true;
+}
+
+// sort the candidate buffer, keep the best top_k, raise theta (local + global)
+template <typename SlotT>
+__device__ __forceinline__ void compact_candidates(BoolSmem<SlotT>& sm, int top_k, uint64_t* g_theta) {
+  __syncthreads();
+  int n = sm.cand_count;
+  if (n > kCandCap) n = kCandCap;  // cannot happen (capacity invariant); defensive
+  int m = next_pow2(n < 2 ? 2 : n);
+  for (int i = n + threadIdx.x; i < m; i += blockDim.x) sm.cand[i] = 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(sm.cand, m);
+  if (threadIdx.x == 0) {
+    int keep = n < top_k ? n : top_k;
+    sm.cand_count = keep;
+    if (keep == top_k) {
+      unsigned long long kth = sm.cand[top_k - 1];
+      unsigned long long old = atomicMax((unsigned long long*)g_theta, kth);
+      unsigned long long t = old > kth ? old : kth;
+      if (t > sm.theta) sm.theta = t;
+    } else {
+      unsigned long long g = *(volatile unsigned long long*)g_theta;
+      if (g > sm.theta) sm.theta = g;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename SlotT>
+__global__ void __launch_bounds__(kThreads, 2) bool_window_kernel(BoolLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BoolSmem<SlotT>& sm = *reinterpret_cast<BoolSmem<SlotT>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  for (int wi = blockIdx.x; wi < L.n_work; wi += gridDim.x) {
+    const int qi = L.work_query[wi];
+    const int slice = L.work_slice[wi];
+    __syncthreads();  // previous work item fully retired
+    if (tid == 0) {
+      sm.q = L.queries[qi];
+      sm.cand_count = 0;
+      sm.theta = *(volatile unsigned long long*)&L.theta[qi];
+    }
+    __syncthreads();
+    const int ncl = sm.q.n_clauses;
+    if (tid < ncl) sm.cl[tid] = L.clauses[sm.q.clause_begin + tid];
+    for (int i = tid; i < kWindowDocs; i += kThreads) sm.slots[i] = 0;
+    __syncthreads();
+    // per-slot BM25 caches
+    for (int i = tid; i < ncl * 256; i += kThreads) {
+      int c = i >> 8;
+      if (sm.cl[c].kind == NRTGPU_TERM) sm.cache[sm.cl[c].slot][i & 255] = L.ix.caches[sm.cl[c].field * 256 + (i & 255)];
+    }
+    const int32_t slice_base = slice * (kSliceWindows * kWindowDocs);
+    int32_t slice_end = slice_base + kSliceWindows * kWindowDocs;
+    if (slice_end > L.ix.n_docs || slice_end < 0) slice_end = L.ix.n_docs;
+    const int nwin = (slice_end - slice_base + kWindowDocs - 1) / kWindowDocs;
+    // posting bounds of every term clause at every window boundary (lower_bound over the full list)
+    for (int i = tid; i < ncl * (kSliceWindows + 1); i += kThreads) {
+      int c = i / (kSliceWindows + 1), w = i % (kSliceWindows + 1);
+      if (sm.cl[c].kind != NRTGPU_TERM) continue;
+      int64_t target64 = (int64_t)slice_base + (int64_t)w * kWindowDocs;
+      int32_t target = target64 > (int64_t)slice_end ? slice_end : (int32_t)target64;
+      const int32_t* docs = L.ix.post_docs + sm.cl[c].post_base;
+      int lo = 0, hi = sm.cl[c].n_post;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(docs + mid) < target) lo = mid + 1; else hi = mid; }
+      sm.bounds[sm.cl[c].slot][w] = (uint32_t)lo;
+    }
+    __syncthreads();
+
+    unsigned long long my_hits = 0;
+    int cand_ub = 0;  // CTA-uniform upper bound of cand_count
+    const bool dense = sm.q.dense_driver != 0;
+    const bool has_after = sm.q.has_after != 0;
+    const uint64_t after_key = sm.q.after_key;
+
+    for (int w = 0; w < nwin; ++w) {
+      const int32_t wbase = slice_base + w * kWindowDocs;
+      const int32_t wlen = min(kWindowDocs, slice_end - wbase);
+      // ---------------- pass 1: scatter tf bytes
+      bool any = dense;
+      for (int c = 0; c < ncl; ++c) {
+        if (sm.cl[c].kind != NRTGPU_TERM) continue;
+        const int s = sm.cl[c].slot;
+        const uint32_t b0 = sm.bounds[s][w], b1 = sm.bounds[s][w + 1];
+        if (b1 > b0) any = true;
+        const int32_t* docs = L.ix.post_docs + sm.cl[c].post_base;
+        const uint8_t* f8 = L.ix.post_f8 + sm.cl[c].post_base;
+        const bool scoring = sm.cl[c].scoring != 0;
+        unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
+        for (uint32_t p = b0 + tid; p < b1; p += kThreads) {
+          int32_t d = docs[p] - wbase;
+          unsigned char f = scoring ? f8[p] : (unsigned char)1;
+          slot_bytes[(size_t)d * sizeof(SlotT) + s] = f;
+        }
+      }
+      if (!any) continue;  // CTA-uniform: no postings in this window
+      __syncthreads();
+      // ---------------- pass 2: emit
+      auto offer = [&](bool matched, int32_t doc, float score) {
+        // converged call (all lanes of the warp)
+        bool is_cand = false;
+        uint64_t key = 0;
+        if (matched) {
+          ++my_hits;
+          key = make_key(score, doc);
+          is_cand = key > sm.theta && (!has_after || key < after_key);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sm.cand_count, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (is_cand) sm.cand[base + __popc(bal & ((1u << lane) - 1))] = key;
+        }
+      };
+      auto round_end = [&]() {
+        cand_ub += kThreads;
+        if (cand_ub > kCandCap - kThreads) {
+          __syncthreads();
+          int n = sm.cand_count;
+          if (n > kCandCap - kThreads) { compact_candidates(sm, L.top_k, &L.theta[qi]); n = sm.cand_count; }
+          cand_ub = n;
+        }
+      };
+      if (!dense) {
+        for (int c = 0; c < ncl; ++c) {
+          if (sm.cl[c].kind != NRTGPU_TERM) continue;
+          const int s = sm.cl[c].slot;
+          if (!((sm.q.driver_mask >> s) & 1u)) continue;
+          // bytes of lower driver slots
+          SlotT below = 0;
+          for (int j = 0; j < s; ++j) if ((sm.q.driver_mask >> j) & 1u) below |= (SlotT)0xff << (8 * j);
+          const SlotT own = (SlotT)0xff << (8 * s);
+          const uint32_t b0 = sm.bounds[s][w], b1 = sm.bounds[s][w + 1];
+          const int32_t* docs = L.ix.post_docs + sm.cl[c].post_base;
+          for (uint32_t p0 = b0; p0 < b1; p0 += kThreads) {
+            uint32_t p = p0 + tid;
+            bool matched = false; int32_t doc = 0; float score = 0.0f;
+            if (p < b1) {
+              doc = docs[p];
+              SlotT v = sm.slots[doc - wbase];
+              if ((v & below) == 0 && (v & own) != 0) {
+                sm.slots[doc - wbase] = 0;
+                matched = evaluate_doc<SlotT>(L.ix, sm, doc, v, &score);
+              }
+            }
+            offer(matched, doc, score);
+            round_end();
+          }
+        }
+      } else {
+        for (int i0 = 0; i0 < wlen; i0 += kThreads) {
+          int i = i0 + tid;
+          bool matched = false; int32_t doc = wbase + i; float score = 0.0f;
+          if (i < wlen) {
+            SlotT v = sm.slots[i];
+            if (v) sm.slots[i] = 0;
+            matched = evaluate_doc<SlotT>(L.ix, sm, doc, v, &score);
+          }
+          offer(matched, doc, score);
+          round_end();
+        }
+      }
+      __syncthreads();
+      // ---------------- pass 3: clear words of non-driver clauses
+      if (!dense && sm.q.has_non_driver) {
+        for (int c = 0; c < ncl; ++c) {
+          if (sm.cl[c].kind != NRTGPU_TERM) continue;
+          const int s = sm.cl[c].slot;
+          if ((sm.q.driver_mask >> s) & 1u) continue;
+          const uint32_t b0 = sm.bounds[s][w], b1 = sm.bounds[s][w + 1];
+          const int32_t* docs = L.ix.post_docs + sm.cl[c].post_base;
+          for (uint32_t p = b0 + tid; p < b1; p += kThreads) sm.slots[docs[p] - wbase] = 0;
+        }
+        __syncthreads();
+      }
+    }
+    // ---------------- finish the work item
+    compact_candidates(sm, L.top_k, &L.theta[qi]);
+    const int keep = sm.cand_count;
+    uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
+    for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
+    if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
+    // total hits
+    for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
+    if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], my_hits);
+  }
+}
+
+// ---- per-query merge of the slice lists (TopDocs.merge semantics: key order is total) ----
+struct MergeLaunch {
+  const uint64_t* slice_keys;  // [nq][n_lists][top_k]
+  const int32_t* slice_cnt;    // [nq][n_lists]
+  int32_t n_lists, top_k, nq;
+  int32_t doc_base;
+  int32_t* out_docs; float* out_scores; int32_t* out_counts;
+};
+
+constexpr int kMergeThreads = 256;
+constexpr int kMergeCap = 4096;
+
+__global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch M) {
+  __shared__ uint64_t keys[kMergeCap];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  int have = 0;  // sorted best-so-far in keys[0..have)
+  int l = 0;
+  while (l < M.n_lists) {
+    // append as many whole lists as fit
+    __syncthreads();
+    int fill = have;
+    int l_end = l;
+    while (l_end < M.n_lists) {
+      int c = M.slice_cnt[(size_t)q * M.n_lists + l_end];
+      if (fill + c > kMergeCap) break;
+      const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + l_end) * M.top_k;
+      for (int i = tid; i < c; i += kMergeThreads) keys[fill + i] = src[i];
+      fill += c; ++l_end;
+    }
+    l = l_end;
+    int m = next_pow2(fill < 2 ? 2 : fill);
+    for (int i = fill + tid; i < m; i += kMergeThreads) keys[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(keys, m);
+    have = fill < M.top_k ? fill : M.top_k;
+  }
+  __syncthreads();
+  for (int i = tid; i < have; i += kMergeThreads) {
+    uint64_t k = keys[i];
+    M.out_docs[(size_t)q * M.top_k + i] = key_doc(k) + M.doc_base;
+    M.out_scores[(size_t)q * M.top_k + i] = key_score(k);
+  }
+  if (tid == 0) M.out_counts[q] = have;
+}
+
+// TopDocs.merge over lists of (doc, score) pairs (cross-shard merge after the NCCL all-gather).
+struct MergePairsLaunch {
+  const int32_t* docs; const float* scores; const int32_t* counts;  // [n_lists][nq][top_k], [n_lists][nq]
+  int32_t n_lists, top_k, nq;
+  int32_t* out_docs; float* out_scores; int32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(MergePairsLaunch M) {
+  __shared__ uint64_t keys[kMergeCap];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  int have = 0;
+  int l = 0;
+  while (l < M.n_lists) {
+    int fill = have;
+    int l_end = l;
+    __syncthreads();
+    while (l_end < M.n_lists) {
+      int c = M.counts[(size_t)l_end * M.nq + q];
+      if (fill + c > kMergeCap) break;
+      size_t base = ((size_t)l_end * M.nq + q) * M.top_k;
+      for (int i = tid; i < c; i += kMergeThreads) keys[fill + i] = make_key(M.scores[base + i], M.docs[base + i]);
+      fill += c; ++l_end;
+    }
+    l = l_end;
+    int m = next_pow2(fill < 2 ? 2 : fill);
+    for (int i = fill + tid; i < m; i += kMergeThreads) keys[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(keys, m);
+    have = fill < M.top_k ? fill : M.top_k;
+  }
+  __syncthreads();
+  for (int i = tid; i < have; i += kMergeThreads) {
+    uint64_t k = keys[i];
+    M.out_docs[(size_t)q * M.top_k + i] = key_doc(k);
+    M.out_scores[(size_t)q * M.top_k + i] = key_score(k);
+  }
+  if (tid == 0) M.out_counts[q] = have;
+}
+
+}  // namespace nrtgpu

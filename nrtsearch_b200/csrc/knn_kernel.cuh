@@ -1,0 +1,244 @@
+// Exact kNN over an HBM-resident float vector field (ExactVectorQuery semantics,
+// reference src/main/java/com/yelp/nrtsearch/server/query/vector/ExactVectorQuery.java:137-173;
+// score = VectorSimilarityFunction.compare(q, v) * boost, .../search/KnnUtils.java:62-64).
+//
+// Two stages per batch:
+//   A. candidate generation: tiled fp32 dot products of every (query, vector) pair, streamed in doc
+//      chunks; a per-query select keeps the best k' = 2k candidates by the fp32 score;
+//   B. exact re-score of the k' candidates with double accumulation (the oracle's arithmetic) and the
+//      Lucene score mapping in float, then the final (score desc, doc asc) top-k.
+// Stage A is the GEMM-shaped part (the tensor-core version replaces only that stage).
+#pragma once
+#include "common.cuh"
+#include "../../include/nrtgpu.h"
+
+namespace nrtgpu {
+
+constexpr int kKnnTile = 64;       // queries x docs per CTA tile
+constexpr int kKnnKStep = 16;
+constexpr int kKnnChunk = 32768;   // docs per streamed chunk
+constexpr int kKnnSelThreads = 256;
+constexpr int kKnnCandCap = 4096;
+
+// per-vector squared magnitude (double accumulate -> float)
+__global__ void knn_norm2_kernel(const float* __restrict__ v, int n, int dims, float* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* p = v + (size_t)warp * dims;
+  double s = 0.0;
+  for (int i = lane; i < dims; i += 32) { double x = p[i]; s += x * x; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[warp] = (float)s;
+}
+
+inline int knn_prepare_norms(const float* d_vec, int n, int dims, float* d_out) {
+  int threads = 256, warps_per_block = threads / 32;
+  knn_norm2_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads>>>(d_vec, n, dims, d_out);
+  NRT_CUDA_TRY(cudaGetLastError());
+  return NRTGPU_OK;
+}
+
+// approximate raw similarity used only to rank candidates (monotone in the final score):
+//   dot / cosine / mip: dot (cosine divides by |d|), l2: -(|q|^2 + |d|^2 - 2 dot)
+__global__ void __launch_bounds__(256) knn_dot_tile_kernel(const float* __restrict__ Q, const float* __restrict__ D,
+                                                           const float* __restrict__ dnorm2, int nq, int n_chunk,
+                                                           int dims, int sim, float* __restrict__ S /*[nq][chunk]*/,
+                                                           int ldS) {
+  __shared__ float sq[kKnnKStep][kKnnTile + 1];
+  __shared__ float sd[kKnnKStep][kKnnTile + 1];
+  const int tq = threadIdx.x / 16, td = threadIdx.x % 16;  // 16x16 threads, 4x4 outputs each
+  const int q0 = blockIdx.y * kKnnTile, d0 = blockIdx.x * kKnnTile;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < dims; k0 += kKnnKStep) {
+    for (int i = threadIdx.x; i < kKnnTile * kKnnKStep; i += 256) {
+      int r = i / kKnnKStep, c = i % kKnnKStep;
+      int k = k0 + c;
+      sq[c][r] = (q0 + r < nq && k < dims) ? Q[(size_t)(q0 + r) * dims + k] : 0.0f;
+      sd[c][r] = (d0 + r < n_chunk && k < dims) ? D[(size_t)(d0 + r) * dims + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kKnnKStep; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sq[k][tq * 4 + i]; b[i] = sd[k][td * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int q = q0 + tq * 4 + i;
+    if (q >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int d = d0 + td * 4 + j;
+      if (d >= n_chunk) continue;
+      float v = acc[i][j];
+      if (sim == NRTGPU_SIM_COSINE) v = v * rsqrtf(fmaxf(dnorm2[d], 1e-30f));
+      else if (sim == NRTGPU_SIM_L2) v = 2.0f * v - dnorm2[d];  // -(d2) + |q|^2 (constant per query)
+      S[(size_t)q * ldS + d] = v;
+    }
+  }
+}
+
+// per query: fold one chunk of approximate scores into the running best-k' candidate list
+struct KnnSelectLaunch {
+  const float* S; int ldS; int n_chunk; int chunk_base;  // ordinal of S[:,0]
+  const uint8_t* filter;   // per DOC 0/1 or NULL
+  const int32_t* vec_docs; // ord -> doc or NULL
+  int kprime; int nq;
+  uint64_t* cand;          // [nq][kprime] sorted desc keys (approx score, ord)
+  int32_t* cand_cnt;       // [nq]
+};
+
+__global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLaunch L) {
+  __shared__ uint64_t buf[kKnnCandCap];
+  __shared__ int count;
+  __shared__ unsigned long long theta;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  int have = L.cand_cnt[q];
+  for (int i = tid; i < have; i += kKnnSelThreads) buf[i] = L.cand[(size_t)q * L.kprime + i];
+  if (tid == 0) { count = have; theta = (have == L.kprime) ? L.cand[(size_t)q * L.kprime + L.kprime - 1] : 0ull; }
+  __syncthreads();
+  int ub = have;
+  auto compact = [&]() {
+    __syncthreads();
+    int n = count;
+    int m = next_pow2(n < 2 ? 2 : n);
+    for (int i = n + tid; i < m; i += kKnnSelThreads) buf[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(buf, m);
+    if (tid == 0) { int keep = n < L.kprime ? n : L.kprime; count = keep; if (keep == L.kprime) theta = buf[L.kprime - 1]; }
+    __syncthreads();
+  };
+  for (int i0 = 0; i0 < L.n_chunk; i0 += kKnnSelThreads) {
+    int i = i0 + tid;
+    bool is_cand = false; uint64_t key = 0;
+    if (i < L.n_chunk) {
+      int ord = L.chunk_base + i;
+      bool ok = true;
+      if (L.filter) { int doc = L.vec_docs ? L.vec_docs[ord] : ord; ok = L.filter[doc] != 0; }
+      if (ok) { key = make_key(L.S[(size_t)q * L.ldS + i], ord); is_cand = key > theta; }
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_cand) buf[base + __popc(bal & ((1u << lane) - 1))] = key;
+    }
+    ub += kKnnSelThreads;
+    if (ub > kKnnCandCap - kKnnSelThreads) {
+      __syncthreads();
+      if (count > kKnnCandCap - kKnnSelThreads) compact();
+      ub = count;
+    }
+  }
+  compact();
+  int keep = count;
+  for (int i = tid; i < keep; i += kKnnSelThreads) L.cand[(size_t)q * L.kprime + i] = buf[i];
+  if (tid == 0) L.cand_cnt[q] = keep;
+}
+
+// exact re-score (double accumulation, Lucene score mapping in float) + final top-k; one CTA per query
+struct KnnRescoreLaunch {
+  const float* Q; const float* D; int dims; int sim;
+  const uint64_t* cand; const int32_t* cand_cnt; int kprime;
+  const int32_t* vec_docs; int doc_base; const float* boosts; int k;
+  int32_t* out_docs; float* out_scores; int32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
+  __shared__ uint64_t keys[kKnnCandCap];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = L.cand_cnt[q];
+  const float* qv = L.Q + (size_t)q * L.dims;
+  const float boost = L.boosts ? L.boosts[q] : 1.0f;
+  for (int c = warp; c < n; c += 8) {
+    int ord = key_doc(L.cand[(size_t)q * L.kprime + c]);
+    const float* dv = L.D + (size_t)ord * L.dims;
+    double dot = 0, na = 0, nb = 0, d2 = 0;
+    for (int i = lane; i < L.dims; i += 32) {
+      double x = qv[i], y = dv[i];
+      dot += x * y; na += x * x; nb += y * y; d2 += (x - y) * (x - y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      dot += __shfl_xor_sync(0xffffffffu, dot, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+      nb += __shfl_xor_sync(0xffffffffu, nb, o);  d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if (lane == 0) {
+      // VectorSimilarityFunction.compare (reference VectorFieldDef.java:664-673 restates the mapping)
+      float s;
+      if (L.sim == NRTGPU_SIM_L2) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, (float)d2));
+      else if (L.sim == NRTGPU_SIM_DOT) { s = __fdiv_rn(__fadd_rn(1.0f, (float)dot), 2.0f); s = s > 0.f ? s : 0.f; }
+      else if (L.sim == NRTGPU_SIM_COSINE) { float cs = (float)(dot / sqrt(na * nb)); s = __fdiv_rn(__fadd_rn(1.0f, cs), 2.0f); s = s > 0.f ? s : 0.f; }
+      else { float t = (float)dot; s = t < 0.f ? __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(-1.0f, t))) : __fadd_rn(t, 1.0f); }
+      s = __fmul_rn(s, boost);
+      int doc = L.vec_docs ? L.vec_docs[ord] : ord;
+      keys[c] = make_key(s, doc);
+    }
+  }
+  __syncthreads();
+  int m = next_pow2(n < 2 ? 2 : n);
+  for (int i = n + tid; i < m; i += 256) keys[i] = 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(keys, m);
+  int keep = n < L.k ? n : L.k;
+  for (int i = tid; i < keep; i += 256) {
+    L.out_docs[(size_t)q * L.k + i] = key_doc(keys[i]) + L.doc_base;
+    L.out_scores[(size_t)q * L.k + i] = key_score(keys[i]);
+  }
+  if (tid == 0) L.out_counts[q] = keep;
+}
+
+struct CudaFreeGuard { void* p; ~CudaFreeGuard() { if (p) cudaFree(p); } };
+
+inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32_t* d_vec_docs, int n, int dims, int sim,
+                           int doc_base, int n_docs, const float* h_queries, int nq, int k, const float* h_boosts,
+                           const uint8_t* h_filter, cudaStream_t st, int32_t* out_docs, float* out_scores,
+                           int32_t* out_counts) {
+  int kprime = 2 * k < 64 ? 64 : 2 * k;
+  if (kprime > kKnnCandCap - kKnnSelThreads) kprime = kKnnCandCap - kKnnSelThreads;
+  float *dQ = nullptr, *dS = nullptr, *dB = nullptr, *dOS = nullptr; uint8_t* dF = nullptr;
+  uint64_t* dC = nullptr; int32_t *dCn = nullptr, *dOD = nullptr, *dOC = nullptr;
+  int chunk = n < kKnnChunk ? n : kKnnChunk;
+  NRT_CUDA_TRY(cudaMalloc((void**)&dQ, (size_t)nq * dims * sizeof(float))); CudaFreeGuard g1{dQ};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dS, (size_t)nq * chunk * sizeof(float))); CudaFreeGuard g2{dS};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dC, (size_t)nq * kprime * sizeof(uint64_t))); CudaFreeGuard g3{dC};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dCn, (size_t)nq * sizeof(int32_t))); CudaFreeGuard g4{dCn};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dOD, (size_t)nq * k * sizeof(int32_t))); CudaFreeGuard g5{dOD};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dOS, (size_t)nq * k * sizeof(float))); CudaFreeGuard g6{dOS};
+  NRT_CUDA_TRY(cudaMalloc((void**)&dOC, (size_t)nq * sizeof(int32_t))); CudaFreeGuard g7{dOC};
+  CudaFreeGuard g8{nullptr}, g9{nullptr};
+  if (h_boosts) { NRT_CUDA_TRY(cudaMalloc((void**)&dB, (size_t)nq * sizeof(float))); g8.p = dB;
+                  NRT_CUDA_TRY(cudaMemcpyAsync(dB, h_boosts, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st)); }
+  if (h_filter) { NRT_CUDA_TRY(cudaMalloc((void**)&dF, (size_t)n_docs)); g9.p = dF;
+                  NRT_CUDA_TRY(cudaMemcpyAsync(dF, h_filter, (size_t)n_docs, cudaMemcpyHostToDevice, st)); }
+  NRT_CUDA_TRY(cudaMemcpyAsync(dQ, h_queries, (size_t)nq * dims * sizeof(float), cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemsetAsync(dCn, 0, (size_t)nq * sizeof(int32_t), st));
+  for (int base = 0; base < n; base += chunk) {
+    int nc = n - base < chunk ? n - base : chunk;
+    dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
+    knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim, dS, chunk);
+    NRT_CUDA_TRY(cudaGetLastError());
+    KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.vec_docs = d_vec_docs;
+    S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
+    knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
+    NRT_CUDA_TRY(cudaGetLastError());
+  }
+  KnnRescoreLaunch R; R.Q = dQ; R.D = d_vec; R.dims = dims; R.sim = sim; R.cand = dC; R.cand_cnt = dCn; R.kprime = kprime;
+  R.vec_docs = d_vec_docs; R.doc_base = doc_base; R.boosts = dB; R.k = k; R.out_docs = dOD; R.out_scores = dOS; R.out_counts = dOC;
+  knn_rescore_kernel<<<nq, 256, 0, st>>>(R);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, dOD, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, dOS, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, dOC, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
+  return NRTGPU_OK;
+}
+
+}  // namespace nrtgpu

@@ -1,0 +1,542 @@
+// nrtgpu.cu -- C ABI (include/nrtgpu.h) of the B200 query-execution engine: context, HBM index image,
+// batch compilation, kernel launches. No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/nrtgpu.h"
+#include "bool_kernel.cuh"
+#include "knn_kernel.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace nrtgpu {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace nrtgpu
+using namespace nrtgpu;
+
+#define NRT_FAIL(code, msg) do { set_error(msg); return (code); } while (0)
+
+struct nrtgpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+};
+
+namespace {
+
+// ---- SmallFloat.byte4ToInt (Lucene) : norm byte -> field length, for the BM25 length table ----
+int64_t int4_to_long(int i) {
+  int64_t bits = i & 0x07;
+  int shift = (i >> 3) - 1;
+  return shift == -1 ? bits : ((bits | 0x08) << shift);
+}
+int32_t byte4_to_int(uint8_t b) {
+  const int kFree = 24;  // 255 - longToInt4(Integer.MAX_VALUE)
+  return b < kFree ? (int32_t)b : (int32_t)(kFree + int4_to_long((int)b - kFree));
+}
+// BM25Similarity.scorer(): cache[i] = 1f / (k1 * ((1 - b) + b * LENGTH_TABLE[i] / avgdl)), float ops
+void bm25_cache(float k1, float b, float avgdl, float* cache) {
+  for (int i = 0; i < 256; ++i) {
+    volatile float t = b * (float)byte4_to_int((uint8_t)i);
+    t = t / avgdl;
+    t = (1.0f - b) + t;
+    t = k1 * t;
+    cache[i] = 1.0f / t;
+  }
+}
+float bm25_idf(int64_t df, int64_t doc_count) {
+  return (float)std::log(1.0 + ((double)doc_count - (double)df + 0.5) / ((double)df + 0.5));
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    if (count == 0) return NRTGPU_OK;
+    NRT_CUDA_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+    return NRTGPU_OK;
+  }
+  int upload(const T* h, size_t count) {
+    int rc = alloc(count);
+    if (rc) return rc;
+    if (count) NRT_CUDA_TRY(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    return NRTGPU_OK;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct nrtgpu_index {
+  nrtgpu_ctx* ctx = nullptr;
+  int32_t n_docs = 0, doc_base = 0, n_terms = 0, n_fields = 0, n_columns = 0;
+  // host-side dictionary
+  std::vector<int64_t> term_off;
+  std::vector<int32_t> term_field;
+  std::vector<int64_t> term_df;
+  std::vector<int64_t> field_doc_count, field_sum_ttf;
+  std::vector<uint8_t> field_has_norms;
+  // device image
+  DevBuf<int32_t> post_docs;
+  DevBuf<uint8_t> post_f8;
+  DevBuf<int64_t> exc_pos;
+  DevBuf<int32_t> exc_freq;
+  std::vector<std::unique_ptr<DevBuf<uint8_t>>> norms;
+  DevBuf<const uint8_t*> norms_ptrs;
+  DevBuf<float> caches;
+  std::vector<std::unique_ptr<DevBuf<int64_t>>> col64;
+  std::vector<std::unique_ptr<DevBuf<int32_t>>> col32;
+  std::vector<std::unique_ptr<DevBuf<uint8_t>>> col_has;
+  DevBuf<const int64_t*> col64_ptrs;
+  DevBuf<const int32_t*> col32_ptrs;
+  DevBuf<const uint8_t*> col_has_ptrs;
+  DevBuf<uint32_t> live_bits;
+  // vectors
+  int32_t vec_dims = 0, vec_sim = 0, vec_count = 0;
+  DevBuf<float> vectors;
+  DevBuf<float> vec_norm2;  // per-vector squared magnitude (double-accumulated, stored float) for cosine
+  DevBuf<int32_t> vec_docs;
+  int64_t device_bytes = 0;
+
+  DevIndexView view() const {
+    DevIndexView v;
+    v.n_docs = n_docs; v.doc_base = doc_base;
+    v.post_docs = post_docs.p; v.post_f8 = post_f8.p;
+    v.exc_pos = exc_pos.p; v.exc_freq = exc_freq.p; v.n_exc = (int32_t)exc_pos.n;
+    v.norms = norms_ptrs.p; v.caches = caches.p;
+    v.col64 = col64_ptrs.p; v.col32 = col32_ptrs.p; v.col_has = col_has_ptrs.p;
+    v.live_bits = live_bits.p;
+    return v;
+  }
+};
+
+struct nrtgpu_batch {
+  nrtgpu_index* ix = nullptr;
+  int32_t nq = 0, top_k = 0, n_slices = 0, n_work = 0;
+  bool wide_slots = false;
+  bool exhaustive = true;
+  int64_t alg_postings = 0;
+  DevBuf<DevClause> clauses;
+  DevBuf<DevQuery> queries;
+  DevBuf<int32_t> work_query, work_slice;
+  DevBuf<uint64_t> theta;
+  DevBuf<unsigned long long> total_hits;
+  DevBuf<uint64_t> slice_keys;
+  DevBuf<int32_t> slice_cnt;
+  DevBuf<int32_t> out_docs;
+  DevBuf<float> out_scores;
+  DevBuf<int32_t> out_counts;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  bool ran = false;
+  ~nrtgpu_batch() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+};
+
+extern "C" {
+
+const char* nrtgpu_last_error(void) { return g_last_error.c_str(); }
+int nrtgpu_version(void) { return 1; }
+
+int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
+  if (!out) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_init: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    NRT_FAIL(NRTGPU_ERR_CUDA, std::string("nrtgpu_init: no CUDA device (") + cudaGetErrorString(e) +
+                                  "); this engine has no CPU fallback");
+  if (device_id < 0 || device_id >= n) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_init: bad device id");
+  NRT_CUDA_TRY(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  NRT_CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major < 10) NRT_FAIL(NRTGPU_ERR_CUDA, "nrtgpu_init: device is not sm_100 class (kernels are built for sm_100a only)");
+  auto* c = new nrtgpu_ctx;
+  c->device = device_id;
+  c->sm_count = prop.multiProcessorCount;
+  NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(BoolSmem<uint32_t>)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(BoolSmem<uint64_t>)));
+  *out = c;
+  return NRTGPU_OK;
+}
+
+void nrtgpu_shutdown(nrtgpu_ctx* ctx) { delete ctx; }
+
+int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index** out) {
+  if (!ctx || !d || !out) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL argument");
+  if (d->n_docs < 0 || d->n_terms < 0 || d->n_fields < 0 || d->n_columns < 0)
+    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: negative size");
+  if (d->n_terms > 0 && (!d->term_off || d->n_fields < 1 || !d->field_doc_count || !d->field_sum_ttf))
+    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: terms need term_off and field statistics");
+  NRT_CUDA_TRY(cudaSetDevice(ctx->device));
+  std::unique_ptr<nrtgpu_index> ix(new nrtgpu_index);
+  ix->ctx = ctx;
+  ix->n_docs = d->n_docs; ix->doc_base = d->doc_base; ix->n_terms = d->n_terms;
+  ix->n_fields = d->n_fields; ix->n_columns = d->n_columns;
+  int rc;
+  const int64_t P = d->n_terms ? d->term_off[d->n_terms] : 0;
+  ix->term_off.assign(d->term_off, d->term_off + (d->n_terms ? d->n_terms + 1 : 0));
+  ix->term_field.resize(d->n_terms);
+  ix->term_df.resize(d->n_terms);
+  for (int t = 0; t < d->n_terms; ++t) {
+    int f = d->term_field ? d->term_field[t] : 0;
+    if (f < 0 || f >= d->n_fields) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: term_field out of range");
+    int64_t len = d->term_off[t + 1] - d->term_off[t];
+    if (len < 0 || len > INT32_MAX) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: bad term_off");
+    ix->term_field[t] = f;
+    ix->term_df[t] = d->term_df ? d->term_df[t] : len;
+  }
+  ix->field_doc_count.assign(d->field_doc_count, d->field_doc_count + d->n_fields);
+  ix->field_sum_ttf.assign(d->field_sum_ttf, d->field_sum_ttf + d->n_fields);
+  // postings
+  if ((rc = ix->post_docs.upload(d->post_docs, (size_t)P))) return rc;
+  {
+    std::vector<uint8_t> f8((size_t)P);
+    std::vector<int64_t> epos; std::vector<int32_t> efreq;
+    for (int64_t p = 0; p < P; ++p) {
+      int32_t f = d->post_freqs[p];
+      if (f < 1) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: term frequency < 1");
+      if (f >= 255) { f8[(size_t)p] = 255; epos.push_back(p); efreq.push_back(f); } else f8[(size_t)p] = (uint8_t)f;
+    }
+    if ((rc = ix->post_f8.upload(f8.data(), (size_t)P))) return rc;
+    if ((rc = ix->exc_pos.upload(epos.data(), epos.size()))) return rc;
+    if ((rc = ix->exc_freq.upload(efreq.data(), efreq.size()))) return rc;
+  }
+  // norms + BM25 caches
+  {
+    std::vector<const uint8_t*> ptrs((size_t)d->n_fields, nullptr);
+    std::vector<float> caches((size_t)d->n_fields * 256);
+    ix->field_has_norms.resize(d->n_fields);
+    for (int f = 0; f < d->n_fields; ++f) {
+      ix->norms.emplace_back(new DevBuf<uint8_t>);
+      const uint8_t* h = d->norms ? d->norms[f] : nullptr;
+      ix->field_has_norms[f] = h != nullptr;
+      if (h) { if ((rc = ix->norms.back()->upload(h, (size_t)d->n_docs))) return rc; ptrs[f] = ix->norms.back()->p; }
+      float k1 = d->field_k1 ? d->field_k1[f] : 1.2f, b = d->field_b ? d->field_b[f] : 0.75f;
+      int64_t dc = d->field_doc_count[f];
+      float avgdl = dc > 0 ? (float)((double)d->field_sum_ttf[f] / (double)dc) : 1.0f;
+      bm25_cache(k1, b, avgdl, &caches[(size_t)f * 256]);
+    }
+    if ((rc = ix->norms_ptrs.upload(ptrs.data(), ptrs.size()))) return rc;
+    if ((rc = ix->caches.upload(caches.data(), caches.size()))) return rc;
+  }
+  // numeric doc-value columns (int32 when the value range allows: 4 B/doc gathers)
+  {
+    std::vector<const int64_t*> p64((size_t)d->n_columns, nullptr);
+    std::vector<const int32_t*> p32((size_t)d->n_columns, nullptr);
+    std::vector<const uint8_t*> ph((size_t)d->n_columns, nullptr);
+    for (int c = 0; c < d->n_columns; ++c) {
+      ix->col64.emplace_back(new DevBuf<int64_t>);
+      ix->col32.emplace_back(new DevBuf<int32_t>);
+      ix->col_has.emplace_back(new DevBuf<uint8_t>);
+      const int64_t* h = d->columns[c];
+      if (!h) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL column");
+      bool fits = true;
+      for (int32_t i = 0; i < d->n_docs; ++i) if (h[i] < INT32_MIN || h[i] > INT32_MAX) { fits = false; break; }
+      if (fits) {
+        std::vector<int32_t> tmp((size_t)d->n_docs);
+        for (int32_t i = 0; i < d->n_docs; ++i) tmp[i] = (int32_t)h[i];
+        if ((rc = ix->col32.back()->upload(tmp.data(), tmp.size()))) return rc;
+        p32[c] = ix->col32.back()->p;
+      } else {
+        if ((rc = ix->col64.back()->upload(h, (size_t)d->n_docs))) return rc;
+        p64[c] = ix->col64.back()->p;
+      }
+      const uint8_t* hh = d->column_has ? d->column_has[c] : nullptr;
+      if (hh) { if ((rc = ix->col_has.back()->upload(hh, (size_t)d->n_docs))) return rc; ph[c] = ix->col_has.back()->p; }
+    }
+    if ((rc = ix->col64_ptrs.upload(p64.data(), p64.size()))) return rc;
+    if ((rc = ix->col32_ptrs.upload(p32.data(), p32.size()))) return rc;
+    if ((rc = ix->col_has_ptrs.upload(ph.data(), ph.size()))) return rc;
+  }
+  if (d->live_docs) {
+    std::vector<uint32_t> bits(((size_t)d->n_docs + 31) / 32, 0u);
+    for (int32_t i = 0; i < d->n_docs; ++i) if (d->live_docs[i]) bits[i >> 5] |= 1u << (i & 31);
+    if ((rc = ix->live_bits.upload(bits.data(), bits.size()))) return rc;
+  }
+  // vectors
+  if (d->vec_dims > 0 && d->vec_count > 0) {
+    if (!d->vectors) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL vectors");
+    if (d->vec_dims > 4096) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: vector dims > 4096 (VectorFieldDef.java:96)");
+    ix->vec_dims = d->vec_dims; ix->vec_sim = d->vec_similarity; ix->vec_count = d->vec_count;
+    if ((rc = ix->vectors.upload(d->vectors, (size_t)d->vec_count * d->vec_dims))) return rc;
+    if (d->vec_docs) { if ((rc = ix->vec_docs.upload(d->vec_docs, (size_t)d->vec_count))) return rc; }
+    if ((rc = ix->vec_norm2.alloc((size_t)d->vec_count))) return rc;
+    if ((rc = knn_prepare_norms(ix->vectors.p, ix->vec_count, ix->vec_dims, ix->vec_norm2.p))) return rc;
+  }
+  ix->device_bytes = (int64_t)(ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
+                               ix->caches.bytes() + ix->live_bits.bytes() + ix->vectors.bytes() + ix->vec_norm2.bytes() +
+                               ix->vec_docs.bytes());
+  for (auto& b : ix->norms) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->col64) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->col32) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->col_has) ix->device_bytes += (int64_t)b->bytes();
+  NRT_CUDA_TRY(cudaDeviceSynchronize());
+  *out = ix.release();
+  return NRTGPU_OK;
+}
+
+int nrtgpu_index_close(nrtgpu_index* ix) {
+  if (!ix) return NRTGPU_OK;
+  cudaSetDevice(ix->ctx->device);
+  delete ix;
+  return NRTGPU_OK;
+}
+
+int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix) { return ix ? ix->device_bytes : 0; }
+
+// ---- batch compilation: flat BooleanQuery -> DevQuery/DevClause, driver selection, work list ----
+int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                         int32_t total_hits_threshold, int32_t flags, nrtgpu_batch** out) {
+  if (!ix || !queries || !out || (n_clauses > 0 && !clauses)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
+  if (nq <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: nq must be > 0");
+  // LazyQueueTopScoreDocCollectorManager.java:93-96: numHits must be > 0
+  if (top_k <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "numHits must be > 0; please use TotalHitCountCollectorManager if you just need the total hit count");
+  if (top_k > kMaxTopK) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_batch_prepare: top_k > 1024 is not on the GPU path");
+  if (total_hits_threshold < 0) NRT_FAIL(NRTGPU_ERR_INVALID, "totalHitsThreshold must be >= 0");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  std::unique_ptr<nrtgpu_batch> b(new nrtgpu_batch);
+  b->ix = ix; b->nq = nq; b->top_k = top_k;
+  b->exhaustive = true;  // TOP_SCORES is served by the exact path too (counts stay EQUAL_TO)
+  (void)flags;
+  const int64_t slice_docs = (int64_t)kSliceWindows * kWindowDocs;
+  b->n_slices = (int32_t)std::max<int64_t>(1, ((int64_t)ix->n_docs + slice_docs - 1) / slice_docs);
+  std::vector<DevClause> dc;
+  std::vector<DevQuery> dq((size_t)nq);
+  dc.reserve((size_t)n_clauses);
+  int max_terms = 0;
+  for (int qi = 0; qi < nq; ++qi) {
+    const nrtgpu_query& q = queries[qi];
+    if (q.clause_begin < 0 || q.clause_end < q.clause_begin || q.clause_end > n_clauses)
+      NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: clause range out of bounds");
+    if (q.min_should_match < 0) NRT_FAIL(NRTGPU_ERR_INVALID, "minimumNumberShouldMatch must be >= 0");
+    int ncl = q.clause_end - q.clause_begin;
+    if (ncl > kMaxClauses) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_batch_prepare: more than 16 clauses in one BooleanQuery");
+    DevQuery& o = dq[(size_t)qi];
+    std::memset(&o, 0, sizeof(o));
+    o.clause_begin = (int32_t)dc.size(); o.n_clauses = ncl; o.msm = q.min_should_match;
+    int n_term = 0, n_req = 0, n_should = 0, n_req_term = 0, n_req_nonterm = 0, n_should_nonterm = 0;
+    int best_req_slot = -1; int32_t best_req_n = INT32_MAX;
+    uint32_t should_term_mask = 0;
+    for (int ci = q.clause_begin; ci < q.clause_end; ++ci) {
+      const nrtgpu_clause& c = clauses[ci];
+      if (c.occur < NRTGPU_SHOULD || c.occur > NRTGPU_MUST_NOT) NRT_FAIL(NRTGPU_ERR_INVALID, "bad occur");
+      if (c.boost < 0.0f) NRT_FAIL(NRTGPU_ERR_INVALID, "Boost must be a positive number");  // QueryNodeMapper.java:127
+      DevClause x; std::memset(&x, 0, sizeof(x));
+      x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.lo = c.lo; x.hi = c.hi;
+      x.scoring = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_SHOULD) ? 1 : 0;
+      bool required = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER);
+      if (c.kind == NRTGPU_TERM) {
+        if (c.id < 0 || c.id >= ix->n_terms) NRT_FAIL(NRTGPU_ERR_INVALID, "term id out of range");
+        if (n_term >= kMaxTermSlots) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_batch_prepare: more than 8 term clauses in one BooleanQuery");
+        int f = ix->term_field[c.id];
+        x.post_base = ix->term_off[c.id];
+        x.n_post = (int32_t)(ix->term_off[c.id + 1] - ix->term_off[c.id]);
+        x.slot = n_term; x.field = f;
+        int64_t df = ix->term_df[c.id];
+        // BM25Scorer: weight = boost * idf
+        x.weight = c.boost * bm25_idf(df > 0 ? df : 1, ix->field_doc_count[f]);
+        if (required) { o.req_term_mask |= 1u << n_term; ++n_req_term; if (x.n_post < best_req_n) { best_req_n = x.n_post; best_req_slot = n_term; } }
+        if (c.occur == NRTGPU_MUST_NOT) o.not_term_mask |= 1u << n_term;
+        if (c.occur == NRTGPU_SHOULD) should_term_mask |= 1u << n_term;
+        if (x.scoring) b->alg_postings += x.n_post; else b->alg_postings += x.n_post;
+        ++n_term;
+      } else if (c.kind == NRTGPU_RANGE_I64) {
+        if (c.id < 0 || c.id >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "column id out of range");
+        x.col = c.id; x.weight = c.boost;  // constant-score query: score = boost
+        o.has_nonterm = 1;
+        if (required) ++n_req_nonterm;
+        if (c.occur == NRTGPU_SHOULD) ++n_should_nonterm;
+      } else if (c.kind == NRTGPU_MATCH_ALL) {
+        x.weight = c.boost;
+        o.has_nonterm = 1;
+        if (required) ++n_req_nonterm;
+        if (c.occur == NRTGPU_SHOULD) ++n_should_nonterm;
+      } else NRT_FAIL(NRTGPU_ERR_INVALID, "bad clause kind");
+      if (required) ++n_req;
+      if (c.occur == NRTGPU_SHOULD) ++n_should;
+      dc.push_back(x);
+    }
+    o.n_term = n_term; o.n_req = n_req;
+    o.need_should = q.min_should_match > 0 ? q.min_should_match : (n_req == 0 ? 1 : 0);
+    max_terms = std::max(max_terms, n_term);
+    if (q.min_should_match > n_should || (n_req == 0 && n_should == 0)) o.empty = 1;
+    // driver selection
+    if (n_req_term > 0) o.driver_mask = 1u << best_req_slot;           // rarest required posting list leads
+    else if (n_req_nonterm > 0 || n_should_nonterm > 0) o.dense_driver = 1;  // no posting list can lead
+    else o.driver_mask = should_term_mask;                             // pure disjunction: every SHOULD list drives
+    uint32_t all_terms = n_term >= 32 ? 0xffffffffu : ((1u << n_term) - 1u);
+    o.has_non_driver = (!o.dense_driver && (all_terms & ~o.driver_mask)) ? 1 : 0;
+    if (q.has_after) {
+      o.has_after = 1;
+      int64_t local = (int64_t)q.after_doc - ix->doc_base;
+      uint32_t ord = float_to_ordered(q.after_score);
+      if (local < 0) o.after_key = ((uint64_t)ord + 1ull) << 32;             // every doc here follows afterDoc
+      else if (local >= ix->n_docs) o.after_key = make_key(q.after_score, INT32_MAX);  // every doc here precedes it
+      else o.after_key = make_key(q.after_score, (int32_t)local);
+    }
+  }
+  b->wide_slots = max_terms > 4;
+  // work list, slice-major so that concurrently resident CTAs share postings of the same doc range in L2;
+  // inside a slice, longer queries first
+  std::vector<int32_t> order;
+  std::vector<int64_t> cost((size_t)nq, 0);
+  for (int qi = 0; qi < nq; ++qi) {
+    if (dq[qi].empty) continue;
+    order.push_back(qi);
+    for (int c = 0; c < dq[qi].n_clauses; ++c) cost[qi] += dc[(size_t)dq[qi].clause_begin + c].n_post;
+    if (dq[qi].dense_driver) cost[qi] += ix->n_docs;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+  std::vector<int32_t> wq, ws;
+  for (int s = 0; s < b->n_slices; ++s)
+    for (int qi : order) { wq.push_back(qi); ws.push_back(s); }
+  b->n_work = (int32_t)wq.size();
+  int rc;
+  if ((rc = b->clauses.upload(dc.data(), dc.size()))) return rc;
+  if ((rc = b->queries.upload(dq.data(), dq.size()))) return rc;
+  if ((rc = b->work_query.upload(wq.data(), wq.size()))) return rc;
+  if ((rc = b->work_slice.upload(ws.data(), ws.size()))) return rc;
+  if ((rc = b->theta.alloc((size_t)nq))) return rc;
+  if ((rc = b->total_hits.alloc((size_t)nq))) return rc;
+  if ((rc = b->slice_keys.alloc((size_t)nq * b->n_slices * top_k))) return rc;
+  if ((rc = b->slice_cnt.alloc((size_t)nq * b->n_slices))) return rc;
+  if ((rc = b->out_docs.alloc((size_t)nq * top_k))) return rc;
+  if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
+  if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
+  for (auto& e : b->ev) NRT_CUDA_TRY(cudaEventCreate(&e));
+  *out = b.release();
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_run: NULL batch");
+  cudaStream_t st = (cudaStream_t)stream_;
+  NRT_CUDA_TRY(cudaSetDevice(b->ix->ctx->device));
+  NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
+  NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
+  NRT_CUDA_TRY(cudaMemsetAsync(b->slice_cnt.p, 0, b->slice_cnt.bytes(), st));
+  NRT_CUDA_TRY(cudaEventRecord(b->ev[0], st));
+  if (b->n_work > 0) {
+    BoolLaunch L;
+    L.ix = b->ix->view();
+    L.clauses = b->clauses.p; L.queries = b->queries.p;
+    L.work_query = b->work_query.p; L.work_slice = b->work_slice.p;
+    L.n_work = b->n_work; L.n_slices = b->n_slices; L.top_k = b->top_k;
+    L.theta = b->theta.p; L.total_hits = b->total_hits.p;
+    L.slice_keys = b->slice_keys.p; L.slice_cnt = b->slice_cnt.p;
+    if (!b->wide_slots)
+      bool_window_kernel<uint32_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint32_t>), st>>>(L);
+    else
+      bool_window_kernel<uint64_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint64_t>), st>>>(L);
+    NRT_CUDA_TRY(cudaGetLastError());
+  }
+  NRT_CUDA_TRY(cudaEventRecord(b->ev[1], st));
+  MergeLaunch M;
+  M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
+  M.n_lists = b->n_slices; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;
+  M.out_docs = b->out_docs.p; M.out_scores = b->out_scores.p; M.out_counts = b->out_counts.p;
+  merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaEventRecord(b->ev[2], st));
+  b->ran = true;
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores,
+                       int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation) {
+  if (!b || !b->ran) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_fetch: batch has not run");
+  cudaStream_t st = (cudaStream_t)stream_;
+  size_t n = (size_t)b->nq * b->top_k;
+  if (out_docs) NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, b->out_docs.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out_scores) NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, b->out_scores.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (out_counts) NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, b->out_counts.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out_total_hits) NRT_CUDA_TRY(cudaMemcpyAsync(out_total_hits, b->total_hits.p, (size_t)b->nq * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
+  if (out_relation) std::memset(out_relation, b->exhaustive ? 0 : 1, (size_t)b->nq);
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  if (d_docs) *d_docs = b->out_docs.p;
+  if (d_scores) *d_scores = b->out_scores.p;
+  if (d_counts) *d_counts = b->out_counts.p;
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run, int64_t* work_items) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  if (alg_postings) *alg_postings = b->alg_postings;
+  if (launches_per_run) *launches_per_run = (b->n_work > 0 ? 1 : 0) + 1;
+  if (work_items) *work_items = b->n_work;
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_stage_ms(nrtgpu_batch* b, int32_t stage, float* ms) {
+  if (!b || !ms || stage < 0 || stage > 1 || !b->ran) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_stage_ms: bad argument");
+  NRT_CUDA_TRY(cudaEventElapsedTime(ms, b->ev[stage], b->ev[stage + 1]));
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_free(nrtgpu_batch* b) {
+  if (b) { cudaSetDevice(b->ix->ctx->device); delete b; }
+  return NRTGPU_OK;
+}
+
+int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                       const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                       int32_t total_hits_threshold, int32_t flags, void* stream, int32_t* out_docs,
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
+                       uint8_t* out_relation) {
+  nrtgpu_batch* b = nullptr;
+  int rc = nrtgpu_batch_prepare(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, &b);
+  if (rc) return rc;
+  rc = nrtgpu_batch_run(b, stream);
+  if (!rc) rc = nrtgpu_batch_fetch(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation);
+  nrtgpu_batch_free(b);
+  return rc;
+}
+
+int nrtgpu_merge_topk_device(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k,
+                             const int32_t* d_docs, const float* d_scores, const int32_t* d_counts,
+                             int32_t* d_out_docs, float* d_out_scores, int32_t* d_out_counts, void* stream) {
+  if (!ctx || n_lists <= 0 || nq <= 0 || top_k <= 0 || top_k > kMaxTopK) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_merge_topk_device: bad argument");
+  NRT_CUDA_TRY(cudaSetDevice(ctx->device));
+  MergePairsLaunch M;
+  M.docs = d_docs; M.scores = d_scores; M.counts = d_counts; M.n_lists = n_lists; M.top_k = top_k; M.nq = nq;
+  M.out_docs = d_out_docs; M.out_scores = d_out_scores; M.out_counts = d_out_counts;
+  merge_pairs_kernel<<<nq, kMergeThreads, 0, (cudaStream_t)stream>>>(M);
+  NRT_CUDA_TRY(cudaGetLastError());
+  return NRTGPU_OK;
+}
+
+int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, const float* boosts,
+                      const uint8_t* filter, void* stream, int32_t* out_docs, float* out_scores,
+                      int32_t* out_counts) {
+  if (!ix || !queries || !out_docs || !out_scores || !out_counts) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn: NULL argument");
+  if (ix->vec_dims <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn: index has no vector field");
+  if (k <= 0 || k > kMaxTopK) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn: k out of range");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
+                         ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
+                         out_scores, out_counts);
+}
+
+int nrtgpu_blend_rrf(nrtgpu_ctx*, int32_t, int32_t, int32_t, const int32_t*, const int32_t*, const float*, int32_t,
+                     int32_t, int32_t*, float*, int32_t*, int32_t*) {
+  NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_blend_rrf: not built yet");
+}
+int nrtgpu_rescore_combine(nrtgpu_ctx*, int32_t, int32_t, const int32_t*, int32_t*, float*, const uint8_t*,
+                           const float*, double, double) {
+  NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_rescore_combine: not built yet");
+}
+
+}  // extern "C"

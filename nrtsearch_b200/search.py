@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's query-execution interface for the hot path.
+
+Names and argument meaning follow the Lucene/nrtsearch API at the three call sites the engine replaces
+ so parity tests read like the reference's own:
+
+  IndexSearcher.search(Query, CollectorManager)   src/main/java/com/yelp/nrtsearch/server/handler/SearchHandler.java:1412
+  BooleanQuery / TermQuery / RangeQuery / BoostQuery / MatchAllDocsQuery
+                                                  src/main/java/com/yelp/nrtsearch/server/query/QueryNodeMapper.java:257-283
+  RelevanceCollector (numHitsToCollect, totalHitsThreshold, searchAfter)
+                                                  src/main/java/com/yelp/nrtsearch/server/search/collectors/RelevanceCollector.java:42-69
+  KnnQuery / ExactVectorQuery                     src/main/java/com/yelp/nrtsearch/server/search/KnnUtils.java:47-66
+
+All execution happens in libnrtgpu.so (CUDA); this module only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from ._native import Clause, NrtGpuError, NrtGpuUnsupported, Query as CQuery, check
+from .index import HostShard, PinnedDesc
+
+TOTAL_HITS_THRESHOLD = 1000  # SearchRequestProcessor.TOTAL_HITS_THRESHOLD (:102)
+INT_MAX = 2**31 - 1
+
+
+class Occur(enum.IntEnum):
+    SHOULD = 0
+    MUST = 1
+    FILTER = 2
+    MUST_NOT = 3
+
+
+@dataclass(frozen=True)
+class TermQuery:
+    term: int  # the adaptor's dense (field, term) id
+
+
+@dataclass(frozen=True)
+class RangeQuery:
+    """IndexOrDocValuesQuery(PointRangeQuery, SortedNumericDocValuesRangeQuery): inclusive bounds in the
+    sortable-long domain (IntFieldDef.getRangeQuery :124-158 folds exclusive bounds with +-1)."""
+    column: int
+    lower: int = -(2**63)
+    upper: int = 2**63 - 1
+
+
+@dataclass(frozen=True)
+class MatchAllDocsQuery:
+    pass
+
+
+@dataclass(frozen=True)
+class BoostQuery:
+    query: object
+    boost: float
+
+
+@dataclass(frozen=True)
+class BooleanClause:
+    query: object
+    occur: Occur
+
+
+@dataclass
+class BooleanQuery:
+    clauses: List[BooleanClause] = field(default_factory=list)
+    minimum_number_should_match: int = 0
+
+    def add(self, query, occur: Occur) -> "BooleanQuery":
+        self.clauses.append(BooleanClause(query, Occur(occur)))
+        return self
+
+
+def boolean_query_from_proto(clauses: Sequence[Tuple[object, Occur]], minimum_number_should_match: int = 0) -> BooleanQuery:
+    """QueryNodeMapper.getBooleanQuery (:257-283): empty => MatchAllDocs MUST; all MUST_NOT => add MatchAllDocs FILTER."""
+    bq = BooleanQuery(minimum_number_should_match=minimum_number_should_match)
+    if not clauses:
+        return bq.add(MatchAllDocsQuery(), Occur.MUST)
+    all_must_not = True
+    for q, occ in clauses:
+        bq.add(q, occ)
+        if occ != Occur.MUST_NOT:
+            all_must_not = False
+    if all_must_not:
+        bq.add(MatchAllDocsQuery(), Occur.FILTER)
+    return bq
+
+
+@dataclass
+class ScoreDoc:
+    doc: int
+    score: float
+
+
+class Relation(enum.IntEnum):
+    EQUAL_TO = 0
+    GREATER_THAN_OR_EQUAL_TO = 1
+
+
+@dataclass
+class TotalHits:
+    value: int
+    relation: Relation
+
+
+@dataclass
+class TopDocs:
+    total_hits: TotalHits
+    score_docs: List[ScoreDoc]
+
+
+@dataclass
+class RelevanceCollector:
+    """DocCollector config (CollectorCreatorContext.java:36-53): numHitsToCollect, totalHitsThreshold, searchAfter."""
+    num_hits_to_collect: int
+    total_hits_threshold: int = TOTAL_HITS_THRESHOLD
+    search_after: Optional[ScoreDoc] = None
+
+
+def _f32(x: float) -> np.float32:
+    return np.float32(x)
+
+
+def _flatten(q, boost: np.float32, out: list, occur: Occur) -> None:
+    """One clause of the flat BooleanQuery; BoostQuery boosts multiply outermost-first in float
+    (BoostQuery.createWeight passes boost * this.boost down)."""
+    while isinstance(q, BoostQuery):
+        if q.boost < 0:
+            raise ValueError("Boost must be a positive number")  # QueryNodeMapper.java:127
+        boost = _f32(boost * _f32(q.boost))
+        q = q.query
+    if isinstance(q, TermQuery):
+        out.append((int(occur), 0, int(q.term), float(boost), 0, 0))
+    elif isinstance(q, RangeQuery):
+        out.append((int(occur), 1, int(q.column), float(boost), int(q.lower), int(q.upper)))
+    elif isinstance(q, MatchAllDocsQuery):
+        out.append((int(occur), 2, 0, float(boost), 0, 0))
+    else:
+        raise NrtGpuUnsupported(3, f"query node {type(q).__name__} is outside the GPU path")
+
+
+def compile_queries(queries: Sequence[object], search_after: Optional[Sequence[Optional[ScoreDoc]]] = None):
+    """Query trees -> (Clause[], Query[]) for nrtgpu_search_bool. A bare leaf is a single MUST clause
+    (Lucene rewrites a one-clause BooleanQuery to its clause; scores are identical)."""
+    flat, qs = [], []
+    for i, q in enumerate(queries):
+        boost = _f32(1.0)
+        while isinstance(q, BoostQuery):
+            if q.boost < 0:
+                raise ValueError("Boost must be a positive number")
+            boost = _f32(boost * _f32(q.boost))
+            q = q.query
+        begin = len(flat)
+        msm = 0
+        if isinstance(q, BooleanQuery):
+            msm = q.minimum_number_should_match
+            for cl in q.clauses:
+                if isinstance(cl.query, BooleanQuery):
+                    raise NrtGpuUnsupported(3, "nested BooleanQuery is outside the GPU path")
+                _flatten(cl.query, boost, flat, cl.occur)
+        else:
+            _flatten(q, boost, flat, Occur.MUST)
+        after = search_after[i] if search_after is not None else None
+        qs.append((begin, len(flat), msm, 1 if after is not None else 0,
+                   after.doc if after is not None else 0, after.score if after is not None else 0.0))
+    carr = (Clause * max(len(flat), 1))()
+    for i, (occ, kind, id_, b, lo, hi) in enumerate(flat):
+        carr[i] = Clause(occ, kind, id_, b, lo, hi)
+    qarr = (CQuery * max(len(qs), 1))()
+    for i, t in enumerate(qs):
+        qarr[i] = CQuery(*t)
+    return carr, len(flat), qarr, len(qs)
+
+
+class GpuContext:
+    def __init__(self, device: int = 0):
+        self._lib = _native.gpu_lib()
+        h = C.c_void_p()
+        check(self._lib.nrtgpu_init(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self._lib.nrtgpu_shutdown(self.handle)
+            self.handle = None
+
+
+class GpuIndex:
+    """Device image of one shard at one reader version (ShardSearcherFactory.newSearcher hook)."""
+
+    def __init__(self, ctx: GpuContext, shard: HostShard):
+        self._lib = _native.gpu_lib()
+        self.ctx = ctx
+        pinned = PinnedDesc(shard)
+        h = C.c_void_p()
+        check(self._lib.nrtgpu_index_build(ctx.handle, C.byref(pinned.desc), C.byref(h)))
+        self.handle = h
+        self.n_docs, self.doc_base = shard.n_docs, shard.doc_base
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.nrtgpu_index_device_bytes(self.handle))
+
+    def close(self):
+        if self.handle:
+            self._lib.nrtgpu_index_close(self.handle)
+            self.handle = None
+
+
+@dataclass
+class BatchResult:
+    docs: np.ndarray      # int32 [nq, k]
+    scores: np.ndarray    # float32 [nq, k]
+    counts: np.ndarray    # int32 [nq]
+    total_hits: np.ndarray  # int64 [nq]
+    relation: np.ndarray  # uint8 [nq]
+
+    def top_docs(self, i: int) -> TopDocs:
+        n = int(self.counts[i])
+        return TopDocs(TotalHits(int(self.total_hits[i]), Relation(int(self.relation[i]))),
+                       [ScoreDoc(int(d), float(s)) for d, s in zip(self.docs[i, :n], self.scores[i, :n])])
+
+
+class PreparedBatch:
+    """nrtgpu_batch: compiled batch resident on the device (launch many times, inputs stay in HBM)."""
+
+    def __init__(self, index: GpuIndex, carr, ncl, qarr, nq, top_k, threshold, flags=0):
+        self._lib = _native.gpu_lib()
+        self.index, self.nq, self.top_k = index, nq, top_k
+        h = C.c_void_p()
+        check(self._lib.nrtgpu_batch_prepare(index.handle, carr, ncl, qarr, nq, top_k, threshold, flags, C.byref(h)))
+        self.handle = h
+
+    def run(self, stream: int = 0):
+        check(self._lib.nrtgpu_batch_run(self.handle, C.c_void_p(stream)))
+
+    def fetch(self, stream: int = 0, out: Optional[BatchResult] = None) -> BatchResult:
+        if out is None:
+            out = BatchResult(np.zeros((self.nq, self.top_k), np.int32), np.zeros((self.nq, self.top_k), np.float32),
+                              np.zeros(self.nq, np.int32), np.zeros(self.nq, np.int64), np.zeros(self.nq, np.uint8))
+        check(self._lib.nrtgpu_batch_fetch(self.handle, C.c_void_p(stream), out.docs.ctypes.data, out.scores.ctypes.data,
+                                           out.counts.ctypes.data, out.total_hits.ctypes.data, out.relation.ctypes.data))
+        return out
+
+    def stats(self):
+        a, l, w = C.c_int64(), C.c_int32(), C.c_int64()
+        check(self._lib.nrtgpu_batch_stats(self.handle, C.byref(a), C.byref(l), C.byref(w)))
+        return {"alg_postings": a.value, "launches_per_run": l.value, "work_items": w.value}
+
+    def stage_ms(self, stage: int) -> float:
+        ms = C.c_float()
+        check(self._lib.nrtgpu_batch_stage_ms(self.handle, stage, C.byref(ms)))
+        return ms.value
+
+    def device_results(self):
+        d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._lib.nrtgpu_batch_device_results(self.handle, C.byref(d), C.byref(s), C.byref(c)))
+        return d.value, s.value, c.value
+
+    def close(self):
+        if self.handle:
+            self._lib.nrtgpu_batch_free(self.handle)
+            self.handle = None
+
+
+class GpuIndexSearcher:
+    """Batched stand-in for MyIndexSearcher.search(Query, CollectorManager)."""
+
+    def __init__(self, index: GpuIndex):
+        self._lib = _native.gpu_lib()
+        self.index = index
+
+    def prepare(self, queries: Sequence[object], collector: RelevanceCollector,
+                search_after: Optional[Sequence[Optional[ScoreDoc]]] = None, flags: int = 0) -> PreparedBatch:
+        if search_after is None and collector.search_after is not None:
+            search_after = [collector.search_after] * len(queries)
+        carr, ncl, qarr, nq = compile_queries(queries, search_after)
+        return PreparedBatch(self.index, carr, ncl, qarr, nq, collector.num_hits_to_collect,
+                             collector.total_hits_threshold, flags)
+
+    def search_batch(self, queries: Sequence[object], collector: RelevanceCollector,
+                     search_after: Optional[Sequence[Optional[ScoreDoc]]] = None, stream: int = 0) -> BatchResult:
+        """One call through the C ABI with HOST buffers (nrtgpu_search_bool)."""
+        if search_after is None and collector.search_after is not None:
+            search_after = [collector.search_after] * len(queries)
+        carr, ncl, qarr, nq = compile_queries(queries, search_after)
+        k = collector.num_hits_to_collect
+        out = BatchResult(np.zeros((nq, max(k, 1)), np.int32), np.zeros((nq, max(k, 1)), np.float32),
+                          np.zeros(nq, np.int32), np.zeros(nq, np.int64), np.zeros(nq, np.uint8))
+        check(self._lib.nrtgpu_search_bool(self.index.handle, carr, ncl, qarr, nq, k, collector.total_hits_threshold, 0,
+                                           C.c_void_p(stream), out.docs.ctypes.data, out.scores.ctypes.data,
+                                           out.counts.ctypes.data, out.total_hits.ctypes.data, out.relation.ctypes.data))
+        return out
+
+    def search(self, query, collector: RelevanceCollector) -> TopDocs:
+        return self.search_batch([query], collector).top_docs(0)
+
+    def knn(self, queries: np.ndarray, k: int, boosts: Optional[np.ndarray] = None,
+            filter_docs: Optional[np.ndarray] = None, stream: int = 0):
+        """Exact kNN (KnnUtils.resolveKnnQueryAndBoost with ExactVectorQuery semantics): returns docs, scores, counts."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        docs = np.zeros((nq, k), np.int32)
+        scores = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.int32)
+        b = None if boosts is None else np.ascontiguousarray(boosts, dtype=np.float32)
+        f = None if filter_docs is None else np.ascontiguousarray(filter_docs, dtype=np.uint8)
+        check(self._lib.nrtgpu_search_knn(self.index.handle, q.ctypes.data, nq, k,
+                                          None if b is None else b.ctypes.data, None if f is None else f.ctypes.data,
+                                          C.c_void_p(stream), docs.ctypes.data, scores.ctypes.data, counts.ctypes.data))
+        return docs, scores, counts
