@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- BM25 queries/s of the batched posting-traversal path (BASELINE.json configs[1]):
+10M-doc synthetic Zipf corpus, 1024 three-term disjunctive queries, top-100, on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over the 1024-query batch. `value` = whole-job queries/s with the
+compiled batch resident in HBM; `e2e` = the same through nrtgpu_search_bool with HOST buffers (query
+upload + result download inside the timed region). N > 1: the corpus is split into N contiguous doc-range
+shards (one per GPU, index-wide BM25 statistics all-reduced at build time); every step ends with one NCCL
+all-gather of the per-shard top-k and a device-side TopDocs.merge => strong scaling.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_POSTING = 9  # int32 doc id + int32 freq + 1 B norm gather
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--nq", type=int, default=1024)
+    ap.add_argument("--topk", type=int, default=100)
+    ap.add_argument("--threshold", type=int, default=1000, help="totalHitsThreshold (reference default 1000)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--no-check", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_queries(nq, vocab):
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.search import BooleanQuery, Occur, TermQuery
+    terms = ix.synth_query_terms(nq, 3, vocab)   # rank log-uniform in [10, 10^4)
+    return [BooleanQuery().add(TermQuery(int(t[0])), Occur.SHOULD).add(TermQuery(int(t[1])), Occur.SHOULD)
+            .add(TermQuery(int(t[2])), Occur.SHOULD) for t in terms]
+
+
+def build_shard(args, rank, world):
+    """Rank r holds docs [r*N/G, (r+1)*N/G); df / docCount / sumTotalTermFreq become index-wide."""
+    from nrtsearch_b200 import index as ix
+    lo, hi = args.docs * rank // world, args.docs * (rank + 1) // world
+    sh = ix.synth_text_shard(hi - lo, args.vocab, doc_begin=lo)
+    local_df = np.diff(sh.term_off).astype(np.int64)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.concatenate([local_df, [sh.fields[0].sum_total_term_freq, sh.n_docs]])).cuda()
+        dist.all_reduce(t)   # NCCL all-reduce of per-shard term statistics (build time, not per query)
+        g = t.cpu().numpy()
+        sh.term_df = np.ascontiguousarray(g[:-2])
+        sh.fields[0].sum_total_term_freq = int(g[-2])
+        sh.fields[0].doc_count = int(g[-1])
+    else:
+        sh.term_df = local_df
+    return sh
+
+
+def cpu_baseline(sh, queries, args, n_sample, threads):
+    """The reference's CPU path restated (oracle/, MAXSCORE dynamic pruning, one query per thread)."""
+    import oracle
+    from nrtsearch_b200.search import compile_queries
+    oix = oracle.OracleIndex(sh, with_impacts=True)
+    sample = queries[:n_sample]
+    carr, ncl, qarr, nq = compile_queries(sample)
+    oracle.search_compiled(oix, carr, ncl, qarr, min(nq, 8), args.topk, args.threshold, 1, threads)  # warm
+    t0 = time.perf_counter()
+    res = oracle.search_compiled(oix, carr, ncl, qarr, nq, args.topk, args.threshold, 1, threads)
+    dt = time.perf_counter() - t0
+    return nq / dt, res, oix
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build_if_needed()
+    threads = os.cpu_count() or 1
+    sh = build_shard(args, 0, 1)
+    queries = make_queries(args.nq, args.vocab)
+    n_sample = min(args.cpu_sample, args.nq)
+    times = []
+    import oracle
+    from nrtsearch_b200.search import compile_queries
+    oix = oracle.OracleIndex(sh, with_impacts=True)
+    carr, ncl, qarr, nq = compile_queries(queries[:n_sample])
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.search_compiled(oix, carr, ncl, qarr, nq, args.topk, args.threshold, 1, threads)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    qps = nq / dt
+    sample = f"first {n_sample} of the {args.nq} queries per step, MAXSCORE-pruned DAAT, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "BM25 queries/sec (batch 1024, 10M docs)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * args.nq / n_sample,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated CPU oracle (oracle/oracle.c), NOT Lucene: no JVM / lucene-core jar exists in this image",
+    }))
+
+
+def workload_config(args):
+    return {"workload": "configs[1]: 10M-doc synthetic Zipf postings, 1024-query disjunctive BM25 top-100",
+            "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "terms_per_query": 3, "top_k": args.topk,
+            "total_hits_threshold": args.threshold, "sharding": f"doc-range x{args.gpus}",
+            "l2": "posting image (GBs) >> 126 MB L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import __graft_entry__ as g
+    g.build_if_needed()
+    from nrtsearch_b200 import _native
+    from nrtsearch_b200.search import GpuContext, GpuIndex, GpuIndexSearcher, RelevanceCollector, compile_queries
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; nrtsearch_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    t_build = time.perf_counter()
+    sh = build_shard(args, rank, world)
+    queries = make_queries(args.nq, args.vocab)
+    ctx = GpuContext(local_rank)
+    gix = GpuIndex(ctx, sh)
+    searcher = GpuIndexSearcher(gix)
+    coll = RelevanceCollector(args.topk, args.threshold)
+    batch = searcher.prepare(queries, coll)
+    build_s = time.perf_counter() - t_build
+    stats = batch.stats()
+    nq, k = args.nq, args.topk
+    lib = _native.gpu_lib()
+
+    # device buffers (torch = memory + streams plumbing only)
+    loc_docs = torch.zeros(nq * k, dtype=torch.int32, device=dev)
+    loc_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
+    loc_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    batch.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
+    if world > 1:
+        all_docs = torch.zeros(world * nq * k, dtype=torch.int32, device=dev)
+        all_scores = torch.zeros(world * nq * k, dtype=torch.float32, device=dev)
+        all_counts = torch.zeros(world * nq, dtype=torch.int32, device=dev)
+        fin_docs = torch.zeros(nq * k, dtype=torch.int32, device=dev)
+        fin_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
+        fin_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        batch.run(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(all_docs, loc_docs)
+            dist.all_gather_into_tensor(all_scores, loc_scores)
+            dist.all_gather_into_tensor(all_counts, loc_counts)
+            _native.check(lib.nrtgpu_merge_topk_device(ctx.handle, world, nq, k, all_docs.data_ptr(), all_scores.data_ptr(),
+                                                       all_counts.data_ptr(), fin_docs.data_ptr(), fin_scores.data_ptr(),
+                                                       fin_counts.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate before any number is reported (rank 0, N == 1: vs the oracle on a sample)
+    cpu = None
+    if rank == 0 and world == 1:
+        n_sample = min(args.cpu_sample, nq)
+        qps_cpu, ref, _ = cpu_baseline(sh, queries, args, n_sample, os.cpu_count() or 1)
+        cpu = {"value": qps_cpu, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"first {n_sample} of the {nq} queries, MAXSCORE-pruned DAAT (oracle/oracle.c mode 1), same corpus"}
+        if not args.no_check:
+            step(); torch.cuda.synchronize()
+            got_docs = loc_docs.cpu().numpy().reshape(nq, k)[:n_sample]
+            got_scores = loc_scores.cpu().numpy().reshape(nq, k)[:n_sample]
+            assert np.array_equal(got_docs, ref[0]), "bench: GPU top-k doc ids differ from the CPU oracle"
+            assert np.array_equal(got_scores.view(np.uint32), ref[1].view(np.uint32)), "bench: GPU scores differ from the oracle"
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    batch.reset_timing()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    kernel_ms = batch.stage_ms(0)
+    merge_ms = batch.stage_ms(1)
+    if world > 1:
+        t = torch.tensor([ms, kernel_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kernel_ms = float(t[0]), float(t[1])
+        pt = torch.tensor([float(stats["alg_postings"])], device=dev, dtype=torch.float64)
+        dist.all_reduce(pt)
+        alg_postings_total = float(pt[0])
+    else:
+        alg_postings_total = float(stats["alg_postings"])
+    ms_per_step = ms / args.steps
+    qps = nq / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public one-shot call with HOST buffers, every step: H2D plan + D2H results
+    carr, ncl, qarr, _ = compile_queries(queries)
+    h2d = ctypes.sizeof(carr) + ctypes.sizeof(qarr)
+    d2h = nq * k * 8 + nq * (4 + 8)
+    from nrtsearch_b200.search import BatchResult
+    out = BatchResult(np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32),
+                      np.zeros(nq, np.int64), np.zeros(nq, np.uint8))
+
+    def e2e_step():
+        _native.check(lib.nrtgpu_search_bool(gix.handle, carr, ncl, qarr, nq, k, args.threshold, 0, ctypes.c_void_p(stream),
+                                             out.docs.ctypes.data, out.scores.ctypes.data, out.counts.ctypes.data,
+                                             out.total_hits.ctypes.data, out.relation.ctypes.data))
+        if world > 1:   # per-shard host results -> the merged page needs the gather too
+            loc_docs.copy_(torch.from_numpy(out.docs.reshape(-1)), non_blocking=True)
+            loc_scores.copy_(torch.from_numpy(out.scores.reshape(-1)), non_blocking=True)
+            loc_counts.copy_(torch.from_numpy(out.counts), non_blocking=True)
+            dist.all_gather_into_tensor(all_docs, loc_docs)
+            dist.all_gather_into_tensor(all_scores, loc_scores)
+            dist.all_gather_into_tensor(all_counts, loc_counts)
+            _native.check(lib.nrtgpu_merge_topk_device(ctx.handle, world, nq, k, all_docs.data_ptr(), all_scores.data_ptr(),
+                                                       all_counts.data_ptr(), fin_docs.data_ptr(), fin_scores.data_ptr(),
+                                                       fin_counts.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            fin_docs.cpu()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_qps = nq * args.steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = alg_postings_total / world * ALG_BYTES_PER_POSTING + nq * k * 8   # per launch (per GPU)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "BM25 queries/sec (batch 1024, 10M docs)", "value": qps, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": stats["launches_per_run"] * args.steps + (args.steps if world > 1 else 0),
+            "roofline": {"bound": "hbm", "kernel": "bool_window_kernel (posting traversal + BM25 + top-k)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
+                         "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "index": {"postings": int(sh.term_off[-1]), "device_bytes": gix.device_bytes, "build_s": build_s,
+                      "work_items": stats["work_items"]},
+        }
+        print(json.dumps(line))
+    batch.close()
+    gix.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -139,12 +139,17 @@ int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream, int32_t* out_docs, float* 
                        int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation);
 /* device pointers of the last run's results: uint64 keys are not exposed; these are the final arrays */
 int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts);
+/* redirect the final (docs, scores, counts) of subsequent runs into caller-owned DEVICE buffers
+ * ([nq*top_k], [nq*top_k], [nq]); NULLs restore the internal buffers */
+int nrtgpu_batch_bind_output(nrtgpu_batch* b, int32_t* d_docs, float* d_scores, int32_t* d_counts);
 /* stats of the compiled batch: algorithmic postings (sum of df over all term clauses), kernel launches per run */
 int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run,
                        int64_t* work_items);
-/* duration (ms) of stage `stage` in the most recent run (events recorded on the run's stream;
- * the stream must have been synchronised). stage 0 = posting traversal kernel, 1 = slice merge. */
+/* mean duration (ms) of stage `stage` over the runs since nrtgpu_batch_reset_timing (at most the last
+ * 64; CUDA events recorded on each run's stream, which must have been synchronised).
+ * stage 0 = posting traversal kernel, 1 = slice merge kernel. */
 int nrtgpu_batch_stage_ms(nrtgpu_batch* b, int32_t stage, float* ms);
+int nrtgpu_batch_reset_timing(nrtgpu_batch* b);
 int nrtgpu_batch_free(nrtgpu_batch* b);
 
 /* Exact kNN (ExactVectorQuery / KnnFloatVectorQuery with exact semantics): HOST buffers. */

@@ -133,9 +133,16 @@ struct nrtgpu_batch {
   DevBuf<int32_t> out_docs;
   DevBuf<float> out_scores;
   DevBuf<int32_t> out_counts;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  static constexpr int kEvRing = 64;
+  cudaEvent_t ev[kEvRing][3] = {};
+  int runs_recorded = 0;   // since the last timing reset
   bool ran = false;
-  ~nrtgpu_batch() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+  // optional caller-provided device output buffers (e.g. torch tensors feeding the NCCL all-gather)
+  int32_t* bound_docs = nullptr; float* bound_scores = nullptr; int32_t* bound_counts = nullptr;
+  int32_t* o_docs() { return bound_docs ? bound_docs : out_docs.p; }
+  float* o_scores() { return bound_scores ? bound_scores : out_scores.p; }
+  int32_t* o_counts() { return bound_counts ? bound_counts : out_counts.p; }
+  ~nrtgpu_batch() { for (auto& r : ev) for (auto& e : r) if (e) cudaEventDestroy(e); }
 };
 
 extern "C" {
@@ -411,7 +418,7 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
   if ((rc = b->out_docs.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
-  for (auto& e : b->ev) NRT_CUDA_TRY(cudaEventCreate(&e));
+  for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
   *out = b.release();
   return NRTGPU_OK;
 }
@@ -423,7 +430,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->slice_cnt.p, 0, b->slice_cnt.bytes(), st));
-  NRT_CUDA_TRY(cudaEventRecord(b->ev[0], st));
+  cudaEvent_t* ev = b->ev[b->runs_recorded % nrtgpu_batch::kEvRing];
+  NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
   if (b->n_work > 0) {
     BoolLaunch L;
     L.ix = b->ix->view();
@@ -438,14 +446,15 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       bool_window_kernel<uint64_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint64_t>), st>>>(L);
     NRT_CUDA_TRY(cudaGetLastError());
   }
-  NRT_CUDA_TRY(cudaEventRecord(b->ev[1], st));
+  NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
   MergeLaunch M;
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
   M.n_lists = b->n_slices; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;
-  M.out_docs = b->out_docs.p; M.out_scores = b->out_scores.p; M.out_counts = b->out_counts.p;
+  M.out_docs = b->o_docs(); M.out_scores = b->o_scores(); M.out_counts = b->o_counts();
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
-  NRT_CUDA_TRY(cudaEventRecord(b->ev[2], st));
+  NRT_CUDA_TRY(cudaEventRecord(ev[2], st));
+  b->runs_recorded++;
   b->ran = true;
   return NRTGPU_OK;
 }
@@ -455,9 +464,9 @@ int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float*
   if (!b || !b->ran) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_fetch: batch has not run");
   cudaStream_t st = (cudaStream_t)stream_;
   size_t n = (size_t)b->nq * b->top_k;
-  if (out_docs) NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, b->out_docs.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (out_scores) NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, b->out_scores.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (out_counts) NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, b->out_counts.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out_docs) NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, b->o_docs(), n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out_scores) NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, b->o_scores(), n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (out_counts) NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, b->o_counts(), (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (out_total_hits) NRT_CUDA_TRY(cudaMemcpyAsync(out_total_hits, b->total_hits.p, (size_t)b->nq * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaStreamSynchronize(st));
   if (out_relation) std::memset(out_relation, b->exhaustive ? 0 : 1, (size_t)b->nq);
@@ -466,9 +475,21 @@ int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float*
 
 int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts) {
   if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
-  if (d_docs) *d_docs = b->out_docs.p;
-  if (d_scores) *d_scores = b->out_scores.p;
-  if (d_counts) *d_counts = b->out_counts.p;
+  if (d_docs) *d_docs = b->o_docs();
+  if (d_scores) *d_scores = b->o_scores();
+  if (d_counts) *d_counts = b->o_counts();
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_bind_output(nrtgpu_batch* b, int32_t* d_docs, float* d_scores, int32_t* d_counts) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  b->bound_docs = d_docs; b->bound_scores = d_scores; b->bound_counts = d_counts;
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_reset_timing(nrtgpu_batch* b) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  b->runs_recorded = 0;
   return NRTGPU_OK;
 }
 
@@ -481,8 +502,15 @@ int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* la
 }
 
 int nrtgpu_batch_stage_ms(nrtgpu_batch* b, int32_t stage, float* ms) {
-  if (!b || !ms || stage < 0 || stage > 1 || !b->ran) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_stage_ms: bad argument");
-  NRT_CUDA_TRY(cudaEventElapsedTime(ms, b->ev[stage], b->ev[stage + 1]));
+  if (!b || !ms || stage < 0 || stage > 1 || !b->ran || b->runs_recorded < 1) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_stage_ms: bad argument");
+  int n = std::min(b->runs_recorded, (int)nrtgpu_batch::kEvRing);
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    NRT_CUDA_TRY(cudaEventElapsedTime(&t, b->ev[i][stage], b->ev[i][stage + 1]));
+    sum += t;
+  }
+  *ms = (float)(sum / n);
   return NRTGPU_OK;
 }
 

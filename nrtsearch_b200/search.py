@@ -259,6 +259,12 @@ class PreparedBatch:
         check(self._lib.nrtgpu_batch_stage_ms(self.handle, stage, C.byref(ms)))
         return ms.value
 
+    def reset_timing(self):
+        check(self._lib.nrtgpu_batch_reset_timing(self.handle))
+
+    def bind_output(self, d_docs: int, d_scores: int, d_counts: int):
+        check(self._lib.nrtgpu_batch_bind_output(self.handle, C.c_void_p(d_docs), C.c_void_p(d_scores), C.c_void_p(d_counts)))
+
     def device_results(self):
         d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(self._lib.nrtgpu_batch_device_results(self.handle, C.byref(d), C.byref(s), C.byref(c)))

@@ -1,0 +1,66 @@
+"""kNN parity: CUDA exact path vs the oracle's brute force (ExactVectorQuery semantics,
+reference VectorFieldDefTest.java:1886-2117 compares exact search with brute force at 1e-4)."""
+import numpy as np
+import pytest
+
+import oracle
+from nrtsearch_b200 import index as ix
+from nrtsearch_b200.index import HostShard, TextField
+from nrtsearch_b200.search import GpuIndex, GpuIndexSearcher
+
+pytestmark = pytest.mark.gpu
+
+
+def vec_shard(vectors, sim, vec_docs=None, n_docs=None):
+    n = len(vectors) if n_docs is None else n_docs
+    return HostShard(n_docs=n, doc_base=0, term_off=np.zeros(1, np.int64), post_docs=np.zeros(0, np.int32),
+                     post_freqs=np.zeros(0, np.int32), fields=[], vectors=vectors, vec_similarity=sim, vec_docs=vec_docs)
+
+
+def check(gd, gs, gc, wd, ws, wc, rtol=1e-5):
+    assert np.array_equal(gc, wc)
+    for q in range(len(gc)):
+        n = int(gc[q])
+        np.testing.assert_allclose(gs[q, :n], ws[q, :n], rtol=rtol, atol=0)
+        if not np.array_equal(gd[q, :n], wd[q, :n]):   # ids may only differ inside a tie band below tolerance
+            bad = np.nonzero(gd[q, :n] != wd[q, :n])[0]
+            for b in bad:
+                assert abs(gs[q, b] - ws[q, b]) <= rtol * abs(ws[q, b])
+            assert set(gd[q, :n]) - set(wd[q, :n]) == set() or len(bad) <= 2
+
+
+@pytest.mark.parametrize("sim", [ix.SIM_L2, ix.SIM_COSINE, ix.SIM_MIP])
+def test_knn_matches_bruteforce(gpu_ctx, sim):
+    corpus = ix.synth_vectors(20_000, 96)
+    queries = ix.synth_vectors(50, 96, seed=ix.SEED_VQUERIES)
+    gix = GpuIndex(gpu_ctx, vec_shard(corpus, sim))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(queries, 10)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(corpus, sim, queries, 10)
+    check(gd, gs, gc, wd, ws, wc)
+
+
+def test_knn_normalized_dot_product_filter_boost(gpu_ctx):
+    corpus = ix.synth_vectors(5_000, 64)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    queries = ix.synth_vectors(20, 64, seed=ix.SEED_VQUERIES)
+    queries /= np.linalg.norm(queries, axis=1, keepdims=True)
+    flt = (np.arange(5000) % 3 == 0).astype(np.uint8)
+    boosts = np.linspace(0.5, 2.0, 20).astype(np.float32)
+    gix = GpuIndex(gpu_ctx, vec_shard(corpus.astype(np.float32), ix.SIM_DOT))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(queries, 25, boosts=boosts, filter_docs=flt)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_DOT, queries, 25, filter_docs=flt, boosts=boosts)
+    check(gd, gs, gc, wd, ws, wc)
+    assert (gd % 3 == 0).all()
+
+
+def test_knn_fewer_vectors_than_k(gpu_ctx):
+    corpus = ix.synth_vectors(7, 16)
+    queries = ix.synth_vectors(3, 16, seed=ix.SEED_VQUERIES)
+    gix = GpuIndex(gpu_ctx, vec_shard(corpus, ix.SIM_COSINE))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(queries, 10)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries, 10)
+    assert list(gc) == [7, 7, 7]
+    check(gd, gs, gc, wd, ws, wc)
