@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--nq", type=int, default=1024)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--threshold", type=int, default=1000, help="totalHitsThreshold (reference default 1000)")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="queries in the bounded CPU-baseline sample")
     ap.add_argument("--no-check", action="store_true")
     return ap.parse_args()
 

@@ -119,10 +119,12 @@ def test_dense_drivers_matchall_range_mustnot(gpu_ctx, corpus):
 
 
 def test_empty_and_degenerate_queries(gpu_ctx, corpus):
-    rare = corpus.n_terms - 1
-    while corpus.df(rare) == 0:
-        rare -= 1
-    empty_term = next(t for t in range(corpus.n_terms - 1, 0, -1) if corpus.df(t) == 0)
+    import copy
+    corpus = copy.copy(corpus)
+    corpus.term_off = np.append(corpus.term_off, corpus.term_off[-1])   # one extra term without postings
+    empty_term = corpus.n_terms - 1
+    rare = empty_term - 1
+    assert corpus.df(empty_term) == 0 and 0 < corpus.df(rare) < 10
     qs = [
         BooleanQuery(),                                             # no clauses at all: matches nothing
         BooleanQuery().add(TermQuery(rare), Occur.MUST_NOT),        # only MUST_NOT (no MatchAll added): nothing
