@@ -2,6 +2,7 @@
 // batch compilation, kernel launches. No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/nrtgpu.h"
 #include "bool_kernel.cuh"
+#include "stream_kernel.cuh"
 #include "knn_kernel.cuh"
 
 #include <algorithm>
@@ -126,6 +127,7 @@ struct nrtgpu_batch {
   DevBuf<DevClause> clauses;
   DevBuf<DevQuery> queries;
   DevBuf<int32_t> work_query, work_slice;
+  DevBuf<int64_t> bounds;   // v2: [nq][4][n_slices+1]
   DevBuf<uint64_t> theta;
   DevBuf<unsigned long long> total_hits;
   DevBuf<uint64_t> slice_keys;
@@ -169,6 +171,8 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(BoolSmem<uint32_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint64_t>)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(v2::StreamSmem)));
   *out = c;
   return NRTGPU_OK;
 }
@@ -202,16 +206,19 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
   ix->field_doc_count.assign(d->field_doc_count, d->field_doc_count + d->n_fields);
   ix->field_sum_ttf.assign(d->field_sum_ttf, d->field_sum_ttf + d->n_fields);
   // postings
-  if ((rc = ix->post_docs.upload(d->post_docs, (size_t)P))) return rc;
+  const size_t pad = 2 * (size_t)v2::kCH;   // whole TMA chunks may extend past the last posting
+  if ((rc = ix->post_docs.alloc((size_t)P + pad))) return rc;
+  NRT_CUDA_TRY(cudaMemset(ix->post_docs.p, 0x7f, ((size_t)P + pad) * sizeof(int32_t)));
+  if (P) NRT_CUDA_TRY(cudaMemcpy(ix->post_docs.p, d->post_docs, (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice));
   {
-    std::vector<uint8_t> f8((size_t)P);
+    std::vector<uint8_t> f8((size_t)P + pad, 0);
     std::vector<int64_t> epos; std::vector<int32_t> efreq;
     for (int64_t p = 0; p < P; ++p) {
       int32_t f = d->post_freqs[p];
       if (f < 1) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: term frequency < 1");
       if (f >= 255) { f8[(size_t)p] = 255; epos.push_back(p); efreq.push_back(f); } else f8[(size_t)p] = (uint8_t)f;
     }
-    if ((rc = ix->post_f8.upload(f8.data(), (size_t)P))) return rc;
+    if ((rc = ix->post_f8.upload(f8.data(), (size_t)P + pad))) return rc;
     if ((rc = ix->exc_pos.upload(epos.data(), epos.size()))) return rc;
     if ((rc = ix->exc_freq.upload(efreq.data(), efreq.size()))) return rc;
   }
@@ -418,6 +425,17 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
   if ((rc = b->out_docs.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
+  if (!b->wide_slots) {
+    // v2 streams each list from its slice start: one lower_bound per (query, term slot, slice boundary)
+    if ((rc = b->bounds.alloc((size_t)nq * v2::kT * (b->n_slices + 1)))) return rc;
+    v2::BoundsLaunch B;
+    B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_slices = b->n_slices;
+    B.slice_docs = (int32_t)slice_docs; B.bounds = b->bounds.p;
+    int total = nq * v2::kT * (b->n_slices + 1);
+    v2::slice_bounds_kernel<<<(total + 127) / 128, 128>>>(B);
+    NRT_CUDA_TRY(cudaGetLastError());
+    NRT_CUDA_TRY(cudaDeviceSynchronize());
+  }
   for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
   *out = b.release();
   return NRTGPU_OK;
@@ -440,9 +458,14 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     L.n_work = b->n_work; L.n_slices = b->n_slices; L.top_k = b->top_k;
     L.theta = b->theta.p; L.total_hits = b->total_hits.p;
     L.slice_keys = b->slice_keys.p; L.slice_cnt = b->slice_cnt.p;
-    if (!b->wide_slots)
-      bool_window_kernel<uint32_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint32_t>), st>>>(L);
-    else
+    if (!b->wide_slots) {
+      v2::StreamLaunch S;
+      S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
+      S.bounds = b->bounds.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
+      S.slice_docs = kSliceWindows * kWindowDocs;
+      S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
+      v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+    } else
       bool_window_kernel<uint64_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint64_t>), st>>>(L);
     NRT_CUDA_TRY(cudaGetLastError());
   }

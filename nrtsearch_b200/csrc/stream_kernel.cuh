@@ -1,0 +1,454 @@
+// posting_stream_kernel -- v2 of the batched BooleanQuery engine (<= 4 term clauses per query).
+//
+// Same algorithm as bool_window_kernel (scatter tf bytes -> owner emits -> exact top-k, see
+// bool_kernel.cuh) but the posting lists are STREAMED: each term clause owns a ring of kNCH chunks of
+// kCH postings in shared memory, filled by 1-D TMA bulk copies (cp.async.bulk.shared.global with
+// mbarrier complete_tx) issued by one elected thread, so HBM latency is hidden behind the processing
+// of earlier chunks instead of being exposed at every load. Windows are ADAPTIVE: a window spans from
+// the first pending doc to the smallest doc up to which every list is resident (at most kW docs), so a
+// dense list contributes up to two chunks per window and there are no per-window binary searches.
+// Term scores for tf <= kTfTab come from a per-CTA table tbl[clause][tf][norm] of exact BM25 floats
+// (computed once per work item with Lucene's formula), which removes the IEEE division from the
+// per-posting path without changing a single bit of any score.
+#pragma once
+#include "bool_kernel.cuh"
+
+namespace nrtgpu {
+namespace v2 {
+
+constexpr int kT = 4;
+constexpr int kW = 8192;
+constexpr int kLogCH = 9;
+constexpr int kCH = 1 << kLogCH;      // postings per chunk
+constexpr int kNCH = 4;               // chunks per ring (power of two)
+constexpr int kRing = kCH * kNCH;
+constexpr int kRingMask = kRing - 1;
+constexpr int kThreads = 384;
+constexpr int kCand = 2048;
+constexpr int kTfTab = 4;
+constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
+constexpr uint32_t kAll = 0xffffffffu;
+
+struct StreamLaunch {
+  DevIndexView ix;
+  const DevClause* clauses;
+  const DevQuery* queries;
+  const int32_t* work_query;
+  const int32_t* work_slice;
+  const int64_t* bounds;     // [nq][kT][n_slices+1] global posting index of the first posting with doc >= slice start
+  int32_t n_work, n_slices, top_k;
+  int32_t slice_docs;
+  uint64_t* theta;
+  unsigned long long* total_hits;
+  uint64_t* slice_keys;
+  int32_t* slice_cnt;
+};
+
+struct alignas(128) StreamSmem {
+  int32_t ring_docs[kT][kRing];   // 32 KB   (TMA destinations: 16 B aligned)
+  uint8_t ring_f8[kT][kRing];     //  8 KB
+  uint32_t slots[kW];             // 32 KB
+  uint64_t cand[kCand];           // 16 KB
+  float tbl[kT][kTfTab][256];     // 16 KB
+  uint64_t full_bar[kT][kNCH];
+  DevClause cl[kMaxClauses];
+  DevQuery q;
+  uint32_t c_cnt[2][kT];
+  // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
+  const int32_t* s_gdocs[kT];
+  const uint8_t* s_gf8[kT];
+  int32_t s_r_begin[kT], s_r_end[kT], s_n_chunks[kT], s_issued[kT];
+  uint32_t s_scoring[kT];
+  int cand_count;
+  unsigned long long theta;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t presence4(uint32_t s) {
+  // bit i set iff byte i of s is non-zero
+  uint32_t t = (s | (s >> 4)) & 0x0f0f0f0fu;
+  t = (t | (t >> 2)) & 0x03030303u;
+  t = (t | (t >> 1)) & 0x01010101u;
+  return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xfu;
+}
+
+__device__ __noinline__ float term_score_slow(const StreamLaunch& L, const StreamSmem& sm, const DevClause& c, int32_t doc,
+                                              uint32_t b, uint32_t nb) {
+  float f = (b == 255u) ? exact_freq_slow<uint32_t>(L.ix, c, doc) : (float)b;
+  return bm25_score(c.weight, f, __ldg(&L.ix.caches[c.field * 256 + nb]));
+}
+
+// boolean constraints + exact score of one doc from its window word (same semantics as evaluate_doc)
+__device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t slot,
+                                                float* out_score) {
+  const DevQuery& q = sm.q;
+  const uint32_t m = presence4(slot);
+  if ((m & q.req_term_mask) != q.req_term_mask) return false;
+  if (m & q.not_term_mask) return false;
+  if (L.ix.live_bits && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
+  double must_sum = 0.0, should_sum = 0.0;
+  int n_should = 0;
+  int cur_field = -1;
+  uint32_t nb = 1u;
+  for (int i = 0; i < q.n_clauses; ++i) {
+    const DevClause& c = sm.cl[i];
+    bool present;
+    float s = 0.0f;
+    if (c.kind == NRTGPU_TERM) {
+      const uint32_t b = (slot >> (8 * c.slot)) & 0xffu;
+      present = b != 0;
+      if (present && c.scoring) {
+        if (c.field != cur_field) {
+          cur_field = c.field;
+          const uint8_t* nrm = L.ix.norms[c.field];
+          nb = nrm ? (uint32_t)__ldg(nrm + doc) : 1u;
+        }
+        s = (b <= (uint32_t)kTfTab) ? sm.tbl[c.slot][b - 1][nb] : term_score_slow(L, sm, c, doc, b, nb);
+      }
+    } else if (c.kind == NRTGPU_RANGE_I64) {
+      const uint8_t* has = L.ix.col_has[c.col];
+      present = !has || has[doc];
+      if (present) {
+        int64_t v = L.ix.col32[c.col] ? (int64_t)__ldg(L.ix.col32[c.col] + doc) : __ldg(L.ix.col64[c.col] + doc);
+        present = (v >= c.lo) && (v <= c.hi);
+      }
+      s = c.weight;
+    } else {
+      present = true;
+      s = c.weight;
+    }
+    if (!present) {
+      if (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER) return false;
+      continue;
+    }
+    switch (c.occur) {
+      case NRTGPU_MUST: must_sum += (double)s; break;
+      case NRTGPU_FILTER: break;
+      case NRTGPU_SHOULD: should_sum += (double)s; ++n_should; break;
+      default: return false;
+    }
+  }
+  if (n_should < q.need_should) return false;
+  float score;
+  if (q.n_req == 0) score = (float)should_sum;
+  else {
+    float req = (float)must_sum;
+    if (n_should == 0) score = req;
+    else {
+      float opt = (float)should_sum;
+      score = (q.msm > 0) ? (float)((double)req + (double)opt) : __fadd_rn(req, opt);
+    }
+  }
+  *out_score = score;
+  return true;
+}
+
+__device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k, uint64_t* g_theta) {
+  __syncthreads();
+  int n = sm.cand_count;
+  if (n > kCand) n = kCand;
+  int m = next_pow2(n < 2 ? 2 : n);
+  for (int i = n + threadIdx.x; i < m; i += blockDim.x) sm.cand[i] = 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(sm.cand, m);
+  if (threadIdx.x == 0) {
+    int keep = n < top_k ? n : top_k;
+    sm.cand_count = keep;
+    if (keep == top_k) {
+      unsigned long long kth = sm.cand[top_k - 1];
+      unsigned long long old = atomicMax((unsigned long long*)g_theta, kth);
+      unsigned long long t = old > kth ? old : kth;
+      if (t > sm.theta) sm.theta = t;
+    } else {
+      unsigned long long g = *(volatile unsigned long long*)g_theta;
+      if (g > sm.theta) sm.theta = g;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunch L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int wi = blockIdx.x;
+  if (wi >= L.n_work) return;
+  const int qi = L.work_query[wi];
+  const int slice = L.work_slice[wi];
+
+  if (tid == 0) {
+    sm.q = L.queries[qi];
+    sm.cand_count = 0;
+    sm.theta = *(volatile unsigned long long*)&L.theta[qi];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+#pragma unroll
+      for (int j = 0; j < kNCH; ++j) mbar_init(&sm.full_bar[t][j], 1);
+      sm.c_cnt[0][t] = kAll;
+      sm.c_cnt[1][t] = kAll;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int ncl = sm.q.n_clauses;
+  if (tid < ncl) sm.cl[tid] = L.clauses[sm.q.clause_begin + tid];
+  for (int i = tid; i < kW; i += kThreads) sm.slots[i] = 0u;
+  __syncthreads();
+
+  // ---- per-slot stream state: descriptors in shared memory, cursors r_cur[] in CTA-uniform registers
+  const int n_term = sm.q.n_term;
+  if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
+                  sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; }
+  __syncthreads();
+  if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
+    const int s = sm.cl[tid].slot;
+    const int64_t* bp = L.bounds + ((size_t)qi * kT + s) * (L.n_slices + 1) + slice;
+    const int64_t g0 = bp[0], g1 = bp[1];
+    const int64_t base_g = (g0 >> kLogCH) << kLogCH;
+    sm.s_r_begin[s] = (int32_t)(g0 - base_g);
+    sm.s_r_end[s] = (int32_t)(g1 - base_g);
+    sm.s_n_chunks[s] = (g1 > g0) ? (int32_t)((g1 - base_g + kCH - 1) >> kLogCH) : 0;
+    sm.s_gdocs[s] = L.ix.post_docs + base_g;
+    sm.s_gf8[s] = L.ix.post_f8 + base_g;
+    sm.s_scoring[s] = sm.cl[tid].scoring != 0;
+  }
+  __syncthreads();
+  int32_t r_cur[kT];
+#pragma unroll
+  for (int t = 0; t < kT; ++t) r_cur[t] = sm.s_r_begin[t];
+  auto issue_chunks = [&]() {  // thread 0 only: fill every free ring slot
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + kNCH);
+      int j = sm.s_issued[t];
+      for (; j < lim; ++j) {
+        uint64_t* bar = &sm.full_bar[t][j & (kNCH - 1)];
+        mbar_arrive_expect_tx(bar, kChunkBytes);
+        bulk_g2s(&sm.ring_docs[t][(j & (kNCH - 1)) << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
+        bulk_g2s(&sm.ring_f8[t][(j & (kNCH - 1)) << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
+      }
+      sm.s_issued[t] = j;
+    }
+  };
+  if (tid == 0) issue_chunks();
+
+  // ---- exact BM25 table: tbl[slot][tf-1][norm byte]
+  for (int i = tid; i < kT * kTfTab * 256; i += kThreads) {
+    const int s = i / (kTfTab * 256), tf = (i / 256) % kTfTab + 1, nb = i & 255;
+    float v = 0.0f;
+    for (int c = 0; c < ncl; ++c)
+      if (sm.cl[c].kind == NRTGPU_TERM && sm.cl[c].slot == s)
+        v = bm25_score(sm.cl[c].weight, (float)tf, __ldg(&L.ix.caches[sm.cl[c].field * 256 + nb]));
+    sm.tbl[s][tf - 1][nb] = v;
+  }
+  __syncthreads();
+
+  const int32_t slice_base = slice * L.slice_docs;
+  int32_t slice_end = slice_base + L.slice_docs;
+  if (slice_end > L.ix.n_docs || slice_end < slice_base) slice_end = L.ix.n_docs;
+  const bool dense = sm.q.dense_driver != 0;
+  const bool has_after = sm.q.has_after != 0;
+  const uint64_t after_key = sm.q.after_key;
+  const uint32_t driver_mask = sm.q.driver_mask;
+  const bool has_non_driver = sm.q.has_non_driver != 0;
+  unsigned long long my_hits = 0;
+  int cand_ub = 0;
+  int32_t wpos = slice_base;  // dense mode: next doc to visit
+  unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
+
+  auto offer = [&](bool matched, int32_t doc, float score) {
+    bool is_cand = false;
+    uint64_t key = 0;
+    if (matched) {
+      ++my_hits;
+      key = make_key(score, doc);
+      is_cand = key > sm.theta && (!has_after || key < after_key);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.cand_count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_cand) sm.cand[base + __popc(bal & ((1u << lane) - 1))] = key;
+    }
+  };
+  auto round_end = [&]() {
+    cand_ub += kThreads;
+    if (cand_ub > kCand - kThreads) {
+      __syncthreads();
+      int n = sm.cand_count;
+      if (n > kCand - kThreads) { compact_candidates_v2(sm, L.top_k, &L.theta[qi]); n = sm.cand_count; }
+      cand_ub = n;
+    }
+  };
+
+  for (int w = 0;; ++w) {
+    // ---------------- A/B: residency + window bounds (every thread computes the same values)
+    int32_t avail_end[kT];
+    int32_t wbase = INT32_MAX, wlimit = INT32_MAX;
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      avail_end[t] = r_cur[t];
+      const int32_t r_end = sm.s_r_end[t];
+      if (t < n_term && r_cur[t] < r_end) {
+        const int jc = r_cur[t] >> kLogCH;
+        mbar_wait(&sm.full_bar[t][jc & (kNCH - 1)], (jc / kNCH) & 1);
+        if (jc + 1 < sm.s_n_chunks[t]) mbar_wait(&sm.full_bar[t][(jc + 1) & (kNCH - 1)], ((jc + 1) / kNCH) & 1);
+        avail_end[t] = min(r_end, (jc + 2) << kLogCH);
+        wbase = min(wbase, sm.ring_docs[t][r_cur[t] & kRingMask]);
+        if (avail_end[t] < r_end) wlimit = min(wlimit, sm.ring_docs[t][(avail_end[t] - 1) & kRingMask] + 1);
+      }
+    }
+    if (dense) wbase = wpos;
+    if (wbase >= slice_end) break;  // every list exhausted (or dense sweep finished)
+    int32_t wend = (slice_end - wbase > kW) ? wbase + kW : slice_end;
+    wend = min(wend, wlimit);
+    if (tid == 0) {
+#pragma unroll
+      for (int t = 0; t < kT; ++t) sm.c_cnt[(w + 1) & 1][t] = kAll;
+    }
+    // ---------------- pass 1: scatter tf bytes; the thread that sees the first doc >= wend records the count
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      if (t >= n_term) break;
+      const bool scoring = sm.s_scoring[t] != 0;
+      for (int32_t r = r_cur[t] + tid; r < avail_end[t]; r += kThreads) {
+        const int32_t doc = sm.ring_docs[t][r & kRingMask];
+        if (doc < wend) {
+          slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.ring_f8[t][r & kRingMask] : (unsigned char)1;
+        } else if (r == r_cur[t] || sm.ring_docs[t][(r - 1) & kRingMask] < wend) {
+          sm.c_cnt[w & 1][t] = (uint32_t)(r - r_cur[t]);
+        }
+      }
+    }
+    __syncthreads();
+    int32_t cnt[kT];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const uint32_t c = sm.c_cnt[w & 1][t];
+      cnt[t] = (c == kAll) ? (avail_end[t] - r_cur[t]) : (int32_t)c;
+    }
+    // ---------------- pass 2: emit
+    if (!dense) {
+#pragma unroll
+      for (int t = 0; t < kT; ++t) {
+        if (t >= n_term) break;
+        if (!((driver_mask >> t) & 1u)) continue;
+        uint32_t below = 0;
+#pragma unroll
+        for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below |= 0xffu << (8 * j);
+        const uint32_t own = 0xffu << (8 * t);
+        const int32_t r1 = r_cur[t] + cnt[t];
+        for (int32_t r0 = r_cur[t]; r0 < r1; r0 += kThreads) {
+          const int32_t r = r0 + tid;
+          bool matched = false; int32_t doc = 0; float score = 0.0f;
+          if (r < r1) {
+            doc = sm.ring_docs[t][r & kRingMask];
+            const uint32_t v = sm.slots[doc - wbase];
+            if ((v & below) == 0 && (v & own) != 0) {
+              sm.slots[doc - wbase] = 0u;
+              matched = evaluate_doc_v2(L, sm, doc, v, &score);
+            }
+          }
+          offer(matched, doc, score);
+          round_end();
+        }
+      }
+    } else {
+      const int32_t wlen = wend - wbase;
+      for (int32_t i0 = 0; i0 < wlen; i0 += kThreads) {
+        const int32_t i = i0 + tid;
+        bool matched = false; const int32_t doc = wbase + i; float score = 0.0f;
+        if (i < wlen) {
+          const uint32_t v = sm.slots[i];
+          if (v) sm.slots[i] = 0u;
+          matched = evaluate_doc_v2(L, sm, doc, v, &score);
+        }
+        offer(matched, doc, score);
+        round_end();
+      }
+    }
+    __syncthreads();
+    // ---------------- pass 3: clear the words pass 2 did not visit
+    if (!dense && has_non_driver) {
+#pragma unroll
+      for (int t = 0; t < kT; ++t) {
+        if (t >= n_term) break;
+        if ((driver_mask >> t) & 1u) continue;
+        const int32_t r1 = r_cur[t] + cnt[t];
+        for (int32_t r = r_cur[t] + tid; r < r1; r += kThreads) sm.slots[sm.ring_docs[t][r & kRingMask] - wbase] = 0u;
+      }
+      __syncthreads();
+    }
+    // ---------------- advance the streams, refill freed ring slots
+#pragma unroll
+    for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
+    wpos = wend;
+    if (tid == 0) issue_chunks();
+  }
+
+  // ---------------- finish the work item
+  compact_candidates_v2(sm, L.top_k, &L.theta[qi]);
+  const int keep = sm.cand_count;
+  uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
+  for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
+  if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
+  for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
+  if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], my_hits);
+}
+
+// posting index of the first posting with doc >= slice start, for every (query, term slot, slice boundary)
+struct BoundsLaunch {
+  DevIndexView ix;
+  const DevClause* clauses;
+  const DevQuery* queries;
+  int32_t nq, n_slices, slice_docs;
+  int64_t* bounds;  // [nq][kT][n_slices+1]
+};
+
+__global__ void slice_bounds_kernel(BoundsLaunch B) {
+  const int per_q = kT * (B.n_slices + 1);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.nq * per_q) return;
+  const int q = i / per_q, s = (i % per_q) / (B.n_slices + 1), b = i % (B.n_slices + 1);
+  const DevQuery dq = B.queries[q];
+  int64_t out = 0;
+  for (int c = 0; c < dq.n_clauses; ++c) {
+    const DevClause cl = B.clauses[dq.clause_begin + c];
+    if (cl.kind != NRTGPU_TERM || cl.slot != s) continue;
+    int64_t target64 = (int64_t)b * B.slice_docs;
+    int32_t target = target64 > (int64_t)B.ix.n_docs ? B.ix.n_docs : (int32_t)target64;
+    const int32_t* docs = B.ix.post_docs + cl.post_base;
+    int lo = 0, hi = cl.n_post;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(docs + mid) < target) lo = mid + 1; else hi = mid; }
+    out = cl.post_base + lo;
+  }
+  B.bounds[i] = out;
+}
+
+}  // namespace v2
+}  // namespace nrtgpu
