@@ -59,6 +59,10 @@ struct DevQuery {
   int32_t has_nonterm;     // 1: range / match-all clauses present
   int32_t empty;           // 1: can match nothing
   int32_t has_after;
+  uint32_t must_term_mask;    // bit s set: term slot s is MUST (scores into the required sum)
+  uint32_t should_term_mask;  // bit s set: term slot s is SHOULD
+  int32_t nonterm_scoring;    // 1: a range / match-all clause is MUST or SHOULD (contributes a constant score)
+  int32_t single_field;       // >= 0: every term clause reads this text field's norms; -1: mixed
   uint64_t after_key;
 };
 

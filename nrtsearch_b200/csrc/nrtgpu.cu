@@ -339,6 +339,7 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
     int n_term = 0, n_req = 0, n_should = 0, n_req_term = 0, n_req_nonterm = 0, n_should_nonterm = 0;
     int best_req_slot = -1; int32_t best_req_n = INT32_MAX;
     uint32_t should_term_mask = 0;
+    int field0 = -2;   // -2: no term yet, -1: mixed
     for (int ci = q.clause_begin; ci < q.clause_end; ++ci) {
       const nrtgpu_clause& c = clauses[ci];
       if (c.occur < NRTGPU_SHOULD || c.occur > NRTGPU_MUST_NOT) NRT_FAIL(NRTGPU_ERR_INVALID, "bad occur");
@@ -360,17 +361,21 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
         if (required) { o.req_term_mask |= 1u << n_term; ++n_req_term; if (x.n_post < best_req_n) { best_req_n = x.n_post; best_req_slot = n_term; } }
         if (c.occur == NRTGPU_MUST_NOT) o.not_term_mask |= 1u << n_term;
         if (c.occur == NRTGPU_SHOULD) should_term_mask |= 1u << n_term;
+        if (c.occur == NRTGPU_MUST) o.must_term_mask |= 1u << n_term;
+        if (x.scoring) field0 = (field0 == -2 || field0 == f) ? f : -1;
         if (x.scoring) b->alg_postings += x.n_post; else b->alg_postings += x.n_post;
         ++n_term;
       } else if (c.kind == NRTGPU_RANGE_I64) {
         if (c.id < 0 || c.id >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "column id out of range");
         x.col = c.id; x.weight = c.boost;  // constant-score query: score = boost
         o.has_nonterm = 1;
+        if (x.scoring) o.nonterm_scoring = 1;
         if (required) ++n_req_nonterm;
         if (c.occur == NRTGPU_SHOULD) ++n_should_nonterm;
       } else if (c.kind == NRTGPU_MATCH_ALL) {
         x.weight = c.boost;
         o.has_nonterm = 1;
+        if (x.scoring) o.nonterm_scoring = 1;
         if (required) ++n_req_nonterm;
         if (c.occur == NRTGPU_SHOULD) ++n_should_nonterm;
       } else NRT_FAIL(NRTGPU_ERR_INVALID, "bad clause kind");
@@ -379,6 +384,8 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
       dc.push_back(x);
     }
     o.n_term = n_term; o.n_req = n_req;
+    o.should_term_mask = should_term_mask;
+    o.single_field = field0 == -2 ? 0 : field0;
     o.need_should = q.min_should_match > 0 ? q.min_should_match : (n_req == 0 ? 1 : 0);
     max_terms = std::max(max_terms, n_term);
     if (q.min_should_match > n_should || (n_req == 0 && n_should == 0)) o.empty = 1;

@@ -53,11 +53,11 @@ struct alignas(128) StreamSmem {
   uint64_t full_bar[kT][kNCH];
   DevClause cl[kMaxClauses];
   DevQuery q;
-  uint32_t c_cnt[2][kT];
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
   const int32_t* s_gdocs[kT];
   const uint8_t* s_gf8[kT];
   int32_t s_r_begin[kT], s_r_end[kT], s_n_chunks[kT], s_issued[kT];
+  int32_t s_field[kT], s_clause[kT];
   uint32_t s_scoring[kT];
   int cand_count;
   unsigned long long theta;
@@ -100,14 +100,10 @@ __device__ __noinline__ float term_score_slow(const StreamLaunch& L, const Strea
   return bm25_score(c.weight, f, __ldg(&L.ix.caches[c.field * 256 + nb]));
 }
 
-// boolean constraints + exact score of one doc from its window word (same semantics as evaluate_doc)
-__device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t slot,
-                                                float* out_score) {
+// Generic evaluation (queries whose range / match-all clauses score): clause-order loop, same as v1.
+__device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t slot,
+                                                  float* out_score) {
   const DevQuery& q = sm.q;
-  const uint32_t m = presence4(slot);
-  if ((m & q.req_term_mask) != q.req_term_mask) return false;
-  if (m & q.not_term_mask) return false;
-  if (L.ix.live_bits && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
   double must_sum = 0.0, should_sum = 0.0;
   int n_should = 0;
   int cur_field = -1;
@@ -165,6 +161,93 @@ __device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const Str
   return true;
 }
 
+// non-scoring range / match-all clauses (FILTER / MUST_NOT) as predicates
+__device__ __noinline__ bool nonterm_filters_pass(const StreamLaunch& L, const StreamSmem& sm, int32_t doc) {
+  const DevQuery& q = sm.q;
+  for (int i = 0; i < q.n_clauses; ++i) {
+    const DevClause& c = sm.cl[i];
+    if (c.kind == NRTGPU_TERM) continue;
+    bool present = true;
+    if (c.kind == NRTGPU_RANGE_I64) {
+      const uint8_t* has = L.ix.col_has[c.col];
+      present = !has || has[doc];
+      if (present) {
+        int64_t v = L.ix.col32[c.col] ? (int64_t)__ldg(L.ix.col32[c.col] + doc) : __ldg(L.ix.col64[c.col] + doc);
+        present = (v >= c.lo) && (v <= c.hi);
+      }
+    }
+    if (c.occur == NRTGPU_MUST_NOT ? present : !present) return false;
+  }
+  return true;
+}
+
+// Per-CTA constants of the fast path (term clauses only contribute to the score)
+struct FastQ {
+  uint32_t req_mask, not_mask, must_mask, should_mask;
+  int32_t need_should, n_req, msm;
+  const uint8_t* norms0;       // single-field norms (may be NULL = omitNorms)
+  bool single_field, has_nonterm, generic, has_live;
+};
+
+// boolean constraints + exact score of one doc from its window word. Clause sums are double in slot
+// (= clause) order; required+optional combine as Lucene's ReqOptSumScorer / ConjunctionScorer.
+__device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const StreamSmem& sm, const FastQ& fq, int32_t doc,
+                                                uint32_t slot, float* out_score) {
+  const uint32_t m = presence4(slot);
+  if ((m & fq.req_mask) != fq.req_mask) return false;
+  if (m & fq.not_mask) return false;
+  const int n_should = __popc(m & fq.should_mask);
+  if (fq.has_live && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
+  if (fq.generic) return evaluate_doc_generic(L, sm, doc, slot, out_score);
+  if (n_should < fq.need_should) return false;
+  if (fq.has_nonterm && !nonterm_filters_pass(L, sm, doc)) return false;
+  uint32_t nb0 = 1u;
+  if (fq.single_field && fq.norms0) nb0 = (uint32_t)__ldg(fq.norms0 + doc);
+  double must_sum = 0.0, should_sum = 0.0;
+#pragma unroll
+  for (int t = 0; t < kT; ++t) {
+    const uint32_t b = (slot >> (8 * t)) & 0xffu;
+    if (b != 0 && (((fq.must_mask | fq.should_mask) >> t) & 1u)) {
+      uint32_t nb = nb0;
+      if (!fq.single_field) {
+        const uint8_t* nrm = L.ix.norms[sm.s_field[t]];
+        nb = nrm ? (uint32_t)__ldg(nrm + doc) : 1u;
+      }
+      float s;
+      if (b <= (uint32_t)kTfTab) s = sm.tbl[t][b - 1][nb];
+      else s = term_score_slow(L, sm, sm.cl[sm.s_clause[t]], doc, b, nb);
+      if ((fq.must_mask >> t) & 1u) must_sum += (double)s; else should_sum += (double)s;
+    }
+  }
+  float score;
+  if (fq.n_req == 0) score = (float)should_sum;
+  else {
+    const float req = (float)must_sum;
+    if (n_should == 0) score = req;
+    else {
+      const float opt = (float)should_sum;
+      score = (fq.msm > 0) ? (float)((double)req + (double)opt) : __fadd_rn(req, opt);
+    }
+  }
+  *out_score = score;
+  return true;
+}
+
+// first index i in [0, n) (n <= 1024) with ring[(r0+i) & mask] >= bound, else n; executed by a converged warp
+__device__ __forceinline__ int32_t warp_lower_bound(const int32_t* ring, int32_t r0, int32_t n, int32_t bound, int lane) {
+  if (n <= 0) return 0;
+  const int32_t stride = (n + 31) >> 5;   // <= 32
+  int32_t p = min(n, (lane + 1) * stride) - 1;
+  bool ge = (lane * stride < n) && ring[(r0 + p) & kRingMask] >= bound;
+  unsigned bal = __ballot_sync(0xffffffffu, ge);
+  if (bal == 0) return n;
+  const int32_t blk = (__ffs(bal) - 1) * stride;
+  p = blk + lane;
+  ge = (lane < stride) && (p < n) && ring[(r0 + p) & kRingMask] >= bound;
+  bal = __ballot_sync(0xffffffffu, ge);
+  return blk + (__ffs(bal) - 1);
+}
+
 __device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k, uint64_t* g_theta) {
   __syncthreads();
   int n = sm.cand_count;
@@ -207,8 +290,6 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     for (int t = 0; t < kT; ++t) {
 #pragma unroll
       for (int j = 0; j < kNCH; ++j) mbar_init(&sm.full_bar[t][j], 1);
-      sm.c_cnt[0][t] = kAll;
-      sm.c_cnt[1][t] = kAll;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -222,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   // ---- per-slot stream state: descriptors in shared memory, cursors r_cur[] in CTA-uniform registers
   const int n_term = sm.q.n_term;
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
-                  sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; }
+                  sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0; }
   __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
@@ -235,6 +316,8 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     sm.s_gdocs[s] = L.ix.post_docs + base_g;
     sm.s_gf8[s] = L.ix.post_f8 + base_g;
     sm.s_scoring[s] = sm.cl[tid].scoring != 0;
+    sm.s_field[s] = sm.cl[tid].field;
+    sm.s_clause[s] = tid;
   }
   __syncthreads();
   int32_t r_cur[kT];
@@ -275,6 +358,13 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   const uint64_t after_key = sm.q.after_key;
   const uint32_t driver_mask = sm.q.driver_mask;
   const bool has_non_driver = sm.q.has_non_driver != 0;
+  FastQ fq;
+  fq.req_mask = sm.q.req_term_mask; fq.not_mask = sm.q.not_term_mask;
+  fq.must_mask = sm.q.must_term_mask; fq.should_mask = sm.q.should_term_mask;
+  fq.need_should = sm.q.need_should; fq.n_req = sm.q.n_req; fq.msm = sm.q.msm;
+  fq.single_field = sm.q.single_field >= 0;
+  fq.norms0 = fq.single_field ? L.ix.norms[sm.q.single_field] : nullptr;
+  fq.has_nonterm = sm.q.has_nonterm != 0; fq.generic = sm.q.nonterm_scoring != 0; fq.has_live = L.ix.live_bits != nullptr;
   unsigned long long my_hits = 0;
   int cand_ub = 0;
   int32_t wpos = slice_base;  // dense mode: next doc to visit
@@ -327,31 +417,23 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     if (wbase >= slice_end) break;  // every list exhausted (or dense sweep finished)
     int32_t wend = (slice_end - wbase > kW) ? wbase + kW : slice_end;
     wend = min(wend, wlimit);
-    if (tid == 0) {
+    // postings of every list inside [wbase, wend): 2-step 32-ary search by every (converged) warp
+    int32_t cnt[kT];
 #pragma unroll
-      for (int t = 0; t < kT; ++t) sm.c_cnt[(w + 1) & 1][t] = kAll;
-    }
-    // ---------------- pass 1: scatter tf bytes; the thread that sees the first doc >= wend records the count
+    for (int t = 0; t < kT; ++t)
+      cnt[t] = (t < n_term) ? warp_lower_bound(sm.ring_docs[t], r_cur[t], avail_end[t] - r_cur[t], wend, lane) : 0;
+    // ---------------- pass 1: scatter tf bytes
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       if (t >= n_term) break;
       const bool scoring = sm.s_scoring[t] != 0;
-      for (int32_t r = r_cur[t] + tid; r < avail_end[t]; r += kThreads) {
+      const int32_t r1 = r_cur[t] + cnt[t];
+      for (int32_t r = r_cur[t] + tid; r < r1; r += kThreads) {
         const int32_t doc = sm.ring_docs[t][r & kRingMask];
-        if (doc < wend) {
-          slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.ring_f8[t][r & kRingMask] : (unsigned char)1;
-        } else if (r == r_cur[t] || sm.ring_docs[t][(r - 1) & kRingMask] < wend) {
-          sm.c_cnt[w & 1][t] = (uint32_t)(r - r_cur[t]);
-        }
+        slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.ring_f8[t][r & kRingMask] : (unsigned char)1;
       }
     }
     __syncthreads();
-    int32_t cnt[kT];
-#pragma unroll
-    for (int t = 0; t < kT; ++t) {
-      const uint32_t c = sm.c_cnt[w & 1][t];
-      cnt[t] = (c == kAll) ? (avail_end[t] - r_cur[t]) : (int32_t)c;
-    }
     // ---------------- pass 2: emit
     if (!dense) {
 #pragma unroll
@@ -371,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
             const uint32_t v = sm.slots[doc - wbase];
             if ((v & below) == 0 && (v & own) != 0) {
               sm.slots[doc - wbase] = 0u;
-              matched = evaluate_doc_v2(L, sm, doc, v, &score);
+              matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
             }
           }
           offer(matched, doc, score);
@@ -386,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
         if (i < wlen) {
           const uint32_t v = sm.slots[i];
           if (v) sm.slots[i] = 0u;
-          matched = evaluate_doc_v2(L, sm, doc, v, &score);
+          matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
         }
         offer(matched, doc, score);
         round_end();
