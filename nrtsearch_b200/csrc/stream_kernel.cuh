@@ -1,4 +1,4 @@
-// posting_stream_kernel -- v2 of the batched BooleanQuery engine (<= 4 term clauses per query).
+// posting_stream_kernel -- streaming version of the batched BooleanQuery engine (<= 4 term clauses per query).
 //
 // Same algorithm as bool_window_kernel (scatter tf bytes -> owner emits -> exact top-k, see
 // bool_kernel.cuh) but the posting lists are STREAMED: each term clause owns a ring of kNCH chunks of
@@ -17,13 +17,12 @@ namespace nrtgpu {
 namespace v2 {
 
 constexpr int kT = 4;
-constexpr int kW = 8192;
+constexpr int kW = 16384;             // docs per window (one 32-bit word each)
 constexpr int kLogCH = 9;
 constexpr int kCH = 1 << kLogCH;      // postings per chunk
-constexpr int kNCH = 4;               // chunks per ring (power of two)
-constexpr int kRing = kCH * kNCH;
-constexpr int kRingMask = kRing - 1;
-constexpr int kThreads = 384;
+constexpr int kPool = 48;             // chunks in the CTA's ring pool, shared by the term clauses
+constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
+constexpr int kThreads = 768;         // one CTA per SM
 constexpr int kCand = 2048;
 constexpr int kTfTab = 4;
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
@@ -45,12 +44,12 @@ struct StreamLaunch {
 };
 
 struct alignas(128) StreamSmem {
-  int32_t ring_docs[kT][kRing];   // 32 KB   (TMA destinations: 16 B aligned)
-  uint8_t ring_f8[kT][kRing];     //  8 KB
-  uint32_t slots[kW];             // 32 KB
-  uint64_t cand[kCand];           // 16 KB
-  float tbl[kT][kTfTab][256];     // 16 KB
-  uint64_t full_bar[kT][kNCH];
+  int32_t pool_docs[kPool * kCH];  // 96 KB  ring pool (TMA destinations: 2 KB aligned chunks)
+  uint8_t pool_f8[kPool * kCH];    // 24 KB
+  uint32_t slots[kW];              // 64 KB
+  uint64_t cand[kCand];            // 16 KB
+  float tbl[kT][kTfTab][256];      // 16 KB
+  uint64_t full_bar[kPool];
   DevClause cl[kMaxClauses];
   DevQuery q;
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
@@ -58,6 +57,7 @@ struct alignas(128) StreamSmem {
   const uint8_t* s_gf8[kT];
   int32_t s_r_begin[kT], s_r_end[kT], s_n_chunks[kT], s_issued[kT];
   int32_t s_field[kT], s_clause[kT];
+  int32_t s_ring_base[kT], s_ring_nch[kT];   // first pool chunk and ring length (chunks, power of two) per slot
   uint32_t s_scoring[kT];
   int cand_count;
   unsigned long long theta;
@@ -233,19 +233,24 @@ __device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const Str
   return true;
 }
 
-// first index i in [0, n) (n <= 1024) with ring[(r0+i) & mask] >= bound, else n; executed by a converged warp
-__device__ __forceinline__ int32_t warp_lower_bound(const int32_t* ring, int32_t r0, int32_t n, int32_t bound, int lane) {
-  if (n <= 0) return 0;
-  const int32_t stride = (n + 31) >> 5;   // <= 32
-  int32_t p = min(n, (lane + 1) * stride) - 1;
-  bool ge = (lane * stride < n) && ring[(r0 + p) & kRingMask] >= bound;
-  unsigned bal = __ballot_sync(0xffffffffu, ge);
-  if (bal == 0) return n;
-  const int32_t blk = (__ffs(bal) - 1) * stride;
-  p = blk + lane;
-  ge = (lane < stride) && (p < n) && ring[(r0 + p) & kRingMask] >= bound;
-  bal = __ballot_sync(0xffffffffu, ge);
-  return blk + (__ffs(bal) - 1);
+// first index i in [0, n) with ring[(r0+i) & mask] >= bound, else n; executed by a converged warp
+// (32-ary search: <= 3 ballot rounds for n <= 32768)
+__device__ __forceinline__ int32_t warp_lower_bound(const int32_t* ring, int32_t mask, int32_t r0, int32_t n, int32_t bound,
+                                                    int lane) {
+  int32_t lo = 0, len = n;   // answer in [lo, lo+len]
+  while (len > 0) {
+    const int32_t stride = (len + 31) >> 5;
+    const int32_t p = lo + min(len, (lane + 1) * stride) - 1;
+    const bool ge = (lane * stride < len) && ring[(r0 + p) & mask] >= bound;
+    const unsigned bal = __ballot_sync(0xffffffffu, ge);
+    if (bal == 0) return lo + len;
+    const int32_t blk = (__ffs(bal) - 1) * stride;
+    const int32_t blk_len = min(len - blk, stride);
+    if (stride == 1) return lo + blk;
+    lo += blk; len = blk_len - 1;   // the last element of the block is known to be >= bound
+    if (len == 0) return lo;
+  }
+  return lo;
 }
 
 __device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k, uint64_t* g_theta) {
@@ -272,7 +277,7 @@ __device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunch L) {
+__global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -286,11 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     sm.q = L.queries[qi];
     sm.cand_count = 0;
     sm.theta = *(volatile unsigned long long*)&L.theta[qi];
-#pragma unroll
-    for (int t = 0; t < kT; ++t) {
-#pragma unroll
-      for (int j = 0; j < kNCH; ++j) mbar_init(&sm.full_bar[t][j], 1);
-    }
+    for (int j = 0; j < kPool; ++j) mbar_init(&sm.full_bar[j], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -298,12 +299,10 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   const int ncl = sm.q.n_clauses;
   if (tid < ncl) sm.cl[tid] = L.clauses[sm.q.clause_begin + tid];
   for (int i = tid; i < kW; i += kThreads) sm.slots[i] = 0u;
-  __syncthreads();
-
-  // ---- per-slot stream state: descriptors in shared memory, cursors r_cur[] in CTA-uniform registers
   const int n_term = sm.q.n_term;
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
-                  sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0; }
+                  sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
+                  sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; }
   __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
@@ -320,19 +319,47 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     sm.s_clause[s] = tid;
   }
   __syncthreads();
-  int32_t r_cur[kT];
+  if (tid == 0) {
+    // split the ring pool: every list starts with 2 chunks; the list with the most chunks still to
+    // stream per ring chunk is doubled while the pool allows (dense lists get long rings)
+    int nch[kT], used = 0;
+    for (int t = 0; t < kT; ++t) { nch[t] = (t < n_term) ? 2 : 0; used += nch[t]; }
+    for (;;) {
+      int best = -1; float best_ratio = 0.5f;
+      for (int t = 0; t < n_term; ++t) {
+        if (nch[t] >= kMaxNCH || used + nch[t] > kPool) continue;
+        float ratio = (float)sm.s_n_chunks[t] / (float)nch[t];
+        if (ratio > best_ratio) { best_ratio = ratio; best = t; }
+      }
+      if (best < 0) break;
+      used += nch[best]; nch[best] *= 2;
+    }
+    int base = 0;
+    for (int t = 0; t < kT; ++t) { sm.s_ring_base[t] = base; sm.s_ring_nch[t] = nch[t] ? nch[t] : 2; base += nch[t]; }
+  }
+  __syncthreads();
+
+  // ---- CTA-uniform per-slot registers
+  int32_t r_cur[kT], rbase[kT], rmask[kT], khalf[kT];
 #pragma unroll
-  for (int t = 0; t < kT; ++t) r_cur[t] = sm.s_r_begin[t];
+  for (int t = 0; t < kT; ++t) {
+    r_cur[t] = sm.s_r_begin[t];
+    rbase[t] = sm.s_ring_base[t] << kLogCH;
+    rmask[t] = (sm.s_ring_nch[t] << kLogCH) - 1;
+    khalf[t] = sm.s_ring_nch[t] >> 1;
+  }
   auto issue_chunks = [&]() {  // thread 0 only: fill every free ring slot
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
-      const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + kNCH);
+      const int nch = sm.s_ring_nch[t];
+      const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + nch);
       int j = sm.s_issued[t];
       for (; j < lim; ++j) {
-        uint64_t* bar = &sm.full_bar[t][j & (kNCH - 1)];
+        const int slot = sm.s_ring_base[t] + (j & (nch - 1));
+        uint64_t* bar = &sm.full_bar[slot];
         mbar_arrive_expect_tx(bar, kChunkBytes);
-        bulk_g2s(&sm.ring_docs[t][(j & (kNCH - 1)) << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
-        bulk_g2s(&sm.ring_f8[t][(j & (kNCH - 1)) << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
+        bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
+        bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
       }
       sm.s_issued[t] = j;
     }
@@ -343,9 +370,10 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   for (int i = tid; i < kT * kTfTab * 256; i += kThreads) {
     const int s = i / (kTfTab * 256), tf = (i / 256) % kTfTab + 1, nb = i & 255;
     float v = 0.0f;
-    for (int c = 0; c < ncl; ++c)
-      if (sm.cl[c].kind == NRTGPU_TERM && sm.cl[c].slot == s)
-        v = bm25_score(sm.cl[c].weight, (float)tf, __ldg(&L.ix.caches[sm.cl[c].field * 256 + nb]));
+    if (s < n_term) {
+      const DevClause& c = sm.cl[sm.s_clause[s]];
+      v = bm25_score(c.weight, (float)tf, __ldg(&L.ix.caches[c.field * 256 + nb]));
+    }
     sm.tbl[s][tf - 1][nb] = v;
   }
   __syncthreads();
@@ -365,20 +393,32 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   fq.single_field = sm.q.single_field >= 0;
   fq.norms0 = fq.single_field ? L.ix.norms[sm.q.single_field] : nullptr;
   fq.has_nonterm = sm.q.has_nonterm != 0; fq.generic = sm.q.nonterm_scoring != 0; fq.has_live = L.ix.live_bits != nullptr;
-  unsigned long long my_hits = 0;
+  uint32_t scoring_bits = 0;
+#pragma unroll
+  for (int t = 0; t < kT; ++t) scoring_bits |= (sm.s_scoring[t] ? 1u : 0u) << t;
+  // word bytes of the driver slots below each slot (ownership test)
+  uint32_t below[kT];
+#pragma unroll
+  for (int t = 0; t < kT; ++t) {
+    below[t] = 0;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below[t] |= 0xffu << (8 * j);
+  }
+  unsigned int warp_hits = 0;   // lane 0 of every warp
   int cand_ub = 0;
-  int32_t wpos = slice_base;  // dense mode: next doc to visit
+  int32_t wpos = slice_base;
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
   auto offer = [&](bool matched, int32_t doc, float score) {
     bool is_cand = false;
     uint64_t key = 0;
     if (matched) {
-      ++my_hits;
       key = make_key(score, doc);
       is_cand = key > sm.theta && (!has_after || key < after_key);
     }
-    unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+    const unsigned mb = __ballot_sync(0xffffffffu, matched);
+    warp_hits += __popc(mb);
+    const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
     if (bal) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&sm.cand_count, __popc(bal));
@@ -396,69 +436,73 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
     }
   };
 
-  for (int w = 0;; ++w) {
-    // ---------------- A/B: residency + window bounds (every thread computes the same values)
-    int32_t avail_end[kT];
+  for (;;) {
+    // ---------------- residency + window bounds (every thread computes the same values)
+    int32_t avail[kT];   // resident postings at and after r_cur
     int32_t wbase = INT32_MAX, wlimit = INT32_MAX;
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
-      avail_end[t] = r_cur[t];
+      avail[t] = 0;
       const int32_t r_end = sm.s_r_end[t];
       if (t < n_term && r_cur[t] < r_end) {
         const int jc = r_cur[t] >> kLogCH;
-        mbar_wait(&sm.full_bar[t][jc & (kNCH - 1)], (jc / kNCH) & 1);
-        if (jc + 1 < sm.s_n_chunks[t]) mbar_wait(&sm.full_bar[t][(jc + 1) & (kNCH - 1)], ((jc + 1) / kNCH) & 1);
-        avail_end[t] = min(r_end, (jc + 2) << kLogCH);
-        wbase = min(wbase, sm.ring_docs[t][r_cur[t] & kRingMask]);
-        if (avail_end[t] < r_end) wlimit = min(wlimit, sm.ring_docs[t][(avail_end[t] - 1) & kRingMask] + 1);
+        const int nch_mask = (rmask[t] >> kLogCH);
+        const int jl = min(sm.s_n_chunks[t], jc + khalf[t]);   // wait for chunks [jc, jl)
+        for (int j = jc; j < jl; ++j)
+          mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
+        const int32_t avail_end = min(r_end, jl << kLogCH);
+        avail[t] = avail_end - r_cur[t];
+        wbase = min(wbase, sm.pool_docs[rbase[t] + (r_cur[t] & rmask[t])]);
+        if (avail_end < r_end) wlimit = min(wlimit, sm.pool_docs[rbase[t] + ((avail_end - 1) & rmask[t])] + 1);
       }
     }
     if (dense) wbase = wpos;
-    if (wbase >= slice_end) break;  // every list exhausted (or dense sweep finished)
+    if (wbase >= slice_end) break;   // every list exhausted (or the dense sweep finished)
     int32_t wend = (slice_end - wbase > kW) ? wbase + kW : slice_end;
     wend = min(wend, wlimit);
-    // postings of every list inside [wbase, wend): 2-step 32-ary search by every (converged) warp
+    // postings of every list inside [wbase, wend)
     int32_t cnt[kT];
 #pragma unroll
     for (int t = 0; t < kT; ++t)
-      cnt[t] = (t < n_term) ? warp_lower_bound(sm.ring_docs[t], r_cur[t], avail_end[t] - r_cur[t], wend, lane) : 0;
-    // ---------------- pass 1: scatter tf bytes
-#pragma unroll
-    for (int t = 0; t < kT; ++t) {
-      if (t >= n_term) break;
-      const bool scoring = sm.s_scoring[t] != 0;
-      const int32_t r1 = r_cur[t] + cnt[t];
-      for (int32_t r = r_cur[t] + tid; r < r1; r += kThreads) {
-        const int32_t doc = sm.ring_docs[t][r & kRingMask];
-        slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.ring_f8[t][r & kRingMask] : (unsigned char)1;
+      cnt[t] = (t < n_term && avail[t] > 0) ? warp_lower_bound(sm.pool_docs + rbase[t], rmask[t], r_cur[t], avail[t], wend, lane) : 0;
+
+    // ---------------- pass 1: scatter tf bytes (one flattened loop over all clauses)
+    {
+      const int32_t e0 = cnt[0], e1 = e0 + cnt[1], e2 = e1 + cnt[2], e3 = e2 + cnt[3];
+      for (int32_t i = tid; i < e3; i += kThreads) {
+        int idx, t;
+        if (i < e0) { t = 0; idx = rbase[0] + ((r_cur[0] + i) & rmask[0]); }
+        else if (i < e1) { t = 1; idx = rbase[1] + ((r_cur[1] + i - e0) & rmask[1]); }
+        else if (i < e2) { t = 2; idx = rbase[2] + ((r_cur[2] + i - e1) & rmask[2]); }
+        else { t = 3; idx = rbase[3] + ((r_cur[3] + i - e2) & rmask[3]); }
+        const int32_t doc = sm.pool_docs[idx];
+        const unsigned char f = ((scoring_bits >> t) & 1u) ? sm.pool_f8[idx] : (unsigned char)1;
+        slot_bytes[(size_t)(doc - wbase) * 4 + t] = f;
       }
     }
     __syncthreads();
-    // ---------------- pass 2: emit
+    // ---------------- pass 2: emit (flattened over the driver clauses)
     if (!dense) {
-#pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        if (t >= n_term) break;
-        if (!((driver_mask >> t) & 1u)) continue;
-        uint32_t below = 0;
-#pragma unroll
-        for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below |= 0xffu << (8 * j);
-        const uint32_t own = 0xffu << (8 * t);
-        const int32_t r1 = r_cur[t] + cnt[t];
-        for (int32_t r0 = r_cur[t]; r0 < r1; r0 += kThreads) {
-          const int32_t r = r0 + tid;
-          bool matched = false; int32_t doc = 0; float score = 0.0f;
-          if (r < r1) {
-            doc = sm.ring_docs[t][r & kRingMask];
-            const uint32_t v = sm.slots[doc - wbase];
-            if ((v & below) == 0 && (v & own) != 0) {
-              sm.slots[doc - wbase] = 0u;
-              matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
-            }
+      const int32_t d0 = (driver_mask & 1u) ? cnt[0] : 0, d1 = d0 + ((driver_mask & 2u) ? cnt[1] : 0),
+                    d2 = d1 + ((driver_mask & 4u) ? cnt[2] : 0), d3 = d2 + ((driver_mask & 8u) ? cnt[3] : 0);
+      for (int32_t i0 = 0; i0 < d3; i0 += kThreads) {
+        const int32_t i = i0 + tid;
+        bool matched = false; int32_t doc = 0; float score = 0.0f;
+        if (i < d3) {
+          int idx; uint32_t bl, own;
+          if (i < d0) { idx = rbase[0] + ((r_cur[0] + i) & rmask[0]); bl = below[0]; own = 0xffu; }
+          else if (i < d1) { idx = rbase[1] + ((r_cur[1] + i - d0) & rmask[1]); bl = below[1]; own = 0xff00u; }
+          else if (i < d2) { idx = rbase[2] + ((r_cur[2] + i - d1) & rmask[2]); bl = below[2]; own = 0xff0000u; }
+          else { idx = rbase[3] + ((r_cur[3] + i - d2) & rmask[3]); bl = below[3]; own = 0xff000000u; }
+          doc = sm.pool_docs[idx];
+          const uint32_t v = sm.slots[doc - wbase];
+          if ((v & bl) == 0 && (v & own) != 0) {
+            sm.slots[doc - wbase] = 0u;
+            matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
           }
-          offer(matched, doc, score);
-          round_end();
         }
+        offer(matched, doc, score);
+        round_end();
       }
     } else {
       const int32_t wlen = wend - wbase;
@@ -481,8 +525,8 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
       for (int t = 0; t < kT; ++t) {
         if (t >= n_term) break;
         if ((driver_mask >> t) & 1u) continue;
-        const int32_t r1 = r_cur[t] + cnt[t];
-        for (int32_t r = r_cur[t] + tid; r < r1; r += kThreads) sm.slots[sm.ring_docs[t][r & kRingMask] - wbase] = 0u;
+        for (int32_t i = tid; i < cnt[t]; i += kThreads)
+          sm.slots[sm.pool_docs[rbase[t] + ((r_cur[t] + i) & rmask[t])] - wbase] = 0u;
       }
       __syncthreads();
     }
@@ -499,8 +543,7 @@ __global__ void __launch_bounds__(kThreads, 2) posting_stream_kernel(StreamLaunc
   uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
   for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
   if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
-  for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
-  if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], my_hits);
+  if (lane == 0 && warp_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)warp_hits);
 }
 
 // posting index of the first posting with doc >= slice start, for every (query, term slot, slice boundary)
