@@ -100,10 +100,14 @@ __device__ __noinline__ float term_score_slow(const StreamLaunch& L, const Strea
   return bm25_score(c.weight, f, __ldg(&L.ix.caches[c.field * 256 + nb]));
 }
 
-// Generic evaluation (queries whose range / match-all clauses score): clause-order loop, same as v1.
+// Universal (slow-path) evaluation: any clause mix, any tf, deleted docs. Clause-order double sums, exactly as v1.
 __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t slot,
                                                   float* out_score) {
   const DevQuery& q = sm.q;
+  const uint32_t m = presence4(slot);
+  if ((m & q.req_term_mask) != q.req_term_mask) return false;
+  if (m & q.not_term_mask) return false;
+  if (L.ix.live_bits && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
   double must_sum = 0.0, should_sum = 0.0;
   int n_should = 0;
   int cur_field = -1;
@@ -161,64 +165,32 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
   return true;
 }
 
-// non-scoring range / match-all clauses (FILTER / MUST_NOT) as predicates
-__device__ __noinline__ bool nonterm_filters_pass(const StreamLaunch& L, const StreamSmem& sm, int32_t doc) {
-  const DevQuery& q = sm.q;
-  for (int i = 0; i < q.n_clauses; ++i) {
-    const DevClause& c = sm.cl[i];
-    if (c.kind == NRTGPU_TERM) continue;
-    bool present = true;
-    if (c.kind == NRTGPU_RANGE_I64) {
-      const uint8_t* has = L.ix.col_has[c.col];
-      present = !has || has[doc];
-      if (present) {
-        int64_t v = L.ix.col32[c.col] ? (int64_t)__ldg(L.ix.col32[c.col] + doc) : __ldg(L.ix.col64[c.col] + doc);
-        present = (v >= c.lo) && (v <= c.hi);
-      }
-    }
-    if (c.occur == NRTGPU_MUST_NOT ? present : !present) return false;
-  }
-  return true;
-}
-
-// Per-CTA constants of the fast path (term clauses only contribute to the score)
+// Per-CTA constants of the fast path: term clauses of ONE text field only, no deleted docs, tf <= kTfTab.
 struct FastQ {
   uint32_t req_mask, not_mask, must_mask, should_mask;
   int32_t need_should, n_req, msm;
-  const uint8_t* norms0;       // single-field norms (may be NULL = omitNorms)
-  bool single_field, has_nonterm, generic, has_live;
+  const uint8_t* norms0;   // norms of the single field (NULL = omitNorms)
+  bool fast;               // false: every doc goes through evaluate_doc_generic
 };
 
 // boolean constraints + exact score of one doc from its window word. Clause sums are double in slot
 // (= clause) order; required+optional combine as Lucene's ReqOptSumScorer / ConjunctionScorer.
 __device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const StreamSmem& sm, const FastQ& fq, int32_t doc,
                                                 uint32_t slot, float* out_score) {
-  const uint32_t m = presence4(slot);
-  if ((m & fq.req_mask) != fq.req_mask) return false;
-  if (m & fq.not_mask) return false;
+  if (!fq.fast) return evaluate_doc_generic(L, sm, doc, slot, out_score);
+  const uint32_t b0 = slot & 0xffu, b1 = (slot >> 8) & 0xffu, b2 = (slot >> 16) & 0xffu, b3 = slot >> 24;
+  const uint32_t m = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
+  if ((m & fq.req_mask) != fq.req_mask || (m & fq.not_mask)) return false;
   const int n_should = __popc(m & fq.should_mask);
-  if (fq.has_live && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
-  if (fq.generic) return evaluate_doc_generic(L, sm, doc, slot, out_score);
   if (n_should < fq.need_should) return false;
-  if (fq.has_nonterm && !nonterm_filters_pass(L, sm, doc)) return false;
-  uint32_t nb0 = 1u;
-  if (fq.single_field && fq.norms0) nb0 = (uint32_t)__ldg(fq.norms0 + doc);
+  if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) return evaluate_doc_generic(L, sm, doc, slot, out_score);
+  const uint32_t nb = fq.norms0 ? (uint32_t)__ldg(fq.norms0 + doc) : 1u;
   double must_sum = 0.0, should_sum = 0.0;
-#pragma unroll
-  for (int t = 0; t < kT; ++t) {
-    const uint32_t b = (slot >> (8 * t)) & 0xffu;
-    if (b != 0 && (((fq.must_mask | fq.should_mask) >> t) & 1u)) {
-      uint32_t nb = nb0;
-      if (!fq.single_field) {
-        const uint8_t* nrm = L.ix.norms[sm.s_field[t]];
-        nb = nrm ? (uint32_t)__ldg(nrm + doc) : 1u;
-      }
-      float s;
-      if (b <= (uint32_t)kTfTab) s = sm.tbl[t][b - 1][nb];
-      else s = term_score_slow(L, sm, sm.cl[sm.s_clause[t]], doc, b, nb);
-      if ((fq.must_mask >> t) & 1u) must_sum += (double)s; else should_sum += (double)s;
-    }
-  }
+  const uint32_t sc = fq.must_mask | fq.should_mask;
+  if (b0 && (sc & 1u)) { const double s = (double)sm.tbl[0][b0 - 1][nb]; if (fq.must_mask & 1u) must_sum += s; else should_sum += s; }
+  if (b1 && (sc & 2u)) { const double s = (double)sm.tbl[1][b1 - 1][nb]; if (fq.must_mask & 2u) must_sum += s; else should_sum += s; }
+  if (b2 && (sc & 4u)) { const double s = (double)sm.tbl[2][b2 - 1][nb]; if (fq.must_mask & 4u) must_sum += s; else should_sum += s; }
+  if (b3 && (sc & 8u)) { const double s = (double)sm.tbl[3][b3 - 1][nb]; if (fq.must_mask & 8u) must_sum += s; else should_sum += s; }
   float score;
   if (fq.n_req == 0) score = (float)should_sum;
   else {
@@ -232,6 +204,7 @@ __device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const Str
   *out_score = score;
   return true;
 }
+
 
 // first index i in [0, n) with ring[(r0+i) & mask] >= bound, else n; executed by a converged warp
 // (32-ary search: <= 3 ballot rounds for n <= 32768)
@@ -390,9 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   fq.req_mask = sm.q.req_term_mask; fq.not_mask = sm.q.not_term_mask;
   fq.must_mask = sm.q.must_term_mask; fq.should_mask = sm.q.should_term_mask;
   fq.need_should = sm.q.need_should; fq.n_req = sm.q.n_req; fq.msm = sm.q.msm;
-  fq.single_field = sm.q.single_field >= 0;
-  fq.norms0 = fq.single_field ? L.ix.norms[sm.q.single_field] : nullptr;
-  fq.has_nonterm = sm.q.has_nonterm != 0; fq.generic = sm.q.nonterm_scoring != 0; fq.has_live = L.ix.live_bits != nullptr;
+  fq.fast = sm.q.single_field >= 0 && !sm.q.has_nonterm && !sm.q.nonterm_scoring && L.ix.live_bits == nullptr;
+  fq.norms0 = (sm.q.single_field >= 0) ? L.ix.norms[sm.q.single_field] : nullptr;
   uint32_t scoring_bits = 0;
 #pragma unroll
   for (int t = 0; t < kT; ++t) scoring_bits |= (sm.s_scoring[t] ? 1u : 0u) << t;
@@ -404,37 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
 #pragma unroll
     for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below[t] |= 0xffu << (8 * j);
   }
-  unsigned int warp_hits = 0;   // lane 0 of every warp
-  int cand_ub = 0;
+  unsigned int my_hits = 0;
   int32_t wpos = slice_base;
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
-
-  auto offer = [&](bool matched, int32_t doc, float score) {
-    bool is_cand = false;
-    uint64_t key = 0;
-    if (matched) {
-      key = make_key(score, doc);
-      is_cand = key > sm.theta && (!has_after || key < after_key);
-    }
-    const unsigned mb = __ballot_sync(0xffffffffu, matched);
-    warp_hits += __popc(mb);
-    const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-    if (bal) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&sm.cand_count, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_cand) sm.cand[base + __popc(bal & ((1u << lane) - 1))] = key;
-    }
-  };
-  auto round_end = [&]() {
-    cand_ub += kThreads;
-    if (cand_ub > kCand - kThreads) {
-      __syncthreads();
-      int n = sm.cand_count;
-      if (n > kCand - kThreads) { compact_candidates_v2(sm, L.top_k, &L.theta[qi]); n = sm.cand_count; }
-      cand_ub = n;
-    }
-  };
 
   for (;;) {
     // ---------------- residency + window bounds (every thread computes the same values)
@@ -447,9 +391,11 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
       if (t < n_term && r_cur[t] < r_end) {
         const int jc = r_cur[t] >> kLogCH;
         const int nch_mask = (rmask[t] >> kLogCH);
-        const int jl = min(sm.s_n_chunks[t], jc + khalf[t]);   // wait for chunks [jc, jl)
-        for (int j = jc; j < jl; ++j)
-          mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
+        const int jl = min(sm.s_n_chunks[t], jc + khalf[t]);   // chunks [jc, jl) must be resident (<= 16)
+        // every warp waits for all of them: lane l polls chunk jc + l, then the warp re-converges
+        const int j = jc + lane;
+        if (j < jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
+        __syncwarp();
         const int32_t avail_end = min(r_end, jl << kLogCH);
         avail[t] = avail_end - r_cur[t];
         wbase = min(wbase, sm.pool_docs[rbase[t] + (r_cur[t] & rmask[t])]);
@@ -466,59 +412,83 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     for (int t = 0; t < kT; ++t)
       cnt[t] = (t < n_term && avail[t] > 0) ? warp_lower_bound(sm.pool_docs + rbase[t], rmask[t], r_cur[t], avail[t], wend, lane) : 0;
 
-    // ---------------- pass 1: scatter tf bytes (one flattened loop over all clauses)
-    {
-      const int32_t e0 = cnt[0], e1 = e0 + cnt[1], e2 = e1 + cnt[2], e3 = e2 + cnt[3];
-      for (int32_t i = tid; i < e3; i += kThreads) {
-        int idx, t;
-        if (i < e0) { t = 0; idx = rbase[0] + ((r_cur[0] + i) & rmask[0]); }
-        else if (i < e1) { t = 1; idx = rbase[1] + ((r_cur[1] + i - e0) & rmask[1]); }
-        else if (i < e2) { t = 2; idx = rbase[2] + ((r_cur[2] + i - e1) & rmask[2]); }
-        else { t = 3; idx = rbase[3] + ((r_cur[3] + i - e2) & rmask[3]); }
+    // ---------------- pass 1: scatter tf bytes
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      if (t >= n_term) break;
+      const bool scoring = (scoring_bits >> t) & 1u;
+      for (int32_t i = tid; i < cnt[t]; i += kThreads) {
+        const int idx = rbase[t] + ((r_cur[t] + i) & rmask[t]);
         const int32_t doc = sm.pool_docs[idx];
-        const unsigned char f = ((scoring_bits >> t) & 1u) ? sm.pool_f8[idx] : (unsigned char)1;
-        slot_bytes[(size_t)(doc - wbase) * 4 + t] = f;
+        slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.pool_f8[idx] : (unsigned char)1;
       }
     }
     __syncthreads();
-    // ---------------- pass 2: emit (flattened over the driver clauses)
-    if (!dense) {
-      const int32_t d0 = (driver_mask & 1u) ? cnt[0] : 0, d1 = d0 + ((driver_mask & 2u) ? cnt[1] : 0),
-                    d2 = d1 + ((driver_mask & 4u) ? cnt[2] : 0), d3 = d2 + ((driver_mask & 8u) ? cnt[3] : 0);
-      for (int32_t i0 = 0; i0 < d3; i0 += kThreads) {
-        const int32_t i = i0 + tid;
-        bool matched = false; int32_t doc = 0; float score = 0.0f;
-        if (i < d3) {
-          int idx; uint32_t bl, own;
-          if (i < d0) { idx = rbase[0] + ((r_cur[0] + i) & rmask[0]); bl = below[0]; own = 0xffu; }
-          else if (i < d1) { idx = rbase[1] + ((r_cur[1] + i - d0) & rmask[1]); bl = below[1]; own = 0xff00u; }
-          else if (i < d2) { idx = rbase[2] + ((r_cur[2] + i - d1) & rmask[2]); bl = below[2]; own = 0xff0000u; }
-          else { idx = rbase[3] + ((r_cur[3] + i - d2) & rmask[3]); bl = below[3]; own = 0xff000000u; }
-          doc = sm.pool_docs[idx];
-          const uint32_t v = sm.slots[doc - wbase];
-          if ((v & bl) == 0 && (v & own) != 0) {
-            sm.slots[doc - wbase] = 0u;
-            matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
+    // ---------------- pass 2: owners emit. No barrier inside: a thread whose candidate does not fit the
+    // buffer parks it (pending) and stops; the CTA then compacts and the parked threads resume.
+    {
+      int32_t it[kT];
+#pragma unroll
+      for (int t = 0; t < kT; ++t) it[t] = tid;
+      int32_t idense = tid;
+      bool pending = false;
+      uint64_t pkey = 0;
+      for (;;) {
+        const unsigned long long theta = sm.theta;
+        if (pending) {
+          pending = false;
+          if (pkey > theta) {
+            const int p = atomicAdd(&sm.cand_count, 1);
+            if (p < kCand) sm.cand[p] = pkey; else pending = true;
           }
         }
-        offer(matched, doc, score);
-        round_end();
-      }
-    } else {
-      const int32_t wlen = wend - wbase;
-      for (int32_t i0 = 0; i0 < wlen; i0 += kThreads) {
-        const int32_t i = i0 + tid;
-        bool matched = false; const int32_t doc = wbase + i; float score = 0.0f;
-        if (i < wlen) {
-          const uint32_t v = sm.slots[i];
-          if (v) sm.slots[i] = 0u;
-          matched = evaluate_doc_v2(L, sm, fq, doc, v, &score);
+        if (!pending) {
+          if (!dense) {
+#pragma unroll
+            for (int t = 0; t < kT; ++t) {
+              if (t >= n_term || pending) break;
+              if (!((driver_mask >> t) & 1u)) continue;
+              const uint32_t own = 0xffu << (8 * t);
+              for (int32_t i = it[t]; i < cnt[t]; i += kThreads) {
+                const int32_t doc = sm.pool_docs[rbase[t] + ((r_cur[t] + i) & rmask[t])];
+                const uint32_t v = sm.slots[doc - wbase];
+                if ((v & below[t]) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
+                sm.slots[doc - wbase] = 0u;
+                float score;
+                if (!evaluate_doc_v2(L, sm, fq, doc, v, &score)) continue;
+                ++my_hits;
+                const uint64_t key = make_key(score, doc);
+                if (key > theta && (!has_after || key < after_key)) {
+                  const int p = atomicAdd(&sm.cand_count, 1);
+                  if (p < kCand) sm.cand[p] = key;
+                  else { pending = true; pkey = key; it[t] = i + kThreads; break; }
+                }
+              }
+              if (!pending) it[t] = cnt[t];
+            }
+          } else {
+            const int32_t wlen = wend - wbase;
+            for (int32_t i = idense; i < wlen; i += kThreads) {
+              const uint32_t v = sm.slots[i];
+              if (v) sm.slots[i] = 0u;
+              float score;
+              if (!evaluate_doc_v2(L, sm, fq, wbase + i, v, &score)) continue;
+              ++my_hits;
+              const uint64_t key = make_key(score, wbase + i);
+              if (key > theta && (!has_after || key < after_key)) {
+                const int p = atomicAdd(&sm.cand_count, 1);
+                if (p < kCand) sm.cand[p] = key;
+                else { pending = true; pkey = key; idense = i + kThreads; break; }
+              }
+            }
+            if (!pending) idense = wlen;
+          }
         }
-        offer(matched, doc, score);
-        round_end();
+        __syncthreads();
+        if (sm.cand_count <= kCand) break;                 // nobody is parked
+        compact_candidates_v2(sm, L.top_k, &L.theta[qi]);  // raises theta, frees the buffer
       }
     }
-    __syncthreads();
     // ---------------- pass 3: clear the words pass 2 did not visit
     if (!dense && has_non_driver) {
 #pragma unroll
@@ -543,7 +513,8 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
   for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
   if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
-  if (lane == 0 && warp_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)warp_hits);
+  for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
+  if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
 }
 
 // posting index of the first posting with doc >= slice start, for every (query, term slot, slice boundary)
