@@ -127,7 +127,8 @@ struct nrtgpu_batch {
   DevBuf<DevClause> clauses;
   DevBuf<DevQuery> queries;
   DevBuf<int32_t> work_query, work_slice;
-  DevBuf<int64_t> bounds;   // v2: [nq][4][n_slices+1]
+  DevBuf<uint32_t> gbounds;  // stream kernel: [nq][4][n_gran+1]
+  int32_t n_gran = 0;
   DevBuf<uint64_t> theta;
   DevBuf<unsigned long long> total_hits;
   DevBuf<uint64_t> slice_keys;
@@ -433,13 +434,15 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
   if (!b->wide_slots) {
-    // v2 streams each list from its slice start: one lower_bound per (query, term slot, slice boundary)
-    if ((rc = b->bounds.alloc((size_t)nq * v2::kT * (b->n_slices + 1)))) return rc;
+    // the stream kernel reads per-granule posting bounds of every (query, term clause): one lower_bound each
+    b->n_gran = (int32_t)(((int64_t)ix->n_docs + v2::kGran - 1) / v2::kGran);
+    if (b->n_gran < 1) b->n_gran = 1;
+    const int64_t total = (int64_t)nq * v2::kT * (b->n_gran + 1);
+    if ((rc = b->gbounds.alloc((size_t)total))) return rc;
     v2::BoundsLaunch B;
-    B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_slices = b->n_slices;
-    B.slice_docs = (int32_t)slice_docs; B.bounds = b->bounds.p;
-    int total = nq * v2::kT * (b->n_slices + 1);
-    v2::slice_bounds_kernel<<<(total + 127) / 128, 128>>>(B);
+    B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_gran = b->n_gran;
+    B.gbounds = b->gbounds.p;
+    v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256>>>(B);
     NRT_CUDA_TRY(cudaGetLastError());
     NRT_CUDA_TRY(cudaDeviceSynchronize());
   }
@@ -468,7 +471,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     if (!b->wide_slots) {
       v2::StreamLaunch S;
       S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
-      S.bounds = b->bounds.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
+      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
       S.slice_docs = kSliceWindows * kWindowDocs;
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
       v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);

@@ -25,6 +25,10 @@ constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
 constexpr int kThreads = 768;         // one CTA per SM
 constexpr int kCand = 2048;
 constexpr int kTfTab = 4;
+constexpr int kLogGran = 11;          // posting bounds are precomputed per (query, clause) at 2048-doc granules
+constexpr int kGran = 1 << kLogGran;
+constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
+constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
 constexpr uint32_t kAll = 0xffffffffu;
 
@@ -34,7 +38,8 @@ struct StreamLaunch {
   const DevQuery* queries;
   const int32_t* work_query;
   const int32_t* work_slice;
-  const int64_t* bounds;     // [nq][kT][n_slices+1] global posting index of the first posting with doc >= slice start
+  const uint32_t* gbounds;   // [nq][kT][n_gran+1]: postings of the clause with doc < g*kGran (relative to post_base)
+  int32_t n_gran;
   int32_t n_work, n_slices, top_k;
   int32_t slice_docs;
   uint64_t* theta;
@@ -50,6 +55,7 @@ struct alignas(128) StreamSmem {
   uint64_t cand[kCand];            // 16 KB
   float tbl[kT][kTfTab][256];      // 16 KB
   uint64_t full_bar[kPool];
+  uint32_t gb[kT][kSliceWindows * kWindowDocs / kGran + 1];   // granule bounds of this slice
   DevClause cl[kMaxClauses];
   DevQuery q;
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
@@ -62,6 +68,8 @@ struct alignas(128) StreamSmem {
   int cand_count;
   unsigned long long theta;
 };
+
+static_assert(sizeof(StreamSmem) <= 232448, "StreamSmem exceeds the 227 KB per-CTA shared memory of sm_100");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -277,10 +285,22 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
                   sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
                   sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; }
   __syncthreads();
+  const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
+  const int g_first = slice * gran_per_slice;
+  const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
+  for (int i = tid; i < kT * (gran_per_slice + 1); i += kThreads) {
+    const int t = i / (gran_per_slice + 1), g = i % (gran_per_slice + 1);
+    uint32_t v = 0;
+    if (t < n_term) {
+      const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
+      v = p[min(g, g_count)];
+    }
+    sm.gb[t][g] = v;
+  }
+  __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
-    const int64_t* bp = L.bounds + ((size_t)qi * kT + s) * (L.n_slices + 1) + slice;
-    const int64_t g0 = bp[0], g1 = bp[1];
+    const int64_t g0 = sm.cl[tid].post_base + sm.gb[s][0], g1 = sm.cl[tid].post_base + sm.gb[s][g_count];
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
@@ -296,7 +316,11 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     // split the ring pool: every list starts with 2 chunks; the list with the most chunks still to
     // stream per ring chunk is doubled while the pool allows (dense lists get long rings)
     int nch[kT], used = 0;
-    for (int t = 0; t < kT; ++t) { nch[t] = (t < n_term) ? 2 : 0; used += nch[t]; }
+    for (int t = 0; t < kT; ++t) {
+      nch[t] = 0;
+      if (t < n_term) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
+      used += nch[t];
+    }
     for (;;) {
       int best = -1; float best_ratio = 0.5f;
       for (int t = 0; t < n_term; ++t) {
@@ -313,13 +337,12 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   __syncthreads();
 
   // ---- CTA-uniform per-slot registers
-  int32_t r_cur[kT], rbase[kT], rmask[kT], khalf[kT];
+  int32_t r_cur[kT], rbase[kT], rmask[kT];
 #pragma unroll
   for (int t = 0; t < kT; ++t) {
     r_cur[t] = sm.s_r_begin[t];
     rbase[t] = sm.s_ring_base[t] << kLogCH;
     rmask[t] = (sm.s_ring_nch[t] << kLogCH) - 1;
-    khalf[t] = sm.s_ring_nch[t] >> 1;
   }
   auto issue_chunks = [&]() {  // thread 0 only: fill every free ring slot
 #pragma unroll
@@ -377,40 +400,44 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below[t] |= 0xffu << (8 * j);
   }
   unsigned int my_hits = 0;
-  int32_t wpos = slice_base;
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
+  int g0 = 0;   // next granule of the slice
   for (;;) {
-    // ---------------- residency + window bounds (every thread computes the same values)
-    int32_t avail[kT];   // resident postings at and after r_cur
-    int32_t wbase = INT32_MAX, wlimit = INT32_MAX;
-#pragma unroll
-    for (int t = 0; t < kT; ++t) {
-      avail[t] = 0;
-      const int32_t r_end = sm.s_r_end[t];
-      if (t < n_term && r_cur[t] < r_end) {
-        const int jc = r_cur[t] >> kLogCH;
-        const int nch_mask = (rmask[t] >> kLogCH);
-        const int jl = min(sm.s_n_chunks[t], jc + khalf[t]);   // chunks [jc, jl) must be resident (<= 16)
-        // every warp waits for all of them: lane l polls chunk jc + l, then the warp re-converges
-        const int j = jc + lane;
-        if (j < jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
-        __syncwarp();
-        const int32_t avail_end = min(r_end, jl << kLogCH);
-        avail[t] = avail_end - r_cur[t];
-        wbase = min(wbase, sm.pool_docs[rbase[t] + (r_cur[t] & rmask[t])]);
-        if (avail_end < r_end) wlimit = min(wlimit, sm.pool_docs[rbase[t] + ((avail_end - 1) & rmask[t])] + 1);
-      }
-    }
-    if (dense) wbase = wpos;
-    if (wbase >= slice_end) break;   // every list exhausted (or the dense sweep finished)
-    int32_t wend = (slice_end - wbase > kW) ? wbase + kW : slice_end;
-    wend = min(wend, wlimit);
-    // postings of every list inside [wbase, wend)
+    if (g0 >= g_count) break;
+    // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
+    int g1 = g0;
     int32_t cnt[kT];
 #pragma unroll
-    for (int t = 0; t < kT; ++t)
-      cnt[t] = (t < n_term && avail[t] > 0) ? warp_lower_bound(sm.pool_docs + rbase[t], rmask[t], r_cur[t], avail[t], wend, lane) : 0;
+    for (int t = 0; t < kT; ++t) cnt[t] = 0;
+    {
+      const int gmax = min(g_count, g0 + kWinGran);
+      for (int g = g0 + 1; g <= gmax; ++g) {
+        bool fits = true;
+#pragma unroll
+        for (int t = 0; t < kT; ++t) fits = fits && (int32_t)(sm.gb[t][g] - sm.gb[t][g0]) <= rmask[t] + 1 - kCH;
+        if (!fits) break;
+        g1 = g;
+      }
+      // a single granule always fits (<= 2048 postings, ring >= kMinNCH chunks or the whole list)
+#pragma unroll
+      for (int t = 0; t < kT; ++t) cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
+    }
+    const int32_t wbase = slice_base + (g0 << kLogGran);
+    const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
+    g0 = g1;
+    if (!dense && (cnt[0] | cnt[1] | cnt[2] | cnt[3]) == 0) continue;   // nothing in these granules
+    // ---------------- residency: every warp waits for the chunks that hold [r_cur, r_cur + cnt)
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      if (t < n_term && cnt[t] > 0) {
+        const int jc = r_cur[t] >> kLogCH, jl = (r_cur[t] + cnt[t] - 1) >> kLogCH;   // chunks [jc, jl] (<= 32)
+        const int nch_mask = (rmask[t] >> kLogCH);
+        const int j = jc + lane;
+        if (j <= jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
+      }
+    }
+    __syncwarp();
 
     // ---------------- pass 1: scatter tf bytes
 #pragma unroll
@@ -503,7 +530,6 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     // ---------------- advance the streams, refill freed ring slots
 #pragma unroll
     for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
-    wpos = wend;
     if (tid == 0) issue_chunks();
   }
 
@@ -517,33 +543,33 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
 }
 
-// posting index of the first posting with doc >= slice start, for every (query, term slot, slice boundary)
+// postings of every (query, term slot) below each 2048-doc granule boundary (relative to the clause's list)
 struct BoundsLaunch {
   DevIndexView ix;
   const DevClause* clauses;
   const DevQuery* queries;
-  int32_t nq, n_slices, slice_docs;
-  int64_t* bounds;  // [nq][kT][n_slices+1]
+  int32_t nq, n_gran;
+  uint32_t* gbounds;  // [nq][kT][n_gran+1]
 };
 
-__global__ void slice_bounds_kernel(BoundsLaunch B) {
-  const int per_q = kT * (B.n_slices + 1);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B.nq * per_q) return;
-  const int q = i / per_q, s = (i % per_q) / (B.n_slices + 1), b = i % (B.n_slices + 1);
+__global__ void granule_bounds_kernel(BoundsLaunch B) {
+  const int64_t per_q = (int64_t)kT * (B.n_gran + 1);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B.nq * per_q) return;
+  const int q = (int)(i / per_q), s = (int)((i % per_q) / (B.n_gran + 1)), g = (int)(i % (B.n_gran + 1));
   const DevQuery dq = B.queries[q];
-  int64_t out = 0;
+  uint32_t out = 0;
   for (int c = 0; c < dq.n_clauses; ++c) {
     const DevClause cl = B.clauses[dq.clause_begin + c];
     if (cl.kind != NRTGPU_TERM || cl.slot != s) continue;
-    int64_t target64 = (int64_t)b * B.slice_docs;
-    int32_t target = target64 > (int64_t)B.ix.n_docs ? B.ix.n_docs : (int32_t)target64;
+    const int64_t target64 = (int64_t)g << kLogGran;
+    const int32_t target = target64 > (int64_t)B.ix.n_docs ? B.ix.n_docs : (int32_t)target64;
     const int32_t* docs = B.ix.post_docs + cl.post_base;
     int lo = 0, hi = cl.n_post;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(docs + mid) < target) lo = mid + 1; else hi = mid; }
-    out = cl.post_base + lo;
+    out = (uint32_t)lo;
   }
-  B.bounds[i] = out;
+  B.gbounds[i] = out;
 }
 
 }  // namespace v2
