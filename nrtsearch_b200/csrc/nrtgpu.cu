@@ -92,6 +92,7 @@ struct nrtgpu_index {
   std::vector<std::unique_ptr<DevBuf<uint8_t>>> norms;
   DevBuf<const uint8_t*> norms_ptrs;
   DevBuf<float> caches;
+  DevBuf<uint8_t> field_min_norm;   // smallest non-zero norm byte per field (0 byte = doc lacks the field)
   std::vector<std::unique_ptr<DevBuf<int64_t>>> col64;
   std::vector<std::unique_ptr<DevBuf<int32_t>>> col32;
   std::vector<std::unique_ptr<DevBuf<uint8_t>>> col_has;
@@ -227,12 +228,19 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
   {
     std::vector<const uint8_t*> ptrs((size_t)d->n_fields, nullptr);
     std::vector<float> caches((size_t)d->n_fields * 256);
+    std::vector<uint8_t> min_norm((size_t)d->n_fields, 1);
     ix->field_has_norms.resize(d->n_fields);
     for (int f = 0; f < d->n_fields; ++f) {
       ix->norms.emplace_back(new DevBuf<uint8_t>);
       const uint8_t* h = d->norms ? d->norms[f] : nullptr;
       ix->field_has_norms[f] = h != nullptr;
-      if (h) { if ((rc = ix->norms.back()->upload(h, (size_t)d->n_docs))) return rc; ptrs[f] = ix->norms.back()->p; }
+      if (h) {
+        if ((rc = ix->norms.back()->upload(h, (size_t)d->n_docs))) return rc;
+        ptrs[f] = ix->norms.back()->p;
+        int mn = 256;
+        for (int32_t i = 0; i < d->n_docs; ++i) if (h[i] != 0 && h[i] < mn) mn = h[i];
+        min_norm[f] = (uint8_t)(mn == 256 ? 0 : mn);
+      }
       float k1 = d->field_k1 ? d->field_k1[f] : 1.2f, b = d->field_b ? d->field_b[f] : 0.75f;
       int64_t dc = d->field_doc_count[f];
       float avgdl = dc > 0 ? (float)((double)d->field_sum_ttf[f] / (double)dc) : 1.0f;
@@ -240,6 +248,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     }
     if ((rc = ix->norms_ptrs.upload(ptrs.data(), ptrs.size()))) return rc;
     if ((rc = ix->caches.upload(caches.data(), caches.size()))) return rc;
+    if ((rc = ix->field_min_norm.upload(min_norm.data(), min_norm.size()))) return rc;
   }
   // numeric doc-value columns (int32 when the value range allows: 4 B/doc gathers)
   {
@@ -471,7 +480,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     if (!b->wide_slots) {
       v2::StreamLaunch S;
       S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
-      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
+      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.field_min_norm = b->ix->field_min_norm.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
       S.slice_docs = kSliceWindows * kWindowDocs;
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
       v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);

@@ -1,15 +1,19 @@
 // posting_stream_kernel -- streaming version of the batched BooleanQuery engine (<= 4 term clauses per query).
 //
 // Same algorithm as bool_window_kernel (scatter tf bytes -> owner emits -> exact top-k, see
-// bool_kernel.cuh) but the posting lists are STREAMED: each term clause owns a ring of kNCH chunks of
-// kCH postings in shared memory, filled by 1-D TMA bulk copies (cp.async.bulk.shared.global with
-// mbarrier complete_tx) issued by one elected thread, so HBM latency is hidden behind the processing
-// of earlier chunks instead of being exposed at every load. Windows are ADAPTIVE: a window spans from
-// the first pending doc to the smallest doc up to which every list is resident (at most kW docs), so a
-// dense list contributes up to two chunks per window and there are no per-window binary searches.
-// Term scores for tf <= kTfTab come from a per-CTA table tbl[clause][tf][norm] of exact BM25 floats
-// (computed once per work item with Lucene's formula), which removes the IEEE division from the
-// per-posting path without changing a single bit of any score.
+// bool_kernel.cuh) but built so that the per-posting instruction count is small:
+//   * posting lists are STREAMED through per-clause rings in shared memory filled by 1-D TMA bulk copies
+//     (cp.async.bulk.shared.global + mbarrier complete_tx, SASS UBLKCP) issued by one elected thread;
+//   * window boundaries come from per-batch granule bounds (granule_bounds_kernel: one lower_bound per
+//     (query, clause, 2048-doc granule)), so the sweep never searches posting data;
+//   * term scores for tf <= kTfTab are read from a per-CTA table tbl[clause][tf][norm] of exact BM25
+//     floats (Lucene's formula evaluated once per work item): no IEEE division per posting;
+//   * for pure disjunctions an upper-bound table ubt[tf pattern] rejects, with one shared-memory load,
+//     every doc whose best possible score is below the running threshold theta (rank-safe: the bound is
+//     the same float expression evaluated at the shortest field length present in the index);
+//   * pass 2 has no barrier inside: a thread whose candidate does not fit the buffer parks it, the CTA
+//     compacts once, and parked threads resume.
+// Results are bit-identical to the exhaustive oracle; totalHits stay exact (every owner is counted).
 #pragma once
 #include "bool_kernel.cuh"
 
@@ -20,17 +24,17 @@ constexpr int kT = 4;
 constexpr int kW = 16384;             // docs per window (one 32-bit word each)
 constexpr int kLogCH = 9;
 constexpr int kCH = 1 << kLogCH;      // postings per chunk
-constexpr int kPool = 48;             // chunks in the CTA's ring pool, shared by the term clauses
+constexpr int kPool = 40;             // chunks in the CTA's ring pool, shared by the term clauses
 constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
-constexpr int kThreads = 768;         // one CTA per SM
+constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
+constexpr int kThreads = 384;         // one CTA per SM
 constexpr int kCand = 2048;
-constexpr int kTfTab = 4;
+constexpr int kTfTab = 4;             // table rows tf = 0..4 (row 0 = 0.0f)
 constexpr int kLogGran = 11;          // posting bounds are precomputed per (query, clause) at 2048-doc granules
 constexpr int kGran = 1 << kLogGran;
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
-constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
+constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
-constexpr uint32_t kAll = 0xffffffffu;
 
 struct StreamLaunch {
   DevIndexView ix;
@@ -39,6 +43,7 @@ struct StreamLaunch {
   const int32_t* work_query;
   const int32_t* work_slice;
   const uint32_t* gbounds;   // [nq][kT][n_gran+1]: postings of the clause with doc < g*kGran (relative to post_base)
+  const uint8_t* field_min_norm;  // [n_fields] norm byte of the shortest field value present (tightest score bound)
   int32_t n_gran;
   int32_t n_work, n_slices, top_k;
   int32_t slice_docs;
@@ -49,13 +54,14 @@ struct StreamLaunch {
 };
 
 struct alignas(128) StreamSmem {
-  int32_t pool_docs[kPool * kCH];  // 96 KB  ring pool (TMA destinations: 2 KB aligned chunks)
-  uint8_t pool_f8[kPool * kCH];    // 24 KB
-  uint32_t slots[kW];              // 64 KB
-  uint64_t cand[kCand];            // 16 KB
-  float tbl[kT][kTfTab][256];      // 16 KB
+  int32_t pool_docs[kPool * kCH];        // 80 KB  ring pool (TMA destinations: 2 KB aligned chunks)
+  uint8_t pool_f8[kPool * kCH];          // 20 KB
+  uint32_t slots[kW];                    // 64 KB
+  uint64_t cand[kCand];                  // 16 KB
+  float tbl[kT][kTfTab + 1][256];        // 20 KB
+  float ubt[kUbt];                       //  5 KB
   uint64_t full_bar[kPool];
-  uint32_t gb[kT][kSliceWindows * kWindowDocs / kGran + 1];   // granule bounds of this slice
+  uint32_t gb[kT][kSliceWindows * kWindowDocs / kGran + 1];   // 8 KB granule bounds of this slice
   DevClause cl[kMaxClauses];
   DevQuery q;
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
@@ -68,7 +74,6 @@ struct alignas(128) StreamSmem {
   int cand_count;
   unsigned long long theta;
 };
-
 static_assert(sizeof(StreamSmem) <= 232448, "StreamSmem exceeds the 227 KB per-CTA shared memory of sm_100");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,20 +100,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 __device__ __forceinline__ uint32_t presence4(uint32_t s) {
-  // bit i set iff byte i of s is non-zero
-  uint32_t t = (s | (s >> 4)) & 0x0f0f0f0fu;
-  t = (t | (t >> 2)) & 0x03030303u;
-  t = (t | (t >> 1)) & 0x01010101u;
-  return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xfu;
+  return ((s & 0xffu) ? 1u : 0u) | ((s & 0xff00u) ? 2u : 0u) | ((s & 0xff0000u) ? 4u : 0u) | ((s & 0xff000000u) ? 8u : 0u);
 }
 
-__device__ __noinline__ float term_score_slow(const StreamLaunch& L, const StreamSmem& sm, const DevClause& c, int32_t doc,
-                                              uint32_t b, uint32_t nb) {
+__device__ __noinline__ float term_score_slow(const StreamLaunch& L, const DevClause& c, int32_t doc, uint32_t b, uint32_t nb) {
   float f = (b == 255u) ? exact_freq_slow<uint32_t>(L.ix, c, doc) : (float)b;
   return bm25_score(c.weight, f, __ldg(&L.ix.caches[c.field * 256 + nb]));
 }
 
-// Universal (slow-path) evaluation: any clause mix, any tf, deleted docs. Clause-order double sums, exactly as v1.
+// Universal evaluation: any clause mix, any tf, deleted docs. Clause-order double sums, exactly as v1.
+// Score combination follows Lucene's BooleanScorerSupplier: conjunction / disjunction sums are double,
+// required+optional is ReqOptSumScorer's float add (msm == 0) or ConjunctionScorer's double add (msm > 0).
 __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t slot,
                                                   float* out_score) {
   const DevQuery& q = sm.q;
@@ -133,7 +135,7 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
           const uint8_t* nrm = L.ix.norms[c.field];
           nb = nrm ? (uint32_t)__ldg(nrm + doc) : 1u;
         }
-        s = (b <= (uint32_t)kTfTab) ? sm.tbl[c.slot][b - 1][nb] : term_score_slow(L, sm, c, doc, b, nb);
+        s = (b <= (uint32_t)kTfTab) ? sm.tbl[c.slot][b][nb] : term_score_slow(L, c, doc, b, nb);
       }
     } else if (c.kind == NRTGPU_RANGE_I64) {
       const uint8_t* has = L.ix.col_has[c.col];
@@ -173,65 +175,22 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
   return true;
 }
 
-// Per-CTA constants of the fast path: term clauses of ONE text field only, no deleted docs, tf <= kTfTab.
-struct FastQ {
-  uint32_t req_mask, not_mask, must_mask, should_mask;
-  int32_t need_should, n_req, msm;
-  const uint8_t* norms0;   // norms of the single field (NULL = omitNorms)
-  bool fast;               // false: every doc goes through evaluate_doc_generic
-};
-
-// boolean constraints + exact score of one doc from its window word. Clause sums are double in slot
-// (= clause) order; required+optional combine as Lucene's ReqOptSumScorer / ConjunctionScorer.
-__device__ __forceinline__ bool evaluate_doc_v2(const StreamLaunch& L, const StreamSmem& sm, const FastQ& fq, int32_t doc,
-                                                uint32_t slot, float* out_score) {
-  if (!fq.fast) return evaluate_doc_generic(L, sm, doc, slot, out_score);
-  const uint32_t b0 = slot & 0xffu, b1 = (slot >> 8) & 0xffu, b2 = (slot >> 16) & 0xffu, b3 = slot >> 24;
-  const uint32_t m = (b0 ? 1u : 0u) | (b1 ? 2u : 0u) | (b2 ? 4u : 0u) | (b3 ? 8u : 0u);
-  if ((m & fq.req_mask) != fq.req_mask || (m & fq.not_mask)) return false;
-  const int n_should = __popc(m & fq.should_mask);
-  if (n_should < fq.need_should) return false;
-  if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) return evaluate_doc_generic(L, sm, doc, slot, out_score);
-  const uint32_t nb = fq.norms0 ? (uint32_t)__ldg(fq.norms0 + doc) : 1u;
-  double must_sum = 0.0, should_sum = 0.0;
-  const uint32_t sc = fq.must_mask | fq.should_mask;
-  if (b0 && (sc & 1u)) { const double s = (double)sm.tbl[0][b0 - 1][nb]; if (fq.must_mask & 1u) must_sum += s; else should_sum += s; }
-  if (b1 && (sc & 2u)) { const double s = (double)sm.tbl[1][b1 - 1][nb]; if (fq.must_mask & 2u) must_sum += s; else should_sum += s; }
-  if (b2 && (sc & 4u)) { const double s = (double)sm.tbl[2][b2 - 1][nb]; if (fq.must_mask & 4u) must_sum += s; else should_sum += s; }
-  if (b3 && (sc & 8u)) { const double s = (double)sm.tbl[3][b3 - 1][nb]; if (fq.must_mask & 8u) must_sum += s; else should_sum += s; }
-  float score;
-  if (fq.n_req == 0) score = (float)should_sum;
-  else {
-    const float req = (float)must_sum;
-    if (n_should == 0) score = req;
-    else {
-      const float opt = (float)should_sum;
-      score = (fq.msm > 0) ? (float)((double)req + (double)opt) : __fadd_rn(req, opt);
-    }
+// exact score of a doc of a PURE DISJUNCTION over one text field (every slot SHOULD): double sum in slot
+// (= clause) order of the table floats; tf > kTfTab goes through the generic path
+__device__ __noinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
+                                                uint32_t v) {
+  const uint32_t b0 = v & 0xffu, b1 = (v >> 8) & 0xffu, b2 = (v >> 16) & 0xffu, b3 = v >> 24;
+  if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) {
+    float s = 0.0f;
+    evaluate_doc_generic(L, sm, doc, v, &s);
+    return s;
   }
-  *out_score = score;
-  return true;
-}
-
-
-// first index i in [0, n) with ring[(r0+i) & mask] >= bound, else n; executed by a converged warp
-// (32-ary search: <= 3 ballot rounds for n <= 32768)
-__device__ __forceinline__ int32_t warp_lower_bound(const int32_t* ring, int32_t mask, int32_t r0, int32_t n, int32_t bound,
-                                                    int lane) {
-  int32_t lo = 0, len = n;   // answer in [lo, lo+len]
-  while (len > 0) {
-    const int32_t stride = (len + 31) >> 5;
-    const int32_t p = lo + min(len, (lane + 1) * stride) - 1;
-    const bool ge = (lane * stride < len) && ring[(r0 + p) & mask] >= bound;
-    const unsigned bal = __ballot_sync(0xffffffffu, ge);
-    if (bal == 0) return lo + len;
-    const int32_t blk = (__ffs(bal) - 1) * stride;
-    const int32_t blk_len = min(len - blk, stride);
-    if (stride == 1) return lo + blk;
-    lo += blk; len = blk_len - 1;   // the last element of the block is known to be >= bound
-    if (len == 0) return lo;
-  }
-  return lo;
+  const uint32_t nb = norms0 ? (uint32_t)__ldg(norms0 + doc) : 1u;
+  double sum = (double)sm.tbl[0][b0][nb];   // rows tf = 0 hold +0.0f: adding them leaves the sum bit-identical
+  sum += (double)sm.tbl[1][b1][nb];
+  sum += (double)sm.tbl[2][b2][nb];
+  sum += (double)sm.tbl[3][b3][nb];
+  return (float)sum;
 }
 
 __device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k, uint64_t* g_theta) {
@@ -284,7 +243,6 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
                   sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
                   sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; }
-  __syncthreads();
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
@@ -313,8 +271,9 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   }
   __syncthreads();
   if (tid == 0) {
-    // split the ring pool: every list starts with 2 chunks; the list with the most chunks still to
-    // stream per ring chunk is doubled while the pool allows (dense lists get long rings)
+    // split the ring pool: every list gets at least one granule's worth (kMinNCH chunks, or the whole
+    // list if shorter); the list with the most chunks still to stream per ring chunk is doubled while
+    // the pool allows (dense lists get long rings = deep TMA prefetch)
     int nch[kT], used = 0;
     for (int t = 0; t < kT; ++t) {
       nch[t] = 0;
@@ -337,12 +296,13 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   __syncthreads();
 
   // ---- CTA-uniform per-slot registers
-  int32_t r_cur[kT], rbase[kT], rmask[kT];
+  int32_t r_cur[kT], rbase[kT], rmask[kT], rlog[kT];
 #pragma unroll
   for (int t = 0; t < kT; ++t) {
     r_cur[t] = sm.s_r_begin[t];
     rbase[t] = sm.s_ring_base[t] << kLogCH;
     rmask[t] = (sm.s_ring_nch[t] << kLogCH) - 1;
+    rlog[t] = 31 - __clz(sm.s_ring_nch[t]);
   }
   auto issue_chunks = [&]() {  // thread 0 only: fill every free ring slot
 #pragma unroll
@@ -362,15 +322,35 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   };
   if (tid == 0) issue_chunks();
 
-  // ---- exact BM25 table: tbl[slot][tf-1][norm byte]
-  for (int i = tid; i < kT * kTfTab * 256; i += kThreads) {
-    const int s = i / (kTfTab * 256), tf = (i / 256) % kTfTab + 1, nb = i & 255;
+  // ---- exact BM25 table tbl[slot][tf][norm byte] (row tf = 0 is +0.0f)
+  for (int i = tid; i < kT * (kTfTab + 1) * 256; i += kThreads) {
+    const int s = i / ((kTfTab + 1) * 256), tf = (i / 256) % (kTfTab + 1), nb = i & 255;
     float v = 0.0f;
-    if (s < n_term) {
+    if (s < n_term && tf > 0) {
       const DevClause& c = sm.cl[sm.s_clause[s]];
-      v = bm25_score(c.weight, (float)tf, __ldg(&L.ix.caches[c.field * 256 + nb]));
+      if (c.scoring) v = bm25_score(c.weight, (float)tf, __ldg(&L.ix.caches[c.field * 256 + nb]));
     }
-    sm.tbl[s][tf - 1][nb] = v;
+    sm.tbl[s][tf][nb] = v;
+  }
+  const bool fast = sm.q.single_field >= 0 && !sm.q.has_nonterm && !sm.q.nonterm_scoring && L.ix.live_bits == nullptr;
+  // pure disjunction of terms over one field: every owner is a hit, score = (float) double sum of the slots
+  const bool simple = fast && sm.q.n_req == 0 && sm.q.not_term_mask == 0 && sm.q.msm <= 1;
+  __syncthreads();
+  // ---- upper bounds per tf pattern (simple queries): same double sum, each term at the shortest field
+  //      length present (largest score); tf >= 5 is bounded by the clause weight (limit tf -> inf)
+  if (simple) {
+    const uint32_t nbmin = L.field_min_norm ? (uint32_t)L.field_min_norm[sm.q.single_field] : 0u;
+    for (int i = tid; i < kUbt; i += kThreads) {
+      const int c[kT] = {i % 6, (i / 6) % 6, (i / 36) % 6, i / 216};
+      double sum = 0.0;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) {
+        float u = 0.0f;
+        if (t < n_term && c[t] > 0) u = (c[t] <= kTfTab) ? sm.tbl[t][c[t]][nbmin] : sm.cl[sm.s_clause[t]].weight;
+        sum += (double)u;
+      }
+      sm.ubt[i] = (float)sum;
+    }
   }
   __syncthreads();
 
@@ -382,12 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   const uint64_t after_key = sm.q.after_key;
   const uint32_t driver_mask = sm.q.driver_mask;
   const bool has_non_driver = sm.q.has_non_driver != 0;
-  FastQ fq;
-  fq.req_mask = sm.q.req_term_mask; fq.not_mask = sm.q.not_term_mask;
-  fq.must_mask = sm.q.must_term_mask; fq.should_mask = sm.q.should_term_mask;
-  fq.need_should = sm.q.need_should; fq.n_req = sm.q.n_req; fq.msm = sm.q.msm;
-  fq.fast = sm.q.single_field >= 0 && !sm.q.has_nonterm && !sm.q.nonterm_scoring && L.ix.live_bits == nullptr;
-  fq.norms0 = (sm.q.single_field >= 0) ? L.ix.norms[sm.q.single_field] : nullptr;
+  const uint8_t* norms0 = (sm.q.single_field >= 0) ? L.ix.norms[sm.q.single_field] : nullptr;
   uint32_t scoring_bits = 0;
 #pragma unroll
   for (int t = 0; t < kT; ++t) scoring_bits |= (sm.s_scoring[t] ? 1u : 0u) << t;
@@ -403,25 +378,19 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
   int g0 = 0;   // next granule of the slice
-  for (;;) {
-    if (g0 >= g_count) break;
+  while (g0 < g_count) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
-    int g1 = g0;
+    int g1 = min(g_count, g0 + kWinGran);
     int32_t cnt[kT];
+    for (;;) {
+      bool fits = true;
 #pragma unroll
-    for (int t = 0; t < kT; ++t) cnt[t] = 0;
-    {
-      const int gmax = min(g_count, g0 + kWinGran);
-      for (int g = g0 + 1; g <= gmax; ++g) {
-        bool fits = true;
-#pragma unroll
-        for (int t = 0; t < kT; ++t) fits = fits && (int32_t)(sm.gb[t][g] - sm.gb[t][g0]) <= rmask[t] + 1 - kCH;
-        if (!fits) break;
-        g1 = g;
+      for (int t = 0; t < kT; ++t) {
+        cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
+        fits = fits && cnt[t] <= rmask[t] + 1 - kCH;
       }
-      // a single granule always fits (<= 2048 postings, ring >= kMinNCH chunks or the whole list)
-#pragma unroll
-      for (int t = 0; t < kT; ++t) cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
+      if (fits || g1 == g0 + 1) break;   // one granule always fits (<= 2048 postings, ring >= kMinNCH chunks)
+      --g1;
     }
     const int32_t wbase = slice_base + (g0 << kLogGran);
     const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
@@ -431,10 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       if (t < n_term && cnt[t] > 0) {
-        const int jc = r_cur[t] >> kLogCH, jl = (r_cur[t] + cnt[t] - 1) >> kLogCH;   // chunks [jc, jl] (<= 32)
-        const int nch_mask = (rmask[t] >> kLogCH);
-        const int j = jc + lane;
-        if (j <= jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & nch_mask)], (j / (nch_mask + 1)) & 1);
+        const int j = (r_cur[t] >> kLogCH) + lane, jl = (r_cur[t] + cnt[t] - 1) >> kLogCH;   // <= 32 chunks
+        if (j <= jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & (rmask[t] >> kLogCH))], (j >> rlog[t]) & 1);
       }
     }
     __syncwarp();
@@ -444,10 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     for (int t = 0; t < kT; ++t) {
       if (t >= n_term) break;
       const bool scoring = (scoring_bits >> t) & 1u;
+      const int32_t* rd = sm.pool_docs + rbase[t];
+      const uint8_t* rf = sm.pool_f8 + rbase[t];
+      unsigned char* sb = slot_bytes + t - 4 * wbase;
       for (int32_t i = tid; i < cnt[t]; i += kThreads) {
-        const int idx = rbase[t] + ((r_cur[t] + i) & rmask[t]);
-        const int32_t doc = sm.pool_docs[idx];
-        slot_bytes[(size_t)(doc - wbase) * 4 + t] = scoring ? sm.pool_f8[idx] : (unsigned char)1;
+        const int idx = (r_cur[t] + i) & rmask[t];
+        sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1;
       }
     }
     __syncthreads();
@@ -462,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
       uint64_t pkey = 0;
       for (;;) {
         const unsigned long long theta = sm.theta;
+        const float theta_s = theta ? key_score(theta) : -INFINITY;
         if (pending) {
           pending = false;
           if (pkey > theta) {
@@ -475,40 +445,63 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
             for (int t = 0; t < kT; ++t) {
               if (t >= n_term || pending) break;
               if (!((driver_mask >> t) & 1u)) continue;
-              const uint32_t own = 0xffu << (8 * t);
-              for (int32_t i = it[t]; i < cnt[t]; i += kThreads) {
-                const int32_t doc = sm.pool_docs[rbase[t] + ((r_cur[t] + i) & rmask[t])];
-                const uint32_t v = sm.slots[doc - wbase];
-                if ((v & below[t]) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
-                sm.slots[doc - wbase] = 0u;
-                float score;
-                if (!evaluate_doc_v2(L, sm, fq, doc, v, &score)) continue;
-                ++my_hits;
-                const uint64_t key = make_key(score, doc);
-                if (key > theta && (!has_after || key < after_key)) {
-                  const int p = atomicAdd(&sm.cand_count, 1);
-                  if (p < kCand) sm.cand[p] = key;
-                  else { pending = true; pkey = key; it[t] = i + kThreads; break; }
+              const uint32_t own = 0xffu << (8 * t), bel = below[t];
+              const int32_t* rd = sm.pool_docs + rbase[t];
+              uint32_t* sl = sm.slots - wbase;
+              int32_t i = it[t];
+              if (simple) {
+                for (; i < cnt[t]; i += kThreads) {
+                  const int32_t doc = rd[(r_cur[t] + i) & rmask[t]];
+                  const uint32_t v = sl[doc];
+                  if ((v & bel) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
+                  sl[doc] = 0u;
+                  ++my_hits;
+                  const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
+                                      216u * min(v >> 24, 5u);
+                  if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
+                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v), doc);
+                  if (key > theta && (!has_after || key < after_key)) {
+                    const int p = atomicAdd(&sm.cand_count, 1);
+                    if (p < kCand) sm.cand[p] = key;
+                    else { pending = true; pkey = key; i += kThreads; break; }
+                  }
+                }
+              } else {
+                for (; i < cnt[t]; i += kThreads) {
+                  const int32_t doc = rd[(r_cur[t] + i) & rmask[t]];
+                  const uint32_t v = sl[doc];
+                  if ((v & bel) != 0 || (v & own) == 0) continue;
+                  sl[doc] = 0u;
+                  float score;
+                  if (!evaluate_doc_generic(L, sm, doc, v, &score)) continue;
+                  ++my_hits;
+                  const uint64_t key = make_key(score, doc);
+                  if (key > theta && (!has_after || key < after_key)) {
+                    const int p = atomicAdd(&sm.cand_count, 1);
+                    if (p < kCand) sm.cand[p] = key;
+                    else { pending = true; pkey = key; i += kThreads; break; }
+                  }
                 }
               }
-              if (!pending) it[t] = cnt[t];
+              it[t] = i;
             }
           } else {
             const int32_t wlen = wend - wbase;
-            for (int32_t i = idense; i < wlen; i += kThreads) {
+            int32_t i = idense;
+            for (; i < wlen; i += kThreads) {
               const uint32_t v = sm.slots[i];
               if (v) sm.slots[i] = 0u;
               float score;
-              if (!evaluate_doc_v2(L, sm, fq, wbase + i, v, &score)) continue;
+              if (!evaluate_doc_generic(L, sm, wbase + i, v, &score)) continue;
               ++my_hits;
               const uint64_t key = make_key(score, wbase + i);
               if (key > theta && (!has_after || key < after_key)) {
                 const int p = atomicAdd(&sm.cand_count, 1);
                 if (p < kCand) sm.cand[p] = key;
-                else { pending = true; pkey = key; idense = i + kThreads; break; }
+                else { pending = true; pkey = key; i += kThreads; break; }
               }
             }
-            if (!pending) idense = wlen;
+            idense = i;
           }
         }
         __syncthreads();
@@ -533,9 +526,10 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     if (tid == 0) issue_chunks();
   }
 
-  // ---------------- finish the work item
-  compact_candidates_v2(sm, L.top_k, &L.theta[qi]);
-  const int keep = sm.cand_count;
+  // ---------------- finish the work item: the slice merge sorts, so only a full buffer needs ordering here
+  __syncthreads();
+  if (sm.cand_count > L.top_k) compact_candidates_v2(sm, L.top_k, &L.theta[qi]);
+  const int keep = min(sm.cand_count, L.top_k);
   uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
   for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
   if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
