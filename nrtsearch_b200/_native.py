@@ -25,6 +25,8 @@ class NrtGpuUnsupported(NrtGpuError):
 
 def _load(name: str) -> C.CDLL:
     path = os.path.join(_HERE, name)
+    if name == "libnrtgpu.so" and os.environ.get("NRTGPU_LIB_PATH"):   # kernel-variant experiments only
+        path = os.environ["NRTGPU_LIB_PATH"]
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

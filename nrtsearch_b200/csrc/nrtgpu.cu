@@ -55,13 +55,20 @@ float bm25_idf(int64_t df, int64_t doc_count) {
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0, cap = 0;
   ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
+  int alloc(size_t count) {   // keeps the allocation when it is already large enough (workspace reuse)
     n = count;
-    if (count == 0) return NRTGPU_OK;
+    if (count <= cap) return NRTGPU_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
     NRT_CUDA_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+    cap = count;
+    return NRTGPU_OK;
+  }
+  int upload_async(const T* h, size_t count, cudaStream_t st) {
+    int rc = alloc(count);
+    if (rc) return rc;
+    if (count) NRT_CUDA_TRY(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
     return NRTGPU_OK;
   }
   int upload(const T* h, size_t count) {
@@ -106,6 +113,10 @@ struct nrtgpu_index {
   DevBuf<float> vec_norm2;  // per-vector squared magnitude (double-accumulated, stored float) for cosine
   DevBuf<int32_t> vec_docs;
   int64_t device_bytes = 0;
+  // reusable batch workspaces of the one-shot entry point (nrtgpu_search_bool), one per concurrent caller
+  std::mutex ws_mu;
+  std::vector<nrtgpu_batch*> ws_free;
+  ~nrtgpu_index();
 
   DevIndexView view() const {
     DevIndexView v;
@@ -119,6 +130,8 @@ struct nrtgpu_index {
   }
 };
 
+struct nrtgpu_batch;
+static void free_batch(nrtgpu_batch* b);
 struct nrtgpu_batch {
   nrtgpu_index* ix = nullptr;
   int32_t nq = 0, top_k = 0, n_slices = 0, n_work = 0;
@@ -148,6 +161,9 @@ struct nrtgpu_batch {
   int32_t* o_counts() { return bound_counts ? bound_counts : out_counts.p; }
   ~nrtgpu_batch() { for (auto& r : ev) for (auto& e : r) if (e) cudaEventDestroy(e); }
 };
+
+static void free_batch(nrtgpu_batch* b) { delete b; }
+nrtgpu_index::~nrtgpu_index() { for (auto* b : ws_free) free_batch(b); }
 
 extern "C" {
 
@@ -316,18 +332,19 @@ int nrtgpu_index_close(nrtgpu_index* ix) {
 int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix) { return ix ? ix->device_bytes : 0; }
 
 // ---- batch compilation: flat BooleanQuery -> DevQuery/DevClause, driver selection, work list ----
-int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
-                         const nrtgpu_query* queries, int32_t nq, int32_t top_k,
-                         int32_t total_hits_threshold, int32_t flags, nrtgpu_batch** out) {
-  if (!ix || !queries || !out || (n_clauses > 0 && !clauses)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
+// compile + upload a batch into `b` (buffers are reused when large enough); asynchronous on `st`
+static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                       const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold,
+                       int32_t flags, cudaStream_t st) {
+  if (!ix || !queries || (n_clauses > 0 && !clauses)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
   if (nq <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: nq must be > 0");
   // LazyQueueTopScoreDocCollectorManager.java:93-96: numHits must be > 0
   if (top_k <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "numHits must be > 0; please use TotalHitCountCollectorManager if you just need the total hit count");
   if (top_k > kMaxTopK) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_batch_prepare: top_k > 1024 is not on the GPU path");
   if (total_hits_threshold < 0) NRT_FAIL(NRTGPU_ERR_INVALID, "totalHitsThreshold must be >= 0");
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
-  std::unique_ptr<nrtgpu_batch> b(new nrtgpu_batch);
   b->ix = ix; b->nq = nq; b->top_k = top_k;
+  b->alg_postings = 0; b->ran = false; b->runs_recorded = 0;
   b->exhaustive = true;  // TOP_SCORES is served by the exact path too (counts stay EQUAL_TO)
   (void)flags;
   const int64_t slice_docs = (int64_t)kSliceWindows * kWindowDocs;
@@ -431,10 +448,11 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
     for (int qi : order) { wq.push_back(qi); ws.push_back(s); }
   b->n_work = (int32_t)wq.size();
   int rc;
-  if ((rc = b->clauses.upload(dc.data(), dc.size()))) return rc;
-  if ((rc = b->queries.upload(dq.data(), dq.size()))) return rc;
-  if ((rc = b->work_query.upload(wq.data(), wq.size()))) return rc;
-  if ((rc = b->work_slice.upload(ws.data(), ws.size()))) return rc;
+  if ((rc = b->clauses.upload_async(dc.data(), dc.size(), st))) return rc;
+  if ((rc = b->queries.upload_async(dq.data(), dq.size(), st))) return rc;
+  if ((rc = b->work_query.upload_async(wq.data(), wq.size(), st))) return rc;
+  if ((rc = b->work_slice.upload_async(ws.data(), ws.size(), st))) return rc;
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
   if ((rc = b->theta.alloc((size_t)nq))) return rc;
   if ((rc = b->total_hits.alloc((size_t)nq))) return rc;
   if ((rc = b->slice_keys.alloc((size_t)nq * b->n_slices * top_k))) return rc;
@@ -451,11 +469,21 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
     v2::BoundsLaunch B;
     B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_gran = b->n_gran;
     B.gbounds = b->gbounds.p;
-    v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256>>>(B);
+    v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B);
     NRT_CUDA_TRY(cudaGetLastError());
-    NRT_CUDA_TRY(cudaDeviceSynchronize());
   }
-  for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
+  if (!b->ev[0][0]) for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                         int32_t total_hits_threshold, int32_t flags, nrtgpu_batch** out) {
+  if (!out) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
+  std::unique_ptr<nrtgpu_batch> b(new nrtgpu_batch);
+  int rc = batch_build(b.get(), ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)0);
+  if (rc) return rc;
+  NRT_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
   *out = b.release();
   return NRTGPU_OK;
 }
@@ -566,12 +594,22 @@ int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n
                        int32_t total_hits_threshold, int32_t flags, void* stream, int32_t* out_docs,
                        float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
                        uint8_t* out_relation) {
+  if (!ix) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool: NULL index");
+  // take a cached workspace (device buffers survive between calls: no cudaMalloc on the request path)
   nrtgpu_batch* b = nullptr;
-  int rc = nrtgpu_batch_prepare(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, &b);
-  if (rc) return rc;
-  rc = nrtgpu_batch_run(b, stream);
+  {
+    std::lock_guard<std::mutex> g(ix->ws_mu);
+    if (!ix->ws_free.empty()) { b = ix->ws_free.back(); ix->ws_free.pop_back(); }
+  }
+  if (!b) b = new nrtgpu_batch;
+  b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr;
+  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream);
+  if (!rc) rc = nrtgpu_batch_run(b, stream);
   if (!rc) rc = nrtgpu_batch_fetch(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation);
-  nrtgpu_batch_free(b);
+  {
+    std::lock_guard<std::mutex> g(ix->ws_mu);
+    ix->ws_free.push_back(b);
+  }
   return rc;
 }
 

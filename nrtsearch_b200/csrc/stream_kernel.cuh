@@ -27,7 +27,10 @@ constexpr int kCH = 1 << kLogCH;      // postings per chunk
 constexpr int kPool = 40;             // chunks in the CTA's ring pool, shared by the term clauses
 constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
 constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
-constexpr int kThreads = 384;         // one CTA per SM
+#ifndef NRT_STREAM_THREADS
+#define NRT_STREAM_THREADS 384
+#endif
+constexpr int kThreads = NRT_STREAM_THREADS;   // one CTA per SM
 constexpr int kCand = 2048;
 constexpr int kTfTab = 4;             // table rows tf = 0..4 (row 0 = 0.0f)
 constexpr int kLogGran = 11;          // posting bounds are precomputed per (query, clause) at 2048-doc granules
