@@ -28,7 +28,7 @@ constexpr int kPool = 40;             // chunks in the CTA's ring pool, shared b
 constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
 constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
 #ifndef NRT_STREAM_THREADS
-#define NRT_STREAM_THREADS 384
+#define NRT_STREAM_THREADS 512
 #endif
 constexpr int kThreads = NRT_STREAM_THREADS;   // one CTA per SM
 constexpr int kCand = 2048;
