@@ -100,20 +100,14 @@ def make_queries(nq, vocab):
 def build_shard(args, rank, world):
     """Rank r holds docs [r*N/G, (r+1)*N/G); df / docCount / sumTotalTermFreq become index-wide."""
     from nrtsearch_b200 import index as ix
-    lo, hi = args.docs * rank // world, args.docs * (rank + 1) // world
+    from nrtsearch_b200.shards import install_global_stats, shard_range
+    lo, hi = shard_range(args.docs, rank, world)
     sh = ix.synth_text_shard(hi - lo, args.vocab, doc_begin=lo)
-    local_df = np.diff(sh.term_off).astype(np.int64)
     if world > 1:
         import torch
-        import torch.distributed as dist
-        t = torch.from_numpy(np.concatenate([local_df, [sh.fields[0].sum_total_term_freq, sh.n_docs]])).cuda()
-        dist.all_reduce(t)   # NCCL all-reduce of per-shard term statistics (build time, not per query)
-        g = t.cpu().numpy()
-        sh.term_df = np.ascontiguousarray(g[:-2])
-        sh.fields[0].sum_total_term_freq = int(g[-2])
-        sh.fields[0].doc_count = int(g[-1])
+        install_global_stats(sh, device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))   # NCCL all-reduce, build time
     else:
-        sh.term_df = local_df
+        sh.term_df = np.diff(sh.term_off).astype(np.int64)
     return sh
 
 
@@ -208,28 +202,17 @@ def main():
     lib = _native.gpu_lib()
 
     # device buffers (torch = memory + streams plumbing only)
-    loc_docs = torch.zeros(nq * k, dtype=torch.int32, device=dev)
-    loc_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
-    loc_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    from nrtsearch_b200.shards import TopKGather
+    tg = TopKGather(nq, k, world, dev)
+    loc_docs, loc_scores, loc_counts = tg.loc_docs, tg.loc_scores, tg.loc_counts
     batch.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
-    if world > 1:
-        all_docs = torch.zeros(world * nq * k, dtype=torch.int32, device=dev)
-        all_scores = torch.zeros(world * nq * k, dtype=torch.float32, device=dev)
-        all_counts = torch.zeros(world * nq, dtype=torch.int32, device=dev)
-        fin_docs = torch.zeros(nq * k, dtype=torch.int32, device=dev)
-        fin_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
-        fin_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         batch.run(stream)
         if world > 1:
-            dist.all_gather_into_tensor(all_docs, loc_docs)
-            dist.all_gather_into_tensor(all_scores, loc_scores)
-            dist.all_gather_into_tensor(all_counts, loc_counts)
-            _native.check(lib.nrtgpu_merge_topk_device(ctx.handle, world, nq, k, all_docs.data_ptr(), all_scores.data_ptr(),
-                                                       all_counts.data_ptr(), fin_docs.data_ptr(), fin_scores.data_ptr(),
-                                                       fin_counts.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            tg.gather()                        # ONE exchange step: NCCL all-gather of the per-shard top-k
+            tg.merge_on_device(ctx, stream)    # TopDocs.merge on every rank
 
     def barrier():
         if world > 1:
@@ -296,13 +279,9 @@ def main():
             loc_docs.copy_(torch.from_numpy(out.docs.reshape(-1)), non_blocking=True)
             loc_scores.copy_(torch.from_numpy(out.scores.reshape(-1)), non_blocking=True)
             loc_counts.copy_(torch.from_numpy(out.counts), non_blocking=True)
-            dist.all_gather_into_tensor(all_docs, loc_docs)
-            dist.all_gather_into_tensor(all_scores, loc_scores)
-            dist.all_gather_into_tensor(all_counts, loc_counts)
-            _native.check(lib.nrtgpu_merge_topk_device(ctx.handle, world, nq, k, all_docs.data_ptr(), all_scores.data_ptr(),
-                                                       all_counts.data_ptr(), fin_docs.data_ptr(), fin_scores.data_ptr(),
-                                                       fin_counts.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            fin_docs.cpu()
+            tg.gather()
+            tg.merge_on_device(ctx, stream)
+            tg.fin_docs.cpu(); tg.fin_scores.cpu()
 
     e2e_step()
     barrier()
@@ -328,7 +307,7 @@ def main():
             "config": workload_config(args),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": stats["launches_per_run"] * args.steps + (args.steps if world > 1 else 0),
-            "roofline": {"bound": "hbm", "kernel": "bool_window_kernel (posting traversal + BM25 + top-k)",
+            "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel (TMA-streamed posting traversal + BM25 + exact top-k)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
                          "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world},

@@ -4,6 +4,7 @@
 #include "bool_kernel.cuh"
 #include "stream_kernel.cuh"
 #include "knn_kernel.cuh"
+#include "hybrid_kernel.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -638,13 +639,70 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
                          out_scores, out_counts);
 }
 
-int nrtgpu_blend_rrf(nrtgpu_ctx*, int32_t, int32_t, int32_t, const int32_t*, const int32_t*, const float*, int32_t,
-                     int32_t, int32_t*, float*, int32_t*, int32_t*) {
-  NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_blend_rrf: not built yet");
+namespace {
+struct DevTmp {   // scoped device scratch for the O(k) hybrid stages
+  void* p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  int get(size_t bytes) { NRT_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 1)); return NRTGPU_OK; }
+};
+}  // namespace
+
+int nrtgpu_blend_rrf(nrtgpu_ctx* ctx, int32_t R, int32_t nq, int32_t top_in, const int32_t* docs, const int32_t* counts,
+                     const float* boosts, int32_t rank_constant, int32_t top_out, int32_t* out_docs, float* out_scores,
+                     int32_t* out_counts, int32_t* out_total) {
+  if (!ctx || !docs || !counts || !boosts || !out_docs || !out_scores || !out_counts || !out_total)
+    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend_rrf: NULL argument");
+  if (R <= 0 || nq <= 0 || top_in <= 0 || top_out <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend_rrf: sizes must be > 0");
+  if ((int64_t)R * top_in > kHybCap || top_in > 65535 || R > 65535) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_blend_rrf: more than 4096 hits per query");
+  // WeightedRrfBlenderOperation.java:47-49: rankConstant <= 0 selects DEFAULT_K = 60
+  const int k = rank_constant > 0 ? rank_constant : 60;
+  NRT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t nd = (size_t)R * nq * top_in, nc = (size_t)R * nq, no = (size_t)nq * top_out;
+  DevTmp dd, dc, db, od, os, oc, ot;
+  int rc;
+  if ((rc = dd.get(nd * 4)) || (rc = dc.get(nc * 4)) || (rc = db.get((size_t)R * 4)) || (rc = od.get(no * 4)) ||
+      (rc = os.get(no * 4)) || (rc = oc.get((size_t)nq * 4)) || (rc = ot.get((size_t)nq * 4))) return rc;
+  NRT_CUDA_TRY(cudaMemcpy(dd.p, docs, nd * 4, cudaMemcpyHostToDevice));
+  NRT_CUDA_TRY(cudaMemcpy(dc.p, counts, nc * 4, cudaMemcpyHostToDevice));
+  NRT_CUDA_TRY(cudaMemcpy(db.p, boosts, (size_t)R * 4, cudaMemcpyHostToDevice));
+  RrfLaunch P;
+  P.docs = (const int32_t*)dd.p; P.counts = (const int32_t*)dc.p; P.boosts = (const float*)db.p;
+  P.R = R; P.nq = nq; P.top_in = top_in; P.rank_constant = k; P.top_out = top_out;
+  P.out_docs = (int32_t*)od.p; P.out_scores = (float*)os.p; P.out_counts = (int32_t*)oc.p; P.out_total = (int32_t*)ot.p;
+  rrf_blend_kernel<<<nq, kHybThreads>>>(P);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaMemcpy(out_docs, od.p, no * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpy(out_scores, os.p, no * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpy(out_counts, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpy(out_total, ot.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+  return NRTGPU_OK;
 }
-int nrtgpu_rescore_combine(nrtgpu_ctx*, int32_t, int32_t, const int32_t*, int32_t*, float*, const uint8_t*,
-                           const float*, double, double) {
-  NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_rescore_combine: not built yet");
+
+int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const int32_t* counts, int32_t* docs, float* scores,
+                           const uint8_t* second_matches, const float* second_scores, double query_weight,
+                           double rescore_weight) {
+  if (!ctx || !docs || !scores || !second_matches || !second_scores) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_combine: NULL argument");
+  if (nq <= 0 || n_hits <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_combine: sizes must be > 0");
+  if (n_hits > kHybCap) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_rescore_combine: more than 4096 hits per query");
+  NRT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)nq * n_hits;
+  DevTmp dd, ds, dm, d2, dc;
+  int rc;
+  if ((rc = dd.get(n * 4)) || (rc = ds.get(n * 4)) || (rc = dm.get(n)) || (rc = d2.get(n * 4)) || (rc = dc.get((size_t)nq * 4))) return rc;
+  NRT_CUDA_TRY(cudaMemcpy(dd.p, docs, n * 4, cudaMemcpyHostToDevice));
+  NRT_CUDA_TRY(cudaMemcpy(ds.p, scores, n * 4, cudaMemcpyHostToDevice));
+  NRT_CUDA_TRY(cudaMemcpy(dm.p, second_matches, n, cudaMemcpyHostToDevice));
+  NRT_CUDA_TRY(cudaMemcpy(d2.p, second_scores, n * 4, cudaMemcpyHostToDevice));
+  if (counts) NRT_CUDA_TRY(cudaMemcpy(dc.p, counts, (size_t)nq * 4, cudaMemcpyHostToDevice));
+  RescoreLaunch P;
+  P.nq = nq; P.n_hits = n_hits; P.counts = counts ? (const int32_t*)dc.p : nullptr;
+  P.docs = (int32_t*)dd.p; P.scores = (float*)ds.p; P.second_matches = (const uint8_t*)dm.p; P.second_scores = (const float*)d2.p;
+  P.query_weight = query_weight; P.rescore_weight = rescore_weight;
+  rescore_combine_kernel<<<nq, kHybThreads>>>(P);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaMemcpy(docs, dd.p, n * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpy(scores, ds.p, n * 4, cudaMemcpyDeviceToHost));
+  return NRTGPU_OK;
 }
 
 }  // extern "C"

@@ -322,3 +322,34 @@ class GpuIndexSearcher:
                                           None if b is None else b.ctypes.data, None if f is None else f.ctypes.data,
                                           C.c_void_p(stream), docs.ctypes.data, scores.ctypes.data, counts.ctypes.data))
         return docs, scores, counts
+
+
+def blend_rrf(ctx: GpuContext, docs: np.ndarray, counts: np.ndarray, boosts: Sequence[float], rank_constant: int,
+              top_hits: int):
+    """BlenderOperation.blend with the weighted-RRF operation (BlenderOperation.java:76-87) for nq queries:
+    docs [R, nq, top_in], counts [R, nq] -> (docs [nq, top_hits], scores, counts, total)."""
+    d = np.ascontiguousarray(docs, np.int32)
+    c = np.ascontiguousarray(counts, np.int32)
+    b = np.ascontiguousarray(boosts, np.float32)
+    R, nq, top_in = d.shape
+    od, os_ = np.zeros((nq, top_hits), np.int32), np.zeros((nq, top_hits), np.float32)
+    oc, ot = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+    check(_native.gpu_lib().nrtgpu_blend_rrf(ctx.handle, R, nq, top_in, d.ctypes.data, c.ctypes.data, b.ctypes.data,
+                                             rank_constant, top_hits, od.ctypes.data, os_.ctypes.data, oc.ctypes.data,
+                                             ot.ctypes.data))
+    return od, os_, oc, ot
+
+
+def rescore_combine(ctx: GpuContext, docs: np.ndarray, scores: np.ndarray, second_matches: np.ndarray,
+                    second_scores: np.ndarray, query_weight: float, rescore_weight: float, counts=None):
+    """QueryRescore (QueryRescore.java:39-57) for nq hit lists [nq, n_hits]: combined + re-sorted copies."""
+    d = np.ascontiguousarray(docs, np.int32).copy()
+    s = np.ascontiguousarray(scores, np.float32).copy()
+    m = np.ascontiguousarray(second_matches, np.uint8)
+    s2 = np.ascontiguousarray(second_scores, np.float32)
+    nq, n_hits = d.shape
+    cn = None if counts is None else np.ascontiguousarray(counts, np.int32)
+    check(_native.gpu_lib().nrtgpu_rescore_combine(ctx.handle, nq, n_hits, None if cn is None else cn.ctypes.data,
+                                                   d.ctypes.data, s.ctypes.data, m.ctypes.data, s2.ctypes.data,
+                                                   query_weight, rescore_weight))
+    return d, s
