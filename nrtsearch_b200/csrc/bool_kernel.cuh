@@ -42,6 +42,8 @@ struct DevClause {
   int32_t col;        // doc-value column for range clauses
   float weight;       // boost*idf (term) or constant score = boost (range / match-all)
   int32_t scoring;    // 1 if the clause contributes to the score (MUST / SHOULD)
+  float ub;           // term clauses: largest score of any posting of the list (index-time max of tf*cache[norm])
+  int32_t pad_;
   int64_t lo, hi;
 };
 

@@ -27,6 +27,29 @@ struct nrtgpu_ctx {
   int sm_count = 0;
 };
 
+// index-time impacts: max over a term's postings of x = tf * cache[norm] (what Lucene keeps as competitive (freq, norm)
+// pairs in its skip data); the BM25 score is monotone in x, so score(weight, max x) bounds the whole list.
+__global__ void term_max_x_kernel(const int64_t* __restrict__ term_off, int n_terms, const int32_t* __restrict__ term_field,
+                                  const int32_t* __restrict__ docs, const uint8_t* __restrict__ f8,
+                                  const int64_t* __restrict__ exc_pos, const int32_t* __restrict__ exc_freq, int n_exc,
+                                  const uint8_t* const* __restrict__ norms, const float* __restrict__ caches, int64_t P,
+                                  unsigned int* __restrict__ out_bits) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int lo = 0, hi = n_terms;   // last term with term_off[t] <= p
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (term_off[mid] <= p) lo = mid; else hi = mid; }
+  const int t = lo, f = term_field[t];
+  float freq = (float)f8[p];
+  if (f8[p] == 255) {
+    int a = 0, b = n_exc;
+    while (a < b) { int m = (a + b) >> 1; if (exc_pos[m] < p) a = m + 1; else b = m; }
+    if (a < n_exc && exc_pos[a] == p) freq = (float)exc_freq[a];
+  }
+  const uint8_t* nrm = norms[f];
+  const float x = __fmul_rn(freq, caches[f * 256 + (nrm ? nrm[docs[p]] : 1)]);
+  atomicMax(out_bits + t, __float_as_uint(x));   // x > 0: float order == unsigned order
+}
+
 namespace {
 
 // ---- SmallFloat.byte4ToInt (Lucene) : norm byte -> field length, for the BM25 length table ----
@@ -90,6 +113,7 @@ struct nrtgpu_index {
   std::vector<int64_t> term_off;
   std::vector<int32_t> term_field;
   std::vector<int64_t> term_df;
+  std::vector<float> term_max_x;
   std::vector<int64_t> field_doc_count, field_sum_ttf;
   std::vector<uint8_t> field_has_norms;
   // device image
@@ -143,6 +167,8 @@ struct nrtgpu_batch {
   DevBuf<DevQuery> queries;
   DevBuf<int32_t> work_query, work_slice;
   DevBuf<uint32_t> gbounds;  // stream kernel: [nq][4][n_gran+1]
+  DevBuf<int32_t> pruned;    // [nq] relation GTE flags
+  int64_t threshold = INT32_MAX;
   int32_t n_gran = 0;
   DevBuf<uint64_t> theta;
   DevBuf<unsigned long long> total_hits;
@@ -296,6 +322,20 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if ((rc = ix->col32_ptrs.upload(p32.data(), p32.size()))) return rc;
     if ((rc = ix->col_has_ptrs.upload(ph.data(), ph.size()))) return rc;
   }
+  // index-time impacts (list-wide score bounds for MAXSCORE)
+  ix->term_max_x.assign((size_t)d->n_terms, 0.0f);
+  if (P > 0) {
+    DevBuf<int64_t> d_off; DevBuf<int32_t> d_tf; DevBuf<unsigned int> d_mx;
+    if ((rc = d_off.upload(ix->term_off.data(), ix->term_off.size()))) return rc;
+    if ((rc = d_tf.upload(ix->term_field.data(), ix->term_field.size()))) return rc;
+    if ((rc = d_mx.alloc((size_t)d->n_terms))) return rc;
+    NRT_CUDA_TRY(cudaMemset(d_mx.p, 0, d_mx.bytes()));
+    term_max_x_kernel<<<(unsigned)((P + 255) / 256), 256>>>(d_off.p, d->n_terms, d_tf.p, ix->post_docs.p, ix->post_f8.p,
+                                                            ix->exc_pos.p, ix->exc_freq.p, (int)ix->exc_pos.n, ix->norms_ptrs.p,
+                                                            ix->caches.p, P, d_mx.p);
+    NRT_CUDA_TRY(cudaGetLastError());
+    NRT_CUDA_TRY(cudaMemcpy(ix->term_max_x.data(), d_mx.p, (size_t)d->n_terms * sizeof(float), cudaMemcpyDeviceToHost));
+  }
   if (d->live_docs) {
     std::vector<uint32_t> bits(((size_t)d->n_docs + 31) / 32, 0u);
     for (int32_t i = 0; i < d->n_docs; ++i) if (d->live_docs[i]) bits[i >> 5] |= 1u << (i & 31);
@@ -346,8 +386,11 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
   b->ix = ix; b->nq = nq; b->top_k = top_k;
   b->alg_postings = 0; b->ran = false; b->runs_recorded = 0;
-  b->exhaustive = true;  // TOP_SCORES is served by the exact path too (counts stay EQUAL_TO)
-  (void)flags;
+  // LazyQueueTopScoreDocCollectorManager.java:102: totalHitsThreshold = max(totalHitsThreshold, numHits);
+  // Integer.MAX_VALUE <=> ScoreMode.COMPLETE (LazyQueueTopScoreDocCollector.java:68-70): exact counts, no list skipping
+  b->threshold = (total_hits_threshold == INT32_MAX || (flags & NRTGPU_FLAG_NO_PRUNING))
+                     ? (int64_t)INT32_MAX : (int64_t)std::max(total_hits_threshold, top_k);
+  b->exhaustive = b->threshold == (int64_t)INT32_MAX;
   const int64_t slice_docs = (int64_t)kSliceWindows * kWindowDocs;
   b->n_slices = (int32_t)std::max<int64_t>(1, ((int64_t)ix->n_docs + slice_docs - 1) / slice_docs);
   std::vector<DevClause> dc;
@@ -386,6 +429,11 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
         int64_t df = ix->term_df[c.id];
         // BM25Scorer: weight = boost * idf
         x.weight = c.boost * bm25_idf(df > 0 ? df : 1, ix->field_doc_count[f]);
+        {
+          volatile float t1 = 1.0f + ix->term_max_x[c.id];
+          volatile float t2 = x.weight / t1;
+          x.ub = x.weight - t2;
+        }
         if (required) { o.req_term_mask |= 1u << n_term; ++n_req_term; if (x.n_post < best_req_n) { best_req_n = x.n_post; best_req_slot = n_term; } }
         if (c.occur == NRTGPU_MUST_NOT) o.not_term_mask |= 1u << n_term;
         if (c.occur == NRTGPU_SHOULD) should_term_mask |= 1u << n_term;
@@ -461,6 +509,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if ((rc = b->out_docs.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
+  if ((rc = b->pruned.alloc((size_t)nq))) return rc;
   if (!b->wide_slots) {
     // the stream kernel reads per-granule posting bounds of every (query, term clause): one lower_bound each
     b->n_gran = (int32_t)(((int64_t)ix->n_docs + v2::kGran - 1) / v2::kGran);
@@ -496,6 +545,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->slice_cnt.p, 0, b->slice_cnt.bytes(), st));
+  NRT_CUDA_TRY(cudaMemsetAsync(b->pruned.p, 0, b->pruned.bytes(), st));
   cudaEvent_t* ev = b->ev[b->runs_recorded % nrtgpu_batch::kEvRing];
   NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
   if (b->n_work > 0) {
@@ -511,6 +561,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
       S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.field_min_norm = b->ix->field_min_norm.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
       S.slice_docs = kSliceWindows * kWindowDocs;
+      S.threshold = b->threshold; S.pruned = b->pruned.p;
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
       v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
     } else
@@ -539,8 +590,13 @@ int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float*
   if (out_scores) NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, b->o_scores(), n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (out_counts) NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, b->o_counts(), (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (out_total_hits) NRT_CUDA_TRY(cudaMemcpyAsync(out_total_hits, b->total_hits.p, (size_t)b->nq * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> pr;
+  if (out_relation) {
+    pr.resize((size_t)b->nq);
+    NRT_CUDA_TRY(cudaMemcpyAsync(pr.data(), b->pruned.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   NRT_CUDA_TRY(cudaStreamSynchronize(st));
-  if (out_relation) std::memset(out_relation, b->exhaustive ? 0 : 1, (size_t)b->nq);
+  if (out_relation) for (int i = 0; i < b->nq; ++i) out_relation[i] = pr[(size_t)i] ? 1 : 0;   // 1 = GREATER_THAN_OR_EQUAL_TO
   return NRTGPU_OK;
 }
 

@@ -50,6 +50,8 @@ struct StreamLaunch {
   int32_t n_gran;
   int32_t n_work, n_slices, top_k;
   int32_t slice_docs;
+  int64_t threshold;         // totalHitsThreshold (max(threshold, numHits)); INT32_MAX = exact counts, no list skipping
+  int32_t* pruned;           // [nq] set to 1 when a work item skipped non-essential lists (relation GTE)
   uint64_t* theta;
   unsigned long long* total_hits;
   uint64_t* slice_keys;
@@ -75,6 +77,7 @@ struct alignas(128) StreamSmem {
   int32_t s_ring_base[kT], s_ring_nch[kT];   // first pool chunk and ring length (chunks, power of two) per slot
   uint32_t s_scoring[kT];
   int cand_count;
+  uint32_t ne_mask;
   unsigned long long theta;
 };
 static_assert(sizeof(StreamSmem) <= 232448, "StreamSmem exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -180,8 +183,24 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
 
 // exact score of a doc of a PURE DISJUNCTION over one text field (every slot SHOULD): double sum in slot
 // (= clause) order of the table floats; tf > kTfTab goes through the generic path
+// tf byte of `doc` in the (non-streamed) list of slot t, 0 if absent: binary search inside the doc's granule
+__device__ __forceinline__ uint32_t probe_tf(const StreamLaunch& L, const StreamSmem& sm, int t, int32_t doc, int g) {
+  const DevClause& c = sm.cl[sm.s_clause[t]];
+  const int32_t* docs = L.ix.post_docs + c.post_base;
+  uint32_t lo = sm.gb[t][g], hi = sm.gb[t][g + 1];
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(docs + mid) < doc) lo = mid + 1; else hi = mid; }
+  if (lo < sm.gb[t][g + 1] && __ldg(docs + lo) == doc) return (uint32_t)__ldg(L.ix.post_f8 + c.post_base + lo);
+  return 0u;
+}
+
 __device__ __noinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
-                                                uint32_t v) {
+                                                uint32_t v, uint32_t ne_mask, int32_t slice_base) {
+  if (ne_mask) {   // MAXSCORE: the non-essential lists were not swept; look this doc up in them
+    const int g = (doc - slice_base) >> kLogGran;
+#pragma unroll
+    for (int t = 0; t < kT; ++t)
+      if ((ne_mask >> t) & 1u) v |= probe_tf(L, sm, t, doc, g) << (8 * t);
+  }
   const uint32_t b0 = v & 0xffu, b1 = (v >> 8) & 0xffu, b2 = (v >> 16) & 0xffu, b3 = v >> 24;
   if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) {
     float s = 0.0f;
@@ -246,6 +265,35 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
                   sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
                   sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; }
+  __syncthreads();
+  // ---- MAXSCORE split (pure term disjunctions, once the query has collected more than totalHitsThreshold hits):
+  // the lists whose list-wide score bounds sum (in double, ascending) to less than theta.score are non-essential --
+  // a doc found only in them cannot beat theta, so they are neither streamed nor scattered; docs of the essential
+  // lists that survive the bound test look their tf up in them (probe_tf). Rank-safe; totalHits becomes a lower bound.
+  if (tid == 0) {
+    uint32_t ne = 0;
+    const DevQuery& q = sm.q;
+    const bool simple_q = q.single_field >= 0 && !q.has_nonterm && !q.nonterm_scoring && L.ix.live_bits == nullptr &&
+                          q.n_req == 0 && q.not_term_mask == 0 && q.msm <= 1;
+    if (simple_q && sm.theta != 0ull && L.threshold < (int64_t)INT32_MAX &&
+        (int64_t)*(volatile unsigned long long*)&L.total_hits[qi] > L.threshold) {
+      const float theta_s = key_score(sm.theta);
+      float ub[kT]; int ord[kT]; int n = 0;
+      for (int i = 0; i < q.n_clauses; ++i)
+        if (sm.cl[i].kind == NRTGPU_TERM) { ub[sm.cl[i].slot] = sm.cl[i].ub; ord[n] = sm.cl[i].slot; ++n; }
+      for (int a = 1; a < n; ++a) { int x = ord[a], b = a - 1; while (b >= 0 && ub[ord[b]] > ub[x]) { ord[b + 1] = ord[b]; --b; } ord[b + 1] = x; }
+      double pre = 0.0;
+      for (int a = 0; a < n; ++a) {
+        const double s2 = pre + (double)ub[ord[a]];
+        if (!((float)s2 < theta_s)) break;
+        pre = s2; ne |= 1u << ord[a];
+      }
+    }
+    sm.ne_mask = ne;
+    if (ne) L.pruned[qi] = 1;
+  }
+  __syncthreads();
+  const uint32_t ne_mask = sm.ne_mask;
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
@@ -265,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
-    sm.s_n_chunks[s] = (g1 > g0) ? (int32_t)((g1 - base_g + kCH - 1) >> kLogCH) : 0;
+    sm.s_n_chunks[s] = (g1 > g0 && !((ne_mask >> s) & 1u)) ? (int32_t)((g1 - base_g + kCH - 1) >> kLogCH) : 0;
     sm.s_gdocs[s] = L.ix.post_docs + base_g;
     sm.s_gf8[s] = L.ix.post_f8 + base_g;
     sm.s_scoring[s] = sm.cl[tid].scoring != 0;
@@ -349,7 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
         float u = 0.0f;
-        if (t < n_term && c[t] > 0) u = (c[t] <= kTfTab) ? sm.tbl[t][c[t]][nbmin] : sm.cl[sm.s_clause[t]].weight;
+        if (t < n_term && ((ne_mask >> t) & 1u)) u = sm.cl[sm.s_clause[t]].ub;   // may be present: probed later
+        else if (t < n_term && c[t] > 0) u = (c[t] <= kTfTab) ? sm.tbl[t][c[t]][nbmin] : sm.cl[sm.s_clause[t]].weight;
         sum += (double)u;
       }
       sm.ubt[i] = (float)sum;
@@ -381,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
   int g0 = 0;   // next granule of the slice
+  if (n_term > 0 && ne_mask == ((1u << n_term) - 1u)) g0 = g_count;   // every list is non-essential: skip the slice
   while (g0 < g_count) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
     int g1 = min(g_count, g0 + kWinGran);
@@ -389,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
       bool fits = true;
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
-        cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
+        cnt[t] = ((ne_mask >> t) & 1u) ? 0 : (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
         fits = fits && cnt[t] <= rmask[t] + 1 - kCH;
       }
       if (fits || g1 == g0 + 1) break;   // one granule always fits (<= 2048 postings, ring >= kMinNCH chunks)
@@ -462,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
                   const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
                                       216u * min(v >> 24, 5u);
                   if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v), doc);
+                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v, ne_mask, slice_base), doc);
                   if (key > theta && (!has_after || key < after_key)) {
                     const int p = atomicAdd(&sm.cand_count, 1);
                     if (p < kCand) sm.cand[p] = key;

@@ -205,3 +205,23 @@ def test_argument_errors(gpu_ctx, corpus):
     with pytest.raises(NrtGpuUnsupported):
         s.search_batch([disj(range(1, 11))], RelevanceCollector(10))
     gix.close()
+
+
+def test_top_scores_mode_skips_lists_but_keeps_topk(gpu_ctx):
+    """totalHitsThreshold < MAX (reference default 1000): MAXSCORE list skipping may run; the (doc, score) lists must
+    still equal the exhaustive oracle, totalHits must be exact when EQUAL_TO and a lower bound > threshold otherwise
+    (TotalHitsThresholdTest.java:72-100 semantics)."""
+    sh = ix.synth_text_shard(2_300_000, 50_000, min_len=4, poisson_mean=12.0)   # 3 slices: later slices see a warm theta
+    terms = ix.synth_query_terms(96, 3, 50_000, seed=21, log10_lo=0.3, log10_hi=4.0)
+    qs = [disj(t) for t in terms]
+    gix = GpuIndex(gpu_ctx, sh)
+    res = GpuIndexSearcher(gix).search_batch(qs, RelevanceCollector(100, 1000))
+    gix.close()
+    carr, ncl, qarr, nq = compile_queries(qs)
+    want = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, nq, 100)
+    got = (res.docs, res.scores, res.counts, res.total_hits, res.relation)
+    assert_same_hits(got, want, check_total=False, what="TOP_SCORES")
+    eq = res.relation == 0
+    assert np.array_equal(res.total_hits[eq], want[3][eq])
+    assert (res.total_hits[~eq] <= want[3][~eq]).all() and (res.total_hits[~eq] > 1000).all()
+    assert (~eq).any(), "expected at least one query to skip a non-essential list"
