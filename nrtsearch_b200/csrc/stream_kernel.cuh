@@ -77,7 +77,10 @@ struct alignas(128) StreamSmem {
   int32_t s_ring_base[kT], s_ring_nch[kT];   // first pool chunk and ring length (chunks, power of two) per slot
   uint32_t s_scoring[kT];
   int cand_count;
-  uint32_t ne_mask;
+  uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
+  int32_t ne_n, ne_order[kT];       // ... in descending bound order
+  float ne_ub[kT];
+  int32_t pw_rcur[kT], pw_cnt[kT];  // ring cursor / posting count of every slot in the current window (for probes)
   unsigned long long theta;
 };
 static_assert(sizeof(StreamSmem) <= 232448, "StreamSmem exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -183,23 +186,39 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
 
 // exact score of a doc of a PURE DISJUNCTION over one text field (every slot SHOULD): double sum in slot
 // (= clause) order of the table floats; tf > kTfTab goes through the generic path
-// tf byte of `doc` in the (non-streamed) list of slot t, 0 if absent: binary search inside the doc's granule
-__device__ __forceinline__ uint32_t probe_tf(const StreamLaunch& L, const StreamSmem& sm, int t, int32_t doc, int g) {
-  const DevClause& c = sm.cl[sm.s_clause[t]];
-  const int32_t* docs = L.ix.post_docs + c.post_base;
-  uint32_t lo = sm.gb[t][g], hi = sm.gb[t][g + 1];
-  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(docs + mid) < doc) lo = mid + 1; else hi = mid; }
-  if (lo < sm.gb[t][g + 1] && __ldg(docs + lo) == doc) return (uint32_t)__ldg(L.ix.post_f8 + c.post_base + lo);
+// tf byte of `doc` in the ring segment of slot t that belongs to the current window, 0 if absent
+__device__ __forceinline__ uint32_t probe_ring(const StreamSmem& sm, int t, int32_t doc) {
+  const int32_t base = sm.s_ring_base[t] << kLogCH, mask = (sm.s_ring_nch[t] << kLogCH) - 1, r0 = sm.pw_rcur[t];
+  int32_t lo = 0, hi = sm.pw_cnt[t];
+  const int32_t n = hi;
+  while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (sm.pool_docs[base + ((r0 + mid) & mask)] < doc) lo = mid + 1; else hi = mid; }
+  if (lo < n && sm.pool_docs[base + ((r0 + lo) & mask)] == doc) return (uint32_t)sm.pool_f8[base + ((r0 + lo) & mask)];
   return 0u;
 }
 
 __device__ __noinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
-                                                uint32_t v, uint32_t ne_mask, int32_t slice_base) {
-  if (ne_mask) {   // MAXSCORE: the non-essential lists were not swept; look this doc up in them
-    const int g = (doc - slice_base) >> kLogGran;
+                                                uint32_t v, uint32_t ne_mask, float theta_s) {
+  if (ne_mask) {
+    // MAXSCORE: the non-essential lists were streamed but not swept. Probe them in descending-bound order and stop as
+    // soon as (known scores + bounds of the lists not yet probed) cannot reach theta: the doc is not competitive.
+    const uint32_t nbp = norms0 ? (uint32_t)__ldg(norms0 + doc) : 1u;
+    double known = 0.0;
 #pragma unroll
-    for (int t = 0; t < kT; ++t)
-      if ((ne_mask >> t) & 1u) v |= probe_tf(L, sm, t, doc, g) << (8 * t);
+    for (int t = 0; t < kT; ++t) {
+      const uint32_t b = (v >> (8 * t)) & 0xffu;
+      if (b) known += (double)(b <= (uint32_t)kTfTab ? sm.tbl[t][b][nbp] : sm.cl[sm.s_clause[t]].weight);
+    }
+    for (int a = 0; a < sm.ne_n; ++a) {
+      double rem = 0.0;
+      for (int c = a; c < sm.ne_n; ++c) rem += (double)sm.ne_ub[c];
+      if ((float)(known + rem) < theta_s) return -1.0f;   // below theta whatever the remaining lists hold
+      const int t = sm.ne_order[a];
+      const uint32_t b = probe_ring(sm, t, doc);
+      if (b) {
+        v |= b << (8 * t);
+        known += (double)(b <= (uint32_t)kTfTab ? sm.tbl[t][b][nbp] : sm.cl[sm.s_clause[t]].weight);
+      }
+    }
   }
   const uint32_t b0 = v & 0xffu, b1 = (v >> 8) & 0xffu, b2 = (v >> 16) & 0xffu, b3 = v >> 24;
   if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) {
@@ -268,8 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
   __syncthreads();
   // ---- MAXSCORE split (pure term disjunctions, once the query has collected more than totalHitsThreshold hits):
   // the lists whose list-wide score bounds sum (in double, ascending) to less than theta.score are non-essential --
-  // a doc found only in them cannot beat theta, so they are neither streamed nor scattered; docs of the essential
-  // lists that survive the bound test look their tf up in them (probe_tf). Rank-safe; totalHits becomes a lower bound.
+  // a doc found only in them cannot beat theta, so they are streamed but neither scattered nor swept; docs of the
+  // essential lists that survive the bound test look their tf up in the ring (probe_ring). Rank-safe; totalHits
+  // becomes a lower bound (relation GREATER_THAN_OR_EQUAL_TO).
   if (tid == 0) {
     uint32_t ne = 0;
     const DevQuery& q = sm.q;
@@ -288,7 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
         if (!((float)s2 < theta_s)) break;
         pre = s2; ne |= 1u << ord[a];
       }
-    }
+      int m = 0;
+      for (int a = n - 1; a >= 0; --a) if ((ne >> ord[a]) & 1u) { sm.ne_order[m] = ord[a]; sm.ne_ub[m] = ub[ord[a]]; ++m; }
+      sm.ne_n = m;
+    } else sm.ne_n = 0;
     sm.ne_mask = ne;
     if (ne) L.pruned[qi] = 1;
   }
@@ -313,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
-    sm.s_n_chunks[s] = (g1 > g0 && !((ne_mask >> s) & 1u)) ? (int32_t)((g1 - base_g + kCH - 1) >> kLogCH) : 0;
+    sm.s_n_chunks[s] = (g1 > g0) ? (int32_t)((g1 - base_g + kCH - 1) >> kLogCH) : 0;
     sm.s_gdocs[s] = L.ix.post_docs + base_g;
     sm.s_gf8[s] = L.ix.post_f8 + base_g;
     sm.s_scoring[s] = sm.cl[tid].scoring != 0;
@@ -439,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
       bool fits = true;
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
-        cnt[t] = ((ne_mask >> t) & 1u) ? 0 : (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
+        cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
         fits = fits && cnt[t] <= rmask[t] + 1 - kCH;
       }
       if (fits || g1 == g0 + 1) break;   // one granule always fits (<= 2048 postings, ring >= kMinNCH chunks)
@@ -448,7 +471,21 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
     const int32_t wbase = slice_base + (g0 << kLogGran);
     const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
     g0 = g1;
-    if (!dense && (cnt[0] | cnt[1] | cnt[2] | cnt[3]) == 0) continue;   // nothing in these granules
+    {
+      int32_t ess = 0;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) if (!((ne_mask >> t) & 1u)) ess |= cnt[t];
+      if (!dense && ess == 0) {   // no posting of an essential list in these granules: just advance the streams
+#pragma unroll
+        for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
+        if (tid == 0) issue_chunks();
+        continue;
+      }
+    }
+    if (ne_mask && tid == 0) {
+#pragma unroll
+      for (int t = 0; t < kT; ++t) { sm.pw_rcur[t] = r_cur[t]; sm.pw_cnt[t] = cnt[t]; }
+    }
     // ---------------- residency: every warp waits for the chunks that hold [r_cur, r_cur + cnt)
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
@@ -463,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       if (t >= n_term) break;
+      if ((ne_mask >> t) & 1u) continue;   // non-essential: probed on demand
       const bool scoring = (scoring_bits >> t) & 1u;
       const int32_t* rd = sm.pool_docs + rbase[t];
       const uint8_t* rf = sm.pool_f8 + rbase[t];
@@ -497,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
 #pragma unroll
             for (int t = 0; t < kT; ++t) {
               if (t >= n_term || pending) break;
-              if (!((driver_mask >> t) & 1u)) continue;
+              if (!((driver_mask >> t) & 1u) || ((ne_mask >> t) & 1u)) continue;
               const uint32_t own = 0xffu << (8 * t), bel = below[t];
               const int32_t* rd = sm.pool_docs + rbase[t];
               uint32_t* sl = sm.slots - wbase;
@@ -512,7 +550,9 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
                   const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
                                       216u * min(v >> 24, 5u);
                   if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v, ne_mask, slice_base), doc);
+                  const float sc = score_disjunction(L, sm, norms0, doc, v, ne_mask, theta_s);
+                  if (sc < 0.0f) continue;                          // proven non-competitive while probing
+                  const uint64_t key = make_key(sc, doc);
                   if (key > theta && (!has_after || key < after_key)) {
                     const int p = atomicAdd(&sm.cand_count, 1);
                     if (p < kCand) sm.cand[p] = key;
