@@ -116,7 +116,9 @@ typedef struct {
 /* flags */
 enum {
   NRTGPU_FLAG_NONE = 0,
-  NRTGPU_FLAG_NO_PRUNING = 1 /* force exhaustive evaluation even when total_hits_threshold allows pruning */
+  NRTGPU_FLAG_NO_PRUNING = 1,    /* force exhaustive evaluation even when total_hits_threshold allows pruning */
+  NRTGPU_FLAG_LIST_SKIPPING = 2  /* allow MAXSCORE non-essential list skipping when totalHits > total_hits_threshold:
+                                    same (doc, score) lists, totalHits becomes a lower bound (relation 1) */
 };
 
 /* One-shot search with HOST buffers (the JNI entry point): uploads the batch, runs, copies results

@@ -168,6 +168,7 @@ struct nrtgpu_batch {
   DevBuf<int32_t> work_query, work_slice;
   DevBuf<uint32_t> gbounds;  // stream kernel: [nq][4][n_gran+1]
   DevBuf<int32_t> pruned;    // [nq] relation GTE flags
+  int32_t slice_docs = 0;
   int64_t threshold = INT32_MAX;
   int32_t n_gran = 0;
   DevBuf<uint64_t> theta;
@@ -388,11 +389,13 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   b->alg_postings = 0; b->ran = false; b->runs_recorded = 0;
   // LazyQueueTopScoreDocCollectorManager.java:102: totalHitsThreshold = max(totalHitsThreshold, numHits);
   // Integer.MAX_VALUE <=> ScoreMode.COMPLETE (LazyQueueTopScoreDocCollector.java:68-70): exact counts, no list skipping
-  b->threshold = (total_hits_threshold == INT32_MAX || (flags & NRTGPU_FLAG_NO_PRUNING))
+  // List skipping (MAXSCORE) is opt-in: on this design the exhaustive sweep with the tf-pattern bound test is
+  // faster than probing (measured 19.2 ms vs 23.0 ms at C2), so TOP_SCORES requests are served exactly by default.
+  b->threshold = (total_hits_threshold == INT32_MAX || (flags & NRTGPU_FLAG_NO_PRUNING) || !(flags & NRTGPU_FLAG_LIST_SKIPPING))
                      ? (int64_t)INT32_MAX : (int64_t)std::max(total_hits_threshold, top_k);
   b->exhaustive = b->threshold == (int64_t)INT32_MAX;
-  const int64_t slice_docs = (int64_t)kSliceWindows * kWindowDocs;
-  b->n_slices = (int32_t)std::max<int64_t>(1, ((int64_t)ix->n_docs + slice_docs - 1) / slice_docs);
+  // slice size depends on the kernel: decided after the clauses are known (wide queries / large top_k -> bool_window_kernel)
+  int64_t slice_docs = (int64_t)kSliceWindows * kWindowDocs;
   std::vector<DevClause> dc;
   std::vector<DevQuery> dq((size_t)nq);
   dc.reserve((size_t)n_clauses);
@@ -480,7 +483,10 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
       else o.after_key = make_key(q.after_score, (int32_t)local);
     }
   }
-  b->wide_slots = max_terms > 4;
+  b->wide_slots = max_terms > 4 || top_k > v2::kMaxTopKStream;
+  if (!b->wide_slots) slice_docs = v2::kSliceDocs;
+  b->slice_docs = (int32_t)slice_docs;
+  b->n_slices = (int32_t)std::max<int64_t>(1, ((int64_t)ix->n_docs + slice_docs - 1) / slice_docs);
   // work list, slice-major so that concurrently resident CTAs share postings of the same doc range in L2;
   // inside a slice, longer queries first
   std::vector<int32_t> order;
@@ -560,7 +566,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       v2::StreamLaunch S;
       S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
       S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.field_min_norm = b->ix->field_min_norm.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
-      S.slice_docs = kSliceWindows * kWindowDocs;
+      S.slice_docs = b->slice_docs;
       S.threshold = b->threshold; S.pruned = b->pruned.p;
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
       v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);

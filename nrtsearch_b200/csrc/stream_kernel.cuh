@@ -21,19 +21,35 @@ namespace nrtgpu {
 namespace v2 {
 
 constexpr int kT = 4;
-constexpr int kW = 16384;             // docs per window (one 32-bit word each)
+#ifndef NRT_STREAM_CTAS
+#define NRT_STREAM_CTAS 2
+#endif
+constexpr int kCtasPerSm = NRT_STREAM_CTAS;
 constexpr int kLogCH = 9;
 constexpr int kCH = 1 << kLogCH;      // postings per chunk
-constexpr int kPool = 40;             // chunks in the CTA's ring pool, shared by the term clauses
 constexpr int kMaxNCH = 32;           // largest ring (chunks, power of two)
+#if NRT_STREAM_CTAS == 1
+constexpr int kW = 16384;             // docs per window (one 32-bit word each)
+constexpr int kPool = 40;             // chunks in the CTA's ring pool, shared by the term clauses
 constexpr int kMinNCH = 8;            // a ring always holds one full granule (<= 2048 postings) plus alignment slack
+constexpr int kLogGran = 11;          // posting bounds are precomputed per (query, clause) at 2048-doc granules
+constexpr int kSliceDocs = 1 << 20;   // docs per work item
+constexpr int kCand = 2048;
+constexpr int kTfTab = 4;             // table rows tf = 0..kTfTab (row 0 = 0.0f)
+#else                                 // two CTAs per SM: half the window / ring pool / candidate buffer each
+constexpr int kW = 8192;
+constexpr int kPool = 18;
+constexpr int kMinNCH = 4;            // one 1024-doc granule (<= 1024 postings = 2 chunks) plus alignment slack
+constexpr int kLogGran = 10;
+constexpr int kSliceDocs = 1 << 19;
+constexpr int kCand = 1024;
+constexpr int kTfTab = 2;
+#endif
+constexpr int kMaxTopKStream = kCand / 2;   // larger top_k goes through bool_window_kernel
 #ifndef NRT_STREAM_THREADS
 #define NRT_STREAM_THREADS 512
 #endif
 constexpr int kThreads = NRT_STREAM_THREADS;   // one CTA per SM
-constexpr int kCand = 2048;
-constexpr int kTfTab = 4;             // table rows tf = 0..4 (row 0 = 0.0f)
-constexpr int kLogGran = 11;          // posting bounds are precomputed per (query, clause) at 2048-doc granules
 constexpr int kGran = 1 << kLogGran;
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
@@ -66,7 +82,7 @@ struct alignas(128) StreamSmem {
   float tbl[kT][kTfTab + 1][256];        // 20 KB
   float ubt[kUbt];                       //  5 KB
   uint64_t full_bar[kPool];
-  uint32_t gb[kT][kSliceWindows * kWindowDocs / kGran + 1];   // 8 KB granule bounds of this slice
+  uint32_t gb[kT][kSliceDocs / kGran + 1];   // 8 KB granule bounds of this slice
   DevClause cl[kMaxClauses];
   DevQuery q;
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
@@ -83,7 +99,7 @@ struct alignas(128) StreamSmem {
   int32_t pw_rcur[kT], pw_cnt[kT];  // ring cursor / posting count of every slot in the current window (for probes)
   unsigned long long theta;
 };
-static_assert(sizeof(StreamSmem) <= 232448, "StreamSmem exceeds the 227 KB per-CTA shared memory of sm_100");
+static_assert(sizeof(StreamSmem) <= (kCtasPerSm == 1 ? 232448 : 115712), "StreamSmem exceeds the shared memory budget of sm_100");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -258,7 +274,7 @@ __device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunch L) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(StreamLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -421,7 +437,10 @@ __global__ void __launch_bounds__(kThreads, 1) posting_stream_kernel(StreamLaunc
       for (int t = 0; t < kT; ++t) {
         float u = 0.0f;
         if (t < n_term && ((ne_mask >> t) & 1u)) u = sm.cl[sm.s_clause[t]].ub;   // may be present: probed later
-        else if (t < n_term && c[t] > 0) u = (c[t] <= kTfTab) ? sm.tbl[t][c[t]][nbmin] : sm.cl[sm.s_clause[t]].weight;
+        else if (t < n_term && c[t] > 0) {
+          const DevClause& cl = sm.cl[sm.s_clause[t]];
+          u = (c[t] <= 4) ? bm25_score(cl.weight, (float)c[t], __ldg(&L.ix.caches[cl.field * 256 + nbmin])) : cl.weight;
+        }
         sum += (double)u;
       }
       sm.ubt[i] = (float)sum;
