@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     }
     __syncwarp();
 
-    // ---------------- pass 1: scatter tf bytes (4 postings per step: one 128-bit doc load + one 32-bit tf load)
+    // ---------------- pass 1: scatter tf bytes
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       if (t >= n_term) break;
@@ -524,19 +524,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       const int32_t* rd = sm.pool_docs + rbase[t];
       const uint8_t* rf = sm.pool_f8 + rbase[t];
       unsigned char* sb = slot_bytes + t - 4 * wbase;
-      const int32_t r0 = r_cur[t], n = cnt[t];
-      const int32_t head = min(n, (-r0) & 3);
-      const int32_t ngrp = (n - head) >> 2;
-      if (tid < head) { const int idx = (r0 + tid) & rmask[t]; sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1; }
-      for (int32_t g = tid; g < ngrp; g += kThreads) {
-        const int idx = (r0 + head + 4 * g) & rmask[t];
-        const int4 d = *reinterpret_cast<const int4*>(rd + idx);
-        const uint32_t f = scoring ? *reinterpret_cast<const uint32_t*>(rf + idx) : 0x01010101u;
-        sb[4 * d.x] = (unsigned char)f; sb[4 * d.y] = (unsigned char)(f >> 8);
-        sb[4 * d.z] = (unsigned char)(f >> 16); sb[4 * d.w] = (unsigned char)(f >> 24);
+      for (int32_t i = tid; i < cnt[t]; i += kThreads) {
+        const int idx = (r_cur[t] + i) & rmask[t];
+        sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1;
       }
-      const int32_t tail0 = head + 4 * ngrp;
-      if (tid < n - tail0) { const int idx = (r0 + tail0 + tid) & rmask[t]; sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1; }
     }
     __syncthreads();
     // ---------------- pass 2: owners emit. No barrier inside: a thread whose candidate does not fit the
@@ -569,52 +560,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
               uint32_t* sl = sm.slots - wbase;
               int32_t i = it[t];
               if (simple) {
-                // i counts GROUPS of 4 consecutive postings here (one 128-bit doc load per group)
-                const int32_t r0 = r_cur[t], n = cnt[t];
-                const int32_t ngrp = (n + 3) >> 2;
-                for (; i < ngrp; i += kThreads) {
-                  int32_t dd[4];
-                  const int32_t p0 = 4 * i;
-                  if (((r0 + p0) & 3) == 0 && p0 + 4 <= n) {
-                    const int4 d4 = *reinterpret_cast<const int4*>(rd + ((r0 + p0) & rmask[t]));
-                    dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
-                  } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) dd[u] = (p0 + u < n) ? rd[(r0 + p0 + u) & rmask[t]] : -1;
+                for (; i < cnt[t]; i += kThreads) {
+                  const int32_t doc = rd[(r_cur[t] + i) & rmask[t]];
+                  const uint32_t v = sl[doc];
+                  if ((v & bel) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
+                  sl[doc] = 0u;
+                  ++my_hits;
+                  const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
+                                      216u * min(v >> 24, 5u);
+                  if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
+                  const float sc = score_disjunction(L, sm, norms0, doc, v, ne_mask, theta_s);
+                  if (sc < 0.0f) continue;                          // proven non-competitive while probing
+                  const uint64_t key = make_key(sc, doc);
+                  if (key > theta && (!has_after || key < after_key)) {
+                    const int p = atomicAdd(&sm.cand_count, 1);
+                    if (p < kCand) sm.cand[p] = key;
+                    else { pending = true; pkey = key; i += kThreads; break; }
                   }
-                  uint32_t vv[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) vv[u] = (dd[u] >= 0) ? sl[dd[u]] : 0u;
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const uint32_t v = vv[u];
-                    if ((v & bel) != 0 || (v & own) == 0) continue;   // absent, or a lower driver slot owns this doc
-                    const int32_t doc = dd[u];
-                    sl[doc] = 0u;
-                    ++my_hits;
-                    const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
-                                        216u * min(v >> 24, 5u);
-                    if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                    const float sc = score_disjunction(L, sm, norms0, doc, v, ne_mask, theta_s);
-                    if (sc < 0.0f) continue;                          // proven non-competitive while probing
-                    const uint64_t key = make_key(sc, doc);
-                    if (key > theta && (!has_after || key < after_key)) {
-                      const int p = atomicAdd(&sm.cand_count, 1);
-                      if (p < kCand) sm.cand[p] = key;
-                      else {
-                        // park: finish the group's remaining docs after the compaction by re-offering this key;
-                        // the docs after u in this group are re-read from their (still set) window words
-                        pending = true; pkey = key;
-                        goto parked_simple;
-                      }
-                    }
-                  }
-                }
-                if (false) {
-                parked_simple:
-                  // the unprocessed docs of the group keep their words; a resumed pass starts again at this group
-                  // (processed docs have cleared words and are skipped), so no hit is lost or double counted
-                  ;
                 }
               } else {
                 for (; i < cnt[t]; i += kThreads) {
