@@ -159,6 +159,11 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
                       const float* boosts /*[nq] or NULL*/, const uint8_t* filter /*[n_docs] 0/1 or NULL*/,
                       void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts);
 
+/* same search, plus the device time (ms, CUDA events on `stream`) of its three stages:
+ * stage_ms[0] candidate GEMM (tcgen05 bf16 when dims % 8 == 0), [1] per-query select, [2] exact fp64 re-score */
+int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream,
+                            int32_t* out_docs, float* out_scores, int32_t* out_counts, float* stage_ms);
+
 /* TopDocs.merge over `n_lists` per-shard lists resident on the DEVICE (the receive buffer of the NCCL
  * all-gather): docs/scores [n_lists][nq][top_k], counts [n_lists][nq]; outputs on the device. */
 int nrtgpu_merge_topk_device(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k,

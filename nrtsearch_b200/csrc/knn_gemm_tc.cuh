@@ -1,0 +1,200 @@
+// Tensor-core candidate stage of the kNN path: S[q, d] = <Q[q,:], D[d,:]> for a chunk of the corpus, bf16 inputs,
+// fp32 accumulation in TMEM, hand-written for sm_100a:
+//   * operands are staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier pipeline,
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x 256 x 16) on shared-memory descriptors,
+//   * the 128 x 256 fp32 accumulator lives in TMEM (256 columns) and is read back with tcgen05.ld.32x32b.x32 by four
+//     epilogue warps, which apply the similarity's monotone transform (cosine: / |d|, l2: 2 dot - |d|^2) and store the
+//     approximate scores for the per-query select (knn_select_kernel). The exact fp64 re-score (knn_rescore_kernel)
+//     restores oracle arithmetic for the surviving candidates, so bf16 only affects which k' = 4k candidates survive.
+// Replaces the GEMM-shaped part of ExactVectorQuery's scan
+// (reference src/main/java/com/yelp/nrtsearch/server/query/vector/ExactVectorQuery.java:137-173).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "../../include/nrtgpu.h"
+
+namespace nrtgpu {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, kStages = 4, kUmmaK = 16;
+constexpr int kGemmThreads = 256;   // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 4-7: epilogue
+constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kTmemCols = 256;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(s_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int crd0, int crd1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(crd0), "r"(crd1) : "memory");
+}
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute SmemDescriptor: start>>4 | LBO 1 | SBO 1024 B | version 1 | SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(const void* p) {
+  uint64_t d = (uint64_t)((s_u32(p) >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+
+struct GemmParams {
+  int M, N, K;            // queries, vectors in this chunk, dims
+  int n_base;             // ordinal of the chunk's first vector (row coordinate into the corpus tensor map)
+  const float* dnorm2;    // chunk-relative |d|^2
+  int sim;
+  float* S; int ldS;      // [M][ldS] approximate scores of the chunk
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
+  extern __shared__ uint8_t gemm_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)gemm_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)kStages * kABytes;
+  uint64_t* full_bar = (uint64_t*)(base + (size_t)kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = (P.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
+    bar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // one warp allocates the accumulator columns and publishes the TMEM base address
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        bar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
+        bar_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_2d(smA + (size_t)s * kABytes, &tmA, &full_bar[s], kb * BK, m0);
+        tma_load_2d(smB + (size_t)s * kBBytes, &tmB, &full_bar[s], kb * BK, P.n_base + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer (single thread)
+      // instruction descriptor (cute UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        bar_wait(&full_bar[s], (kb / kStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = make_smem_desc(smA + (size_t)s * kABytes), db = make_smem_desc(smB + (size_t)s * kBBytes);
+#pragma unroll
+        for (int k = 0; k < BK / kUmmaK; ++k)   // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the address field
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);         // accumulator complete
+    }
+  } else if (warp >= 4) {             // ===== epilogue: TMEM -> registers -> global
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    bar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int gq = m0 + row;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (gq < P.M) {
+        float* out = P.S + (size_t)gq * P.ldS + n0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int gd = n0 + c * 32 + j;
+          if (gd < P.N) {
+            float x = __uint_as_float(v[j]);
+            if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(P.dnorm2[gd], 1e-30f));
+            else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - P.dnorm2[gd];
+            out[j] = x;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// 2-D row-major bf16 tensor map [rows][cols], box = box_rows x 64 columns, 128-byte swizzle
+inline int make_tensor_map_bf16(CUtensorMap* map, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return NRTGPU_ERR_CUDA;
+    }
+    fn = (EncodeFn)p;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return NRTGPU_ERR_CUDA; }
+  return NRTGPU_OK;
+}
+
+}  // namespace tc
+}  // namespace nrtgpu

@@ -10,6 +10,7 @@
 // Stage A is the GEMM-shaped part (the tensor-core version replaces only that stage).
 #pragma once
 #include "common.cuh"
+#include "knn_gemm_tc.cuh"
 #include "../../include/nrtgpu.h"
 
 namespace nrtgpu {
@@ -197,15 +198,21 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
 
 struct CudaFreeGuard { void* p; ~CudaFreeGuard() { if (p) cudaFree(p); } };
 
+// d_vec_bf16 / tm_corpus: bf16 copy of the corpus and its TMA tensor map (NULL => SIMT fp32 candidate stage).
+// stage_ms (optional): [0] = candidate GEMM kernels, [1] = select kernels, [2] = exact re-score (CUDA events on st).
 inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32_t* d_vec_docs, int n, int dims, int sim,
                            int doc_base, int n_docs, const float* h_queries, int nq, int k, const float* h_boosts,
                            const uint8_t* h_filter, cudaStream_t st, int32_t* out_docs, float* out_scores,
-                           int32_t* out_counts) {
-  int kprime = 2 * k < 64 ? 64 : 2 * k;
+                           int32_t* out_counts, const __nv_bfloat16* d_vec_bf16 = nullptr,
+                           const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr) {
+  const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr;
+  int kprime = use_tc ? (4 * k < 128 ? 128 : 4 * k) : (2 * k < 64 ? 64 : 2 * k);
   if (kprime > kKnnCandCap - kKnnSelThreads) kprime = kKnnCandCap - kKnnSelThreads;
   float *dQ = nullptr, *dS = nullptr, *dB = nullptr, *dOS = nullptr; uint8_t* dF = nullptr;
   uint64_t* dC = nullptr; int32_t *dCn = nullptr, *dOD = nullptr, *dOC = nullptr;
-  int chunk = n < kKnnChunk ? n : kKnnChunk;
+  const int chunk_max = use_tc ? 65536 : kKnnChunk;
+  int chunk = n < chunk_max ? n : chunk_max;
+  chunk = (chunk + 3) & ~3;   // keep score rows 16-byte aligned
   NRT_CUDA_TRY(cudaMalloc((void**)&dQ, (size_t)nq * dims * sizeof(float))); CudaFreeGuard g1{dQ};
   NRT_CUDA_TRY(cudaMalloc((void**)&dS, (size_t)nq * chunk * sizeof(float))); CudaFreeGuard g2{dS};
   NRT_CUDA_TRY(cudaMalloc((void**)&dC, (size_t)nq * kprime * sizeof(uint64_t))); CudaFreeGuard g3{dC};
@@ -220,20 +227,55 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
                   NRT_CUDA_TRY(cudaMemcpyAsync(dF, h_filter, (size_t)n_docs, cudaMemcpyHostToDevice, st)); }
   NRT_CUDA_TRY(cudaMemcpyAsync(dQ, h_queries, (size_t)nq * dims * sizeof(float), cudaMemcpyHostToDevice, st));
   NRT_CUDA_TRY(cudaMemsetAsync(dCn, 0, (size_t)nq * sizeof(int32_t), st));
+  __nv_bfloat16* dQb = nullptr; CudaFreeGuard g10{nullptr};
+  CUtensorMap tmQ;
+  if (use_tc) {
+    NRT_CUDA_TRY(cudaMalloc((void**)&dQb, (size_t)nq * dims * sizeof(__nv_bfloat16))); g10.p = dQb;
+    tc::f32_to_bf16_kernel<<<256, 256, 0, st>>>(dQ, dQb, (size_t)nq * dims);
+    NRT_CUDA_TRY(cudaGetLastError());
+    int rc = tc::make_tensor_map_bf16(&tmQ, dQb, (uint64_t)nq, (uint64_t)dims, tc::BM);
+    if (rc) return rc;
+  }
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float gemm_ms = 0.f, select_ms = 0.f;
+  if (stage_ms) for (auto& e : ev) NRT_CUDA_TRY(cudaEventCreate(&e));
   for (int base = 0; base < n; base += chunk) {
     int nc = n - base < chunk ? n - base : chunk;
-    dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
-    knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim, dS, chunk);
+    if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (use_tc) {
+      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.sim = sim; G.S = dS; G.ldS = chunk;
+      dim3 grid((nc + tc::BN - 1) / tc::BN, (nq + tc::BM - 1) / tc::BM);
+      tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
+    } else {
+      dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
+      knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim, dS, chunk);
+    }
     NRT_CUDA_TRY(cudaGetLastError());
+    if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
     KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.vec_docs = d_vec_docs;
     S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
     knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
     NRT_CUDA_TRY(cudaGetLastError());
+    if (stage_ms) {
+      NRT_CUDA_TRY(cudaEventRecord(ev[2], st));
+      NRT_CUDA_TRY(cudaEventSynchronize(ev[2]));
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+      gemm_ms += a; select_ms += b;
+    }
   }
+  if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
   KnnRescoreLaunch R; R.Q = dQ; R.D = d_vec; R.dims = dims; R.sim = sim; R.cand = dC; R.cand_cnt = dCn; R.kprime = kprime;
   R.vec_docs = d_vec_docs; R.doc_base = doc_base; R.boosts = dB; R.k = k; R.out_docs = dOD; R.out_scores = dOS; R.out_counts = dOC;
   knn_rescore_kernel<<<nq, 256, 0, st>>>(R);
   NRT_CUDA_TRY(cudaGetLastError());
+  if (stage_ms) {
+    NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
+    NRT_CUDA_TRY(cudaEventSynchronize(ev[1]));
+    float c = 0.f; cudaEventElapsedTime(&c, ev[0], ev[1]);
+    stage_ms[0] = gemm_ms; stage_ms[1] = select_ms; stage_ms[2] = c;
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, dOD, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, dOS, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, dOC, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -135,6 +135,9 @@ struct nrtgpu_index {
   // vectors
   int32_t vec_dims = 0, vec_sim = 0, vec_count = 0;
   DevBuf<float> vectors;
+  DevBuf<__nv_bfloat16> vec_bf16;   // bf16 copy of the corpus for the tensor-core candidate stage (dims % 8 == 0)
+  CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16
+  bool vec_tc = false;
   DevBuf<float> vec_norm2;  // per-vector squared magnitude (double-accumulated, stored float) for cosine
   DevBuf<int32_t> vec_docs;
   int64_t device_bytes = 0;
@@ -219,6 +222,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(BoolSmem<uint64_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
   *out = c;
   return NRTGPU_OK;
 }
@@ -351,10 +355,17 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if (d->vec_docs) { if ((rc = ix->vec_docs.upload(d->vec_docs, (size_t)d->vec_count))) return rc; }
     if ((rc = ix->vec_norm2.alloc((size_t)d->vec_count))) return rc;
     if ((rc = knn_prepare_norms(ix->vectors.p, ix->vec_count, ix->vec_dims, ix->vec_norm2.p))) return rc;
+    if (d->vec_dims % 8 == 0) {   // TMA needs 16-byte row pitch
+      if ((rc = ix->vec_bf16.alloc((size_t)d->vec_count * d->vec_dims))) return rc;
+      tc::f32_to_bf16_kernel<<<1024, 256>>>(ix->vectors.p, ix->vec_bf16.p, (size_t)d->vec_count * d->vec_dims);
+      NRT_CUDA_TRY(cudaGetLastError());
+      if ((rc = tc::make_tensor_map_bf16(&ix->vec_tmap, ix->vec_bf16.p, (uint64_t)d->vec_count, (uint64_t)d->vec_dims, tc::BN))) return rc;
+      ix->vec_tc = true;
+    }
   }
   ix->device_bytes = (int64_t)(ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
                                ix->caches.bytes() + ix->live_bits.bytes() + ix->vectors.bytes() + ix->vec_norm2.bytes() +
-                               ix->vec_docs.bytes());
+                               ix->vec_docs.bytes() + ix->vec_bf16.bytes());
   for (auto& b : ix->norms) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col64) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col32) ix->device_bytes += (int64_t)b->bytes();
@@ -696,9 +707,22 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
   if (ix->vec_dims <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn: index has no vector field");
   if (k <= 0 || k > kMaxTopK) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn: k out of range");
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
                          ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
-                         out_scores, out_counts);
+                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr);
+}
+
+int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream, int32_t* out_docs,
+                            float* out_scores, int32_t* out_counts, float* stage_ms /*[3]: gemm, select, rescore*/) {
+  if (!ix || !queries || !out_docs || !out_scores || !out_counts || !stage_ms) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn_timed: NULL argument");
+  if (ix->vec_dims <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn_timed: index has no vector field");
+  if (k <= 0 || k > kMaxTopK / 4) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_knn_timed: k out of range");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
+  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
+                         ix->doc_base, ix->n_docs, queries, nq, k, nullptr, nullptr, (cudaStream_t)stream, out_docs,
+                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms);
 }
 
 namespace {

@@ -64,3 +64,17 @@ def test_knn_fewer_vectors_than_k(gpu_ctx):
     wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries, 10)
     assert list(gc) == [7, 7, 7]
     check(gd, gs, gc, wd, ws, wc)
+
+
+def test_knn_768_dims_tensor_core_path(gpu_ctx):
+    # C4 shape at reduced N: 768-d cosine, top-100; the bf16 tensor-core stage only picks candidates, the exact
+    # re-score must reproduce the oracle's ids and scores (recall 1.0 expected)
+    corpus = ix.synth_vectors(30_000, 768)
+    queries = ix.synth_vectors(130, 768, seed=ix.SEED_VQUERIES)   # not a multiple of the 128-row MMA tile
+    gix = GpuIndex(gpu_ctx, vec_shard(corpus, ix.SIM_COSINE))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(queries, 100)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries, 100)
+    recall = np.mean([len(set(gd[q]) & set(wd[q])) / 100.0 for q in range(len(queries))])
+    assert recall >= 0.999, recall
+    check(gd, gs, gc, wd, ws, wc)
