@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--threshold", type=int, default=1000, help="totalHitsThreshold (reference default 1000)")
     ap.add_argument("--cpu-sample", type=int, default=512, help="queries in the bounded CPU-baseline sample")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--workload", default="bm25", choices=["bm25", "conj", "knn"],
+                    help="bm25 = configs[1] (the headline line); conj = configs[2]; knn = configs[3] (extra lines, N=1 only)")
+    ap.add_argument("--vectors", type=int, default=1_000_000)
+    ap.add_argument("--dims", type=int, default=768)
     return ap.parse_args()
 
 
@@ -63,7 +67,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -87,6 +91,75 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def make_conj_queries(nq, vocab):
+    """configs[2]: 2 MUST terms + FILTER price in [lo, lo + 1e5] (10 % selective), SURVEY.md App. B."""
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.search import BooleanQuery, Occur, RangeQuery, TermQuery
+    terms = ix.synth_query_terms(nq, 2, vocab)
+    los = (ix.synth_uniform(nq, ix.SEED_RANGE) * 900_000).astype(np.int64)
+    return [BooleanQuery().add(TermQuery(int(t[0])), Occur.MUST).add(TermQuery(int(t[1])), Occur.MUST)
+            .add(RangeQuery(0, int(lo), int(lo) + 100_000), Occur.FILTER) for t, lo in zip(terms, los)]
+
+
+def run_knn(args):
+    """configs[3]: 1M x 768 fp32 vectors, batch-1024 cosine top-100 (exact search; tensor-core candidate stage)."""
+    import torch
+    import __graft_entry__ as g
+    g.build_if_needed()
+    import oracle
+    from nrtsearch_b200 import _native, index as ix
+    from nrtsearch_b200.index import HostShard
+    from nrtsearch_b200.search import GpuContext, GpuIndex
+    n, dims, nq, k = args.vectors, args.dims, args.nq, args.topk
+    corpus = ix.synth_vectors(n, dims)
+    queries = ix.synth_vectors(nq, dims, seed=ix.SEED_VQUERIES)
+    sh = HostShard(n_docs=n, doc_base=0, term_off=np.zeros(1, np.int64), post_docs=np.zeros(0, np.int32),
+                   post_freqs=np.zeros(0, np.int32), fields=[], vectors=corpus, vec_similarity=ix.SIM_COSINE)
+    ctx = GpuContext(0)
+    gix = GpuIndex(ctx, sh)
+    lib = _native.gpu_lib()
+    docs, scores, counts = np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
+    stage = (ctypes.c_float * 3)()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        _native.check(lib.nrtgpu_search_knn_timed(gix.handle, queries.ctypes.data, nq, k, ctypes.c_void_p(stream), docs.ctypes.data,
+                                                  scores.ctypes.data, counts.ctypes.data, stage))
+    for _ in range(args.warmup):
+        call()
+    sampler = ClockSampler(0); sampler.start()
+    gemm, sel, resc, wall = [], [], [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); call(); wall.append(time.perf_counter() - t0)
+        gemm.append(stage[0]); sel.append(stage[1]); resc.append(stage[2])
+    clocks = sampler.stop()
+    ns = min(32, nq)
+    wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries[:ns], k, n_threads=os.cpu_count() or 1)
+    recall = float(np.mean([len(set(docs[q]) & set(wd[q])) / k for q in range(ns)]))
+    t0 = time.perf_counter(); oracle.knn_exact(corpus, ix.SIM_COSINE, queries[:ns], k, n_threads=os.cpu_count() or 1)
+    cpu_qps = ns / (time.perf_counter() - t0)
+    gemm_ms, dev_ms, wall_ms = float(np.mean(gemm)), float(np.mean(gemm) + np.mean(sel) + np.mean(resc)), float(np.mean(wall)) * 1e3
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); peak, src = float(pk["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    flops = 2.0 * nq * n * dims
+    print(json.dumps({
+        "metric": "kNN queries/sec (batch 1024, 1M x 768 cosine top-100, exact)", "value": nq / (dev_ms * 1e-3), "unit": "queries/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16 candidates + f64 exact re-score", "data": "synthetic",
+        "config": {"workload": "configs[3]: 1M x 768-d fp32 vectors, batch-1024 cosine top-100", "vectors": n, "dims": dims, "batch": nq, "top_k": k},
+        "e2e": {"value": nq / (wall_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * dims * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4},
+        "recall_at_k_vs_exact": recall,
+        "roofline": {"bound": "tensor", "kernel": "knn_gemm_bf16_kernel (tcgen05 UMMA 128x256x16, TMEM accumulators, TMA operands)",
+                     "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak,
+                     "traffic": None, "peak_source": src, "gemm_ms": gemm_ms, "select_ms": float(np.mean(sel)), "rescore_ms": float(np.mean(resc))},
+        "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": f"{ns} queries, exact fp64 brute force (oracle/oracle.c), same corpus"},
+        "clocks": clocks}))
+    gix.close(); ctx.close()
 
 
 def make_queries(nq, vocab):
@@ -159,6 +232,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
+    if getattr(args, "workload", "bm25") == "conj":
+        return {"workload": "configs[2]: 10M-doc synthetic, conjunctive AND (2 MUST terms) + int range FILTER, 1024-query batch top-100",
+                "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "top_k": args.topk, "sharding": f"doc-range x{args.gpus}"}
     return {"workload": "configs[1]: 10M-doc synthetic Zipf postings, 1024-query disjunctive BM25 top-100",
             "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "terms_per_query": 3, "top_k": args.topk,
             "total_hits_threshold": args.threshold, "sharding": f"doc-range x{args.gpus}",
@@ -172,6 +248,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.workload == "knn":
+        return run_knn(args) if rank == 0 else None
 
     import torch
     import __graft_entry__ as g
@@ -190,7 +268,15 @@ def main():
 
     t_build = time.perf_counter()
     sh = build_shard(args, rank, world)
-    queries = make_queries(args.nq, args.vocab)
+    if args.workload == "conj":
+        from nrtsearch_b200 import index as ix
+        from nrtsearch_b200.shards import shard_range
+        lo_, hi_ = shard_range(args.docs, rank, world)
+        sh.columns = [ix.synth_int_column(hi_ - lo_, doc_begin=lo_)]
+        sh.column_has = [None]
+        queries = make_conj_queries(args.nq, args.vocab)
+    else:
+        queries = make_queries(args.nq, args.vocab)
     ctx = GpuContext(local_rank)
     gix = GpuIndex(ctx, sh)
     searcher = GpuIndexSearcher(gix)
