@@ -61,7 +61,14 @@ struct GemmParams {
   int n_base;             // ordinal of the chunk's first vector (row coordinate into the corpus tensor map)
   const float* dnorm2;    // chunk-relative |d|^2
   int sim;
-  float* S; int ldS;      // [M][ldS] approximate scores of the chunk
+  float* S; int ldS;      // [M][ldS] approximate scores of the chunk (unfused mode), or NULL
+  // fused top-k' epilogue: a value survives if it is >= the query's running k'-th best approximate score
+  const float* theta;     // [M]
+  uint64_t* cc;           // [M][cc_cap] keys (approx score, ordinal) of this chunk's survivors
+  int* cc_cnt;            // [M] (may exceed cc_cap: overflow, detected by the merge kernel)
+  int cc_cap;
+  const uint8_t* filter;  // per DOC 0/1 or NULL
+  const int32_t* vec_docs;  // ordinal -> doc or NULL
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -142,15 +149,35 @@ knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (gq < P.M) {
-        float* out = P.S + (size_t)gq * P.ldS + n0 + c * 32;
+        if (P.S) {   // unfused: store the approximate scores
+          float* out = P.S + (size_t)gq * P.ldS + n0 + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int gd = n0 + c * 32 + j;
-          if (gd < P.N) {
+          for (int j = 0; j < 32; ++j) {
+            const int gd = n0 + c * 32 + j;
+            if (gd < P.N) {
+              float x = __uint_as_float(v[j]);
+              if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(P.dnorm2[gd], 1e-30f));
+              else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - P.dnorm2[gd];
+              out[j] = x;
+            }
+          }
+        } else {     // fused top-k': keep only values that can still enter the query's best k'
+          const float th = P.theta[gq];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gd = n0 + c * 32 + j;
             float x = __uint_as_float(v[j]);
-            if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(P.dnorm2[gd], 1e-30f));
-            else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - P.dnorm2[gd];
-            out[j] = x;
+            if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(__ldg(P.dnorm2 + min(gd, P.N - 1)), 1e-30f));
+            else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - __ldg(P.dnorm2 + min(gd, P.N - 1));
+            if (gd < P.N && x >= th) {
+              const int ord = P.n_base + gd;
+              bool ok = true;
+              if (P.filter) ok = P.filter[P.vec_docs ? P.vec_docs[ord] : ord] != 0;
+              if (ok) {
+                const int pos = atomicAdd(P.cc_cnt + gq, 1);
+                if (pos < P.cc_cap) P.cc[(size_t)gq * P.cc_cap + pos] = make_key(x, ord);
+              }
+            }
           }
         }
       }

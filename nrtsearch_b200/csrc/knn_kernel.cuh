@@ -196,6 +196,40 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
   if (tid == 0) L.out_counts[q] = keep;
 }
 
+// fused path: fold the survivors of one chunk into the running best-k' list and refresh the query's threshold
+struct KnnMergeChunkLaunch {
+  uint64_t* cc; int* cc_cnt; int cc_cap;
+  uint64_t* cand; int32_t* cand_cnt; int kprime;
+  float* theta; int* overflow;
+};
+
+__global__ void __launch_bounds__(kKnnSelThreads) knn_merge_chunk_kernel(KnnMergeChunkLaunch L) {
+  __shared__ uint64_t buf[kKnnCandCap];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int have = L.cand_cnt[q];
+  int nc = L.cc_cnt[q];
+  if (nc > L.cc_cap) { if (tid == 0) *L.overflow = 1; nc = L.cc_cap; }
+  for (int i = tid; i < have; i += kKnnSelThreads) buf[i] = L.cand[(size_t)q * L.kprime + i];
+  for (int i = tid; i < nc; i += kKnnSelThreads) buf[have + i] = L.cc[(size_t)q * L.cc_cap + i];
+  const int n = have + nc;
+  const int m = next_pow2(n < 2 ? 2 : n);
+  for (int i = n + tid; i < m; i += kKnnSelThreads) buf[i] = 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(buf, m);
+  const int keep = n < L.kprime ? n : L.kprime;
+  for (int i = tid; i < keep; i += kKnnSelThreads) L.cand[(size_t)q * L.kprime + i] = buf[i];
+  if (tid == 0) {
+    L.cand_cnt[q] = keep;
+    L.cc_cnt[q] = 0;
+    if (keep == L.kprime) L.theta[q] = key_score(buf[L.kprime - 1]);
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, int n, float v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 struct CudaFreeGuard { void* p; ~CudaFreeGuard() { if (p) cudaFree(p); } };
 
 // d_vec_bf16 / tm_corpus: bf16 copy of the corpus and its TMA tensor map (NULL => SIMT fp32 candidate stage).
@@ -208,13 +242,27 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr;
   int kprime = use_tc ? (4 * k < 128 ? 128 : 4 * k) : (2 * k < 64 ? 64 : 2 * k);
   if (kprime > kKnnCandCap - kKnnSelThreads) kprime = kKnnCandCap - kKnnSelThreads;
+  bool fused = use_tc && kprime <= 1024;           // best-k' (<= 1024) + chunk survivors (<= 3072) fit one 4096-key sort
+  const int cc_cap = kKnnCandCap - 1024;
   float *dQ = nullptr, *dS = nullptr, *dB = nullptr, *dOS = nullptr; uint8_t* dF = nullptr;
   uint64_t* dC = nullptr; int32_t *dCn = nullptr, *dOD = nullptr, *dOC = nullptr;
   const int chunk_max = use_tc ? 65536 : kKnnChunk;
+  float* dTheta = nullptr; uint64_t* dCC = nullptr; int *dCCn = nullptr, *dOvf = nullptr;
+  CudaFreeGuard g11{nullptr}, g12{nullptr}, g13{nullptr}, g14{nullptr};
+  if (fused) {
+    NRT_CUDA_TRY(cudaMalloc((void**)&dTheta, (size_t)nq * sizeof(float))); g11.p = dTheta;
+    NRT_CUDA_TRY(cudaMalloc((void**)&dCC, (size_t)nq * cc_cap * sizeof(uint64_t))); g12.p = dCC;
+    NRT_CUDA_TRY(cudaMalloc((void**)&dCCn, (size_t)nq * sizeof(int))); g13.p = dCCn;
+    NRT_CUDA_TRY(cudaMalloc((void**)&dOvf, sizeof(int))); g14.p = dOvf;
+    NRT_CUDA_TRY(cudaMemsetAsync(dCCn, 0, (size_t)nq * sizeof(int), st));
+    NRT_CUDA_TRY(cudaMemsetAsync(dOvf, 0, sizeof(int), st));
+    fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(dTheta, nq, -INFINITY);
+  }
   int chunk = n < chunk_max ? n : chunk_max;
   chunk = (chunk + 3) & ~3;   // keep score rows 16-byte aligned
   NRT_CUDA_TRY(cudaMalloc((void**)&dQ, (size_t)nq * dims * sizeof(float))); CudaFreeGuard g1{dQ};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dS, (size_t)nq * chunk * sizeof(float))); CudaFreeGuard g2{dS};
+  if (!fused) NRT_CUDA_TRY(cudaMalloc((void**)&dS, (size_t)nq * chunk * sizeof(float)));
+  CudaFreeGuard g2{dS};
   NRT_CUDA_TRY(cudaMalloc((void**)&dC, (size_t)nq * kprime * sizeof(uint64_t))); CudaFreeGuard g3{dC};
   NRT_CUDA_TRY(cudaMalloc((void**)&dCn, (size_t)nq * sizeof(int32_t))); CudaFreeGuard g4{dCn};
   NRT_CUDA_TRY(cudaMalloc((void**)&dOD, (size_t)nq * k * sizeof(int32_t))); CudaFreeGuard g5{dOD};
@@ -239,11 +287,16 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float gemm_ms = 0.f, select_ms = 0.f;
   if (stage_ms) for (auto& e : ev) NRT_CUDA_TRY(cudaEventCreate(&e));
-  for (int base = 0; base < n; base += chunk) {
-    int nc = n - base < chunk ? n - base : chunk;
+  // fused mode: the first chunks are small (every value survives an empty threshold) and double up to `chunk`
+  int cur = fused ? 2048 : chunk, n_done = 0;
+  for (int base = 0; base < n; base += cur, ++n_done) {
+    if (fused && n_done >= 2 && cur < chunk) cur = cur * 2 < chunk ? cur * 2 : chunk;
+    int nc = n - base < cur ? n - base : cur;
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
     if (use_tc) {
-      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.sim = sim; G.S = dS; G.ldS = chunk;
+      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.sim = sim;
+      G.S = fused ? nullptr : dS; G.ldS = chunk;
+      G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
       dim3 grid((nc + tc::BN - 1) / tc::BN, (nq + tc::BM - 1) / tc::BM);
       tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
     } else {
@@ -252,9 +305,15 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     }
     NRT_CUDA_TRY(cudaGetLastError());
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
-    KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.vec_docs = d_vec_docs;
-    S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
-    knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
+    if (fused) {
+      KnnMergeChunkLaunch Mg; Mg.cc = dCC; Mg.cc_cnt = dCCn; Mg.cc_cap = cc_cap; Mg.cand = dC; Mg.cand_cnt = dCn; Mg.kprime = kprime;
+      Mg.theta = dTheta; Mg.overflow = dOvf;
+      knn_merge_chunk_kernel<<<nq, kKnnSelThreads, 0, st>>>(Mg);
+    } else {
+      KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.vec_docs = d_vec_docs;
+      S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
+      knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
+    }
     NRT_CUDA_TRY(cudaGetLastError());
     if (stage_ms) {
       NRT_CUDA_TRY(cudaEventRecord(ev[2], st));
@@ -262,6 +321,16 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       float a = 0.f, b = 0.f;
       cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
       gemm_ms += a; select_ms += b;
+    }
+  }
+  if (fused) {   // a chunk produced more survivors than the buffer holds (adversarial order): redo without fusion
+    int ovf = 0;
+    NRT_CUDA_TRY(cudaMemcpyAsync(&ovf, dOvf, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NRT_CUDA_TRY(cudaStreamSynchronize(st));
+    if (ovf) {
+      if (stage_ms) for (auto& e : ev) cudaEventDestroy(e);
+      return knn_search_host(d_vec, d_norm2, d_vec_docs, n, dims, sim, doc_base, n_docs, h_queries, nq, k, h_boosts, h_filter, st,
+                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms);
     }
   }
   if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
