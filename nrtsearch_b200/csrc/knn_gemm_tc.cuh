@@ -83,7 +83,9 @@ knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // query tiles vary fastest: the CTAs that share a corpus tile run together, so it is fetched from HBM once and
+  // served to the other query tiles by L2
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_kb = (P.K + BK - 1) / BK;
 
   if (tid == 0) {

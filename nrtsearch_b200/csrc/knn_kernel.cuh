@@ -297,7 +297,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.sim = sim;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
-      dim3 grid((nc + tc::BN - 1) / tc::BN, (nq + tc::BM - 1) / tc::BM);
+      dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
       tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
     } else {
       dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
