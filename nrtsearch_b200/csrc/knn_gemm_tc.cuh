@@ -17,7 +17,11 @@
 namespace nrtgpu {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, kStages = 4, kUmmaK = 16;
+#ifndef NRT_GEMM_STAGES
+#define NRT_GEMM_STAGES 2
+#endif
+constexpr int BM = 128, BN = 256, BK = 64, kStages = NRT_GEMM_STAGES, kUmmaK = 16;
+constexpr int kGemmCtasPerSm = kStages <= 2 ? 2 : 1;   // 2 x (2 stages x 48 KB) fit one SM: the epilogue of one CTA overlaps the mainloop of the other
 constexpr int kGemmThreads = 256;   // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 4-7: epilogue
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kTmemCols = 256;
@@ -71,7 +75,7 @@ struct GemmParams {
   const int32_t* vec_docs;  // ordinal -> doc or NULL
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, kGemmCtasPerSm)
 knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
   extern __shared__ uint8_t gemm_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)gemm_raw + 1023) & ~(uintptr_t)1023);
