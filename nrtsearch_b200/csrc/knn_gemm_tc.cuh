@@ -64,6 +64,7 @@ struct GemmParams {
   int M, N, K;            // queries, vectors in this chunk, dims
   int n_base;             // ordinal of the chunk's first vector (row coordinate into the corpus tensor map)
   const float* dnorm2;    // chunk-relative |d|^2
+  const float2* ab;       // chunk-relative (a, b): approximate score = a * dot + b (cosine: 1/|d|, 0; l2: 2, -|d|^2; else 1, 0)
   int sim;
   float* S; int ldS;      // [M][ldS] approximate scores of the chunk (unfused mode), or NULL
   // fused top-k' epilogue: a value survives if it is >= the query's running k'-th best approximate score
@@ -172,9 +173,8 @@ knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gd = n0 + c * 32 + j;
-            float x = __uint_as_float(v[j]);
-            if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(__ldg(P.dnorm2 + min(gd, P.N - 1)), 1e-30f));
-            else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - __ldg(P.dnorm2 + min(gd, P.N - 1));
+            const float2 ab = __ldg(P.ab + min(gd, P.N - 1));
+            const float x = fmaf(ab.x, __uint_as_float(v[j]), ab.y);
             if (gd < P.N && x >= th) {
               const int ord = P.n_base + gd;
               bool ok = true;

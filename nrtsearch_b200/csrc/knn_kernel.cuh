@@ -32,6 +32,16 @@ __global__ void knn_norm2_kernel(const float* __restrict__ v, int n, int dims, f
   if (lane == 0) out[warp] = (float)s;
 }
 
+// (a, b) with approximate score = a * dot + b, monotone in the final Lucene score of the similarity
+__global__ void knn_ab_kernel(const float* __restrict__ norm2, int n, int sim, float2* __restrict__ ab) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 r = make_float2(1.0f, 0.0f);
+  if (sim == NRTGPU_SIM_COSINE) r.x = rsqrtf(fmaxf(norm2[i], 1e-30f));
+  else if (sim == NRTGPU_SIM_L2) r = make_float2(2.0f, -norm2[i]);
+  ab[i] = r;
+}
+
 inline int knn_prepare_norms(const float* d_vec, int n, int dims, float* d_out) {
   int threads = 256, warps_per_block = threads / 32;
   knn_norm2_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads>>>(d_vec, n, dims, d_out);
@@ -238,8 +248,8 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
                            int doc_base, int n_docs, const float* h_queries, int nq, int k, const float* h_boosts,
                            const uint8_t* h_filter, cudaStream_t st, int32_t* out_docs, float* out_scores,
                            int32_t* out_counts, const __nv_bfloat16* d_vec_bf16 = nullptr,
-                           const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr) {
-  const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr;
+                           const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr, const float2* d_ab = nullptr) {
+  const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr && d_ab != nullptr;
   int kprime = use_tc ? (4 * k < 128 ? 128 : 4 * k) : (2 * k < 64 ? 64 : 2 * k);
   if (kprime > kKnnCandCap - kKnnSelThreads) kprime = kKnnCandCap - kKnnSelThreads;
   bool fused = use_tc && kprime <= 1024;           // best-k' (<= 1024) + chunk survivors (<= 3072) fit one 4096-key sort
@@ -294,7 +304,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     int nc = n - base < cur ? n - base : cur;
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
     if (use_tc) {
-      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.sim = sim;
+      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
       dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);

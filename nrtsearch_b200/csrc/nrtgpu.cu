@@ -137,6 +137,7 @@ struct nrtgpu_index {
   DevBuf<float> vectors;
   DevBuf<__nv_bfloat16> vec_bf16;   // bf16 copy of the corpus for the tensor-core candidate stage (dims % 8 == 0)
   CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16
+  DevBuf<float2> vec_ab;            // per-vector (a, b) of the approximate score a * dot + b
   bool vec_tc = false;
   DevBuf<float> vec_norm2;  // per-vector squared magnitude (double-accumulated, stored float) for cosine
   DevBuf<int32_t> vec_docs;
@@ -360,6 +361,9 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       tc::f32_to_bf16_kernel<<<1024, 256>>>(ix->vectors.p, ix->vec_bf16.p, (size_t)d->vec_count * d->vec_dims);
       NRT_CUDA_TRY(cudaGetLastError());
       if ((rc = tc::make_tensor_map_bf16(&ix->vec_tmap, ix->vec_bf16.p, (uint64_t)d->vec_count, (uint64_t)d->vec_dims, tc::BN))) return rc;
+      if ((rc = ix->vec_ab.alloc((size_t)d->vec_count))) return rc;
+      knn_ab_kernel<<<(d->vec_count + 255) / 256, 256>>>(ix->vec_norm2.p, d->vec_count, d->vec_similarity, ix->vec_ab.p);
+      NRT_CUDA_TRY(cudaGetLastError());
       ix->vec_tc = true;
     }
   }
@@ -710,7 +714,7 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
   const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
                          ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
-                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr);
+                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr, ix->vec_ab.p);
 }
 
 int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream, int32_t* out_docs,
@@ -722,7 +726,7 @@ int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, 
   const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
                          ix->doc_base, ix->n_docs, queries, nq, k, nullptr, nullptr, (cudaStream_t)stream, out_docs,
-                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms);
+                         out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms, ix->vec_ab.p);
 }
 
 namespace {
