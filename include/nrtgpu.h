@@ -116,9 +116,11 @@ typedef struct {
 /* flags */
 enum {
   NRTGPU_FLAG_NONE = 0,
-  NRTGPU_FLAG_NO_PRUNING = 1,    /* force exhaustive evaluation even when total_hits_threshold allows pruning */
-  NRTGPU_FLAG_LIST_SKIPPING = 2  /* allow MAXSCORE non-essential list skipping when totalHits > total_hits_threshold:
-                                    same (doc, score) lists, totalHits becomes a lower bound (relation 1) */
+  NRTGPU_FLAG_NO_PRUNING = 1     /* force exhaustive evaluation (exact totalHits) even when total_hits_threshold < MAX
+                                    would allow MAXSCORE: by default, once a query has collected more than
+                                    total_hits_threshold hits, lists whose score bounds cannot reach the running k-th
+                                    score stop driving the sweep -- same (doc, score) lists, totalHits becomes a lower
+                                    bound (relation 1), exactly the contract of the reference's TOP_SCORES mode */
 };
 
 /* One-shot search with HOST buffers (the JNI entry point): uploads the batch, runs, copies results

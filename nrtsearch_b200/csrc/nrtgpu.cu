@@ -404,9 +404,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   b->alg_postings = 0; b->ran = false; b->runs_recorded = 0;
   // LazyQueueTopScoreDocCollectorManager.java:102: totalHitsThreshold = max(totalHitsThreshold, numHits);
   // Integer.MAX_VALUE <=> ScoreMode.COMPLETE (LazyQueueTopScoreDocCollector.java:68-70): exact counts, no list skipping
-  // List skipping (MAXSCORE) is opt-in: on this design the exhaustive sweep with the tf-pattern bound test is
-  // faster than probing (measured 19.2 ms vs 23.0 ms at C2), so TOP_SCORES requests are served exactly by default.
-  b->threshold = (total_hits_threshold == INT32_MAX || (flags & NRTGPU_FLAG_NO_PRUNING) || !(flags & NRTGPU_FLAG_LIST_SKIPPING))
+  b->threshold = (total_hits_threshold == INT32_MAX || (flags & NRTGPU_FLAG_NO_PRUNING))
                      ? (int64_t)INT32_MAX : (int64_t)std::max(total_hits_threshold, top_k);
   b->exhaustive = b->threshold == (int64_t)INT32_MAX;
   // slice size depends on the kernel: decided after the clauses are known (wide queries / large top_k -> bool_window_kernel)

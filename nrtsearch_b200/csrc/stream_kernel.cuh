@@ -94,9 +94,6 @@ struct alignas(128) StreamSmem {
   uint32_t s_scoring[kT];
   int cand_count;
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
-  int32_t ne_n, ne_order[kT];       // ... in descending bound order
-  float ne_ub[kT];
-  int32_t pw_rcur[kT], pw_cnt[kT];  // ring cursor / posting count of every slot in the current window (for probes)
   unsigned long long theta;
 };
 static_assert(sizeof(StreamSmem) <= (kCtasPerSm == 1 ? 232448 : 115712), "StreamSmem exceeds the shared memory budget of sm_100");
@@ -202,40 +199,8 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
 
 // exact score of a doc of a PURE DISJUNCTION over one text field (every slot SHOULD): double sum in slot
 // (= clause) order of the table floats; tf > kTfTab goes through the generic path
-// tf byte of `doc` in the ring segment of slot t that belongs to the current window, 0 if absent
-__device__ __forceinline__ uint32_t probe_ring(const StreamSmem& sm, int t, int32_t doc) {
-  const int32_t base = sm.s_ring_base[t] << kLogCH, mask = (sm.s_ring_nch[t] << kLogCH) - 1, r0 = sm.pw_rcur[t];
-  int32_t lo = 0, hi = sm.pw_cnt[t];
-  const int32_t n = hi;
-  while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (sm.pool_docs[base + ((r0 + mid) & mask)] < doc) lo = mid + 1; else hi = mid; }
-  if (lo < n && sm.pool_docs[base + ((r0 + lo) & mask)] == doc) return (uint32_t)sm.pool_f8[base + ((r0 + lo) & mask)];
-  return 0u;
-}
-
 __device__ __noinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
-                                                uint32_t v, uint32_t ne_mask, float theta_s) {
-  if (ne_mask) {
-    // MAXSCORE: the non-essential lists were streamed but not swept. Probe them in descending-bound order and stop as
-    // soon as (known scores + bounds of the lists not yet probed) cannot reach theta: the doc is not competitive.
-    const uint32_t nbp = norms0 ? (uint32_t)__ldg(norms0 + doc) : 1u;
-    double known = 0.0;
-#pragma unroll
-    for (int t = 0; t < kT; ++t) {
-      const uint32_t b = (v >> (8 * t)) & 0xffu;
-      if (b) known += (double)(b <= (uint32_t)kTfTab ? sm.tbl[t][b][nbp] : sm.cl[sm.s_clause[t]].weight);
-    }
-    for (int a = 0; a < sm.ne_n; ++a) {
-      double rem = 0.0;
-      for (int c = a; c < sm.ne_n; ++c) rem += (double)sm.ne_ub[c];
-      if ((float)(known + rem) < theta_s) return -1.0f;   // below theta whatever the remaining lists hold
-      const int t = sm.ne_order[a];
-      const uint32_t b = probe_ring(sm, t, doc);
-      if (b) {
-        v |= b << (8 * t);
-        known += (double)(b <= (uint32_t)kTfTab ? sm.tbl[t][b][nbp] : sm.cl[sm.s_clause[t]].weight);
-      }
-    }
-  }
+                                                uint32_t v) {
   const uint32_t b0 = v & 0xffu, b1 = (v >> 8) & 0xffu, b2 = (v >> 16) & 0xffu, b3 = v >> 24;
   if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) {
     float s = 0.0f;
@@ -303,9 +268,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   __syncthreads();
   // ---- MAXSCORE split (pure term disjunctions, once the query has collected more than totalHitsThreshold hits):
   // the lists whose list-wide score bounds sum (in double, ascending) to less than theta.score are non-essential --
-  // a doc found only in them cannot beat theta, so they are streamed but neither scattered nor swept; docs of the
-  // essential lists that survive the bound test look their tf up in the ring (probe_ring). Rank-safe; totalHits
-  // becomes a lower bound (relation GREATER_THAN_OR_EQUAL_TO).
+  // a doc found only in them cannot beat theta. They are still streamed and scattered (so the owners of the
+  // essential lists see their exact tf -- no probing), but they do not drive pass 2: their postings are only cleared
+  // in pass 3 (~half the per-posting work). Rank-safe; docs matching only non-essential lists are not counted, so
+  // totalHits becomes a lower bound (relation GREATER_THAN_OR_EQUAL_TO).
   if (tid == 0) {
     uint32_t ne = 0;
     const DevQuery& q = sm.q;
@@ -324,10 +290,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         if (!((float)s2 < theta_s)) break;
         pre = s2; ne |= 1u << ord[a];
       }
-      int m = 0;
-      for (int a = n - 1; a >= 0; --a) if ((ne >> ord[a]) & 1u) { sm.ne_order[m] = ord[a]; sm.ne_ub[m] = ub[ord[a]]; ++m; }
-      sm.ne_n = m;
-    } else sm.ne_n = 0;
+    }
     sm.ne_mask = ne;
     if (ne) L.pruned[qi] = 1;
   }
@@ -436,8 +399,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
         float u = 0.0f;
-        if (t < n_term && ((ne_mask >> t) & 1u)) u = sm.cl[sm.s_clause[t]].ub;   // may be present: probed later
-        else if (t < n_term && c[t] > 0) {
+        if (t < n_term && c[t] > 0) {
           const DevClause& cl = sm.cl[sm.s_clause[t]];
           u = (c[t] <= 4) ? bm25_score(cl.weight, (float)c[t], __ldg(&L.ix.caches[cl.field * 256 + nbmin])) : cl.weight;
         }
@@ -454,8 +416,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   const bool dense = sm.q.dense_driver != 0;
   const bool has_after = sm.q.has_after != 0;
   const uint64_t after_key = sm.q.after_key;
-  const uint32_t driver_mask = sm.q.driver_mask;
-  const bool has_non_driver = sm.q.has_non_driver != 0;
+  const uint32_t driver_mask = sm.q.driver_mask & ~ne_mask;            // non-essential lists never own a doc
+  const bool has_non_driver = sm.q.has_non_driver != 0 || ne_mask != 0;  // ... pass 3 clears their words
   const uint8_t* norms0 = (sm.q.single_field >= 0) ? L.ix.norms[sm.q.single_field] : nullptr;
   uint32_t scoring_bits = 0;
 #pragma unroll
@@ -501,10 +463,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         continue;
       }
     }
-    if (ne_mask && tid == 0) {
-#pragma unroll
-      for (int t = 0; t < kT; ++t) { sm.pw_rcur[t] = r_cur[t]; sm.pw_cnt[t] = cnt[t]; }
-    }
+
     // ---------------- residency: every warp waits for the chunks that hold [r_cur, r_cur + cnt)
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
@@ -519,7 +478,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       if (t >= n_term) break;
-      if ((ne_mask >> t) & 1u) continue;   // non-essential: probed on demand
       const bool scoring = (scoring_bits >> t) & 1u;
       const int32_t* rd = sm.pool_docs + rbase[t];
       const uint8_t* rf = sm.pool_f8 + rbase[t];
@@ -554,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
             for (int t = 0; t < kT; ++t) {
               if (t >= n_term || pending) break;
-              if (!((driver_mask >> t) & 1u) || ((ne_mask >> t) & 1u)) continue;
+              if (!((driver_mask >> t) & 1u)) continue;
               const uint32_t own = 0xffu << (8 * t), bel = below[t];
               const int32_t* rd = sm.pool_docs + rbase[t];
               uint32_t* sl = sm.slots - wbase;
@@ -569,9 +527,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
                   const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
                                       216u * min(v >> 24, 5u);
                   if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                  const float sc = score_disjunction(L, sm, norms0, doc, v, ne_mask, theta_s);
-                  if (sc < 0.0f) continue;                          // proven non-competitive while probing
-                  const uint64_t key = make_key(sc, doc);
+                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v), doc);
                   if (key > theta && (!has_after || key < after_key)) {
                     const int p = atomicAdd(&sm.cand_count, 1);
                     if (p < kCand) sm.cand[p] = key;

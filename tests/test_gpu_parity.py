@@ -215,7 +215,7 @@ def test_top_scores_mode_skips_lists_but_keeps_topk(gpu_ctx):
     terms = ix.synth_query_terms(96, 3, 50_000, seed=21, log10_lo=0.3, log10_hi=4.0)
     qs = [disj(t) for t in terms]
     gix = GpuIndex(gpu_ctx, sh)
-    batch = GpuIndexSearcher(gix).prepare(qs, RelevanceCollector(100, 1000), flags=2)   # NRTGPU_FLAG_LIST_SKIPPING
+    batch = GpuIndexSearcher(gix).prepare(qs, RelevanceCollector(100, 1000))
     batch.run()
     res = batch.fetch()
     batch.close()
