@@ -349,6 +349,27 @@ def main():
     ms_per_step = ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
 
+    # ---- the same batch with exact counts (ScoreMode.COMPLETE: every posting swept, no MAXSCORE): the exhaustive
+    #      kernel's roofline, reported beside the default TOP_SCORES run
+    exh_ms = None
+    if args.threshold != 2**31 - 1:
+        bex = searcher.prepare(queries, RelevanceCollector(args.topk, 2**31 - 1))
+        bex.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
+        for _ in range(2):
+            bex.run(stream)
+        torch.cuda.synchronize()
+        bex.reset_timing()
+        for _ in range(5):
+            bex.run(stream)
+        torch.cuda.synchronize()
+        exh_ms = bex.stage_ms(0)
+        bex.close()
+        batch.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
+        if world > 1:
+            t = torch.tensor([exh_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exh_ms = float(t[0])
+
     # ---- e2e: the public one-shot call with HOST buffers, every step: H2D plan + D2H results
     carr, ncl, qarr, _ = compile_queries(queries)
     h2d = ctypes.sizeof(carr) + ctypes.sizeof(qarr)
@@ -396,7 +417,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel (TMA-streamed posting traversal + BM25 + exact top-k)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
-                         "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world},
+                         "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world,
+                         "mode": "TOP_SCORES (totalHitsThreshold %d: MAXSCORE may stop lists from driving)" % args.threshold
+                                 if args.threshold != 2**31 - 1 else "COMPLETE (every posting swept)",
+                         "exhaustive": None if exh_ms is None else
+                                       {"kernel_ms": exh_ms, "achieved": alg_bytes / (exh_ms * 1e-3) / 1e9,
+                                        "frac": alg_bytes / (exh_ms * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "index": {"postings": int(sh.term_off[-1]), "device_bytes": gix.device_bytes, "build_s": build_s,
