@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--threshold", type=int, default=1000, help="totalHitsThreshold (reference default 1000)")
     ap.add_argument("--cpu-sample", type=int, default=512, help="queries in the bounded CPU-baseline sample")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--workload", default="bm25", choices=["bm25", "conj", "knn"],
+    ap.add_argument("--workload", default="bm25", choices=["bm25", "conj", "knn", "hybrid"],
                     help="bm25 = configs[1] (the headline line); conj = configs[2]; knn = configs[3] (extra lines, N=1 only)")
     ap.add_argument("--vectors", type=int, default=1_000_000)
     ap.add_argument("--dims", type=int, default=768)
@@ -162,6 +162,50 @@ def run_knn(args):
     gix.close(); ctx.close()
 
 
+def run_hybrid(args):
+    """configs[4] shape on one shard: text retriever (3-term disjunction, top-100) + kNN retriever (k = 100) ->
+    weighted RRF (rankConstant 60, boosts 1) -> top-100, every stage through the C ABI with host buffers."""
+    import __graft_entry__ as g
+    g.build_if_needed()
+    import oracle
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.search import GpuContext, GpuIndex, GpuIndexSearcher, RelevanceCollector, blend_rrf, compile_queries
+    n, dims, nq, k = args.docs, args.dims, args.nq, args.topk
+    sh = ix.synth_text_shard(n, args.vocab)
+    sh.term_df = np.diff(sh.term_off).astype(np.int64)
+    sh.vectors = ix.synth_vectors(n, dims)
+    sh.vec_similarity = ix.SIM_COSINE
+    queries = make_queries(nq, args.vocab)
+    qvec = ix.synth_vectors(nq, dims, seed=ix.SEED_VQUERIES)
+    ctx = GpuContext(0); gix = GpuIndex(ctx, sh); s = GpuIndexSearcher(gix)
+    coll = RelevanceCollector(k, args.threshold)
+
+    def step():
+        t = s.search_batch(queries, coll)
+        kd, ks, kc = s.knn(qvec, k)
+        return blend_rrf(ctx, np.stack([t.docs, kd]), np.stack([t.counts, kc]), [1.0, 1.0], 60, k), t, (kd, ks, kc)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        (bd, bs, bc, bt), t, kn = step()
+    dt = (time.perf_counter() - t0) / args.steps
+    # parity of the whole pipeline on a sample
+    ns = min(16, nq)
+    carr, ncl, qarr, _ = compile_queries(queries[:ns])
+    od, os_, oc, _, _ = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, ns, k)
+    kd, ks, kc = oracle.knn_exact(sh.vectors, ix.SIM_COSINE, qvec[:ns], k, n_threads=os.cpu_count() or 1)
+    same = 0
+    for q in range(ns):
+        wd, ws, wt = oracle.blend_rrf(np.stack([od[q], kd[q]]), [oc[q], kc[q]], [1.0, 1.0], 60, k)
+        same += int(np.array_equal(bd[q, :bc[q]], wd) and np.allclose(bs[q, :bc[q]], ws, rtol=1e-6))
+    print(json.dumps({"metric": "hybrid BM25 + kNN + weighted-RRF queries/sec (batch 1024, one shard)", "value": nq / dt, "unit": "queries/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                      "data": "synthetic", "config": {"workload": "configs[4] shape, single shard", "docs": n, "dims": dims, "batch": nq, "top_k": k},
+                      "parity_sample": {"queries": ns, "identical_to_oracle_pipeline": same}}))
+    gix.close(); ctx.close()
+
+
 def make_queries(nq, vocab):
     from nrtsearch_b200 import index as ix
     from nrtsearch_b200.search import BooleanQuery, Occur, TermQuery
@@ -250,6 +294,8 @@ def main():
         return run_reference(args, rank, world)
     if args.workload == "knn":
         return run_knn(args) if rank == 0 else None
+    if args.workload == "hybrid":
+        return run_hybrid(args) if rank == 0 else None
 
     import torch
     import __graft_entry__ as g

@@ -76,3 +76,31 @@ def test_cross_shard_merge_on_device(gpu_ctx):
     gd, gs = od.cpu().numpy().reshape(nq, k), os_.cpu().numpy().reshape(nq, k)
     for q in range(nq):
         assert np.array_equal(gd[q, :gc[q]], wd[q, :gc[q]]) and np.array_equal(gs[q, :gc[q]], ws[q, :gc[q]])
+
+
+def test_hybrid_pipeline_equals_oracle_pipeline(gpu_ctx):
+    """text retriever + kNN retriever + weighted RRF, stage by stage through the C ABI (SearchHandler.executeMultiRetriever
+    :528-667 shape): the blended page must equal the oracle pipeline's."""
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.search import (BooleanQuery, GpuIndex, GpuIndexSearcher, Occur, RelevanceCollector, TermQuery,
+                                       compile_queries)
+    n, dims, nq, k = 30_000, 64, 24, 50
+    sh = ix.synth_text_shard(n, 3_000)
+    sh.vectors = ix.synth_vectors(n, dims)
+    sh.vec_similarity = ix.SIM_COSINE
+    terms = ix.synth_query_terms(nq, 3, 3_000, log10_lo=0.3, log10_hi=3.0)
+    qs = [BooleanQuery().add(TermQuery(int(t[0])), Occur.SHOULD).add(TermQuery(int(t[1])), Occur.SHOULD)
+          .add(TermQuery(int(t[2])), Occur.SHOULD) for t in terms]
+    qv = ix.synth_vectors(nq, dims, seed=ix.SEED_VQUERIES)
+    gix = GpuIndex(gpu_ctx, sh)
+    s = GpuIndexSearcher(gix)
+    t = s.search_batch(qs, RelevanceCollector(k, 2**31 - 1))
+    kd, ks, kc = s.knn(qv, k)
+    bd, bs, bc, bt = blend_rrf(gpu_ctx, np.stack([t.docs, kd]), np.stack([t.counts, kc]), [1.0, 2.0], 60, k)
+    gix.close()
+    od, os_, oc, _, _ = oracle.search_compiled(oracle.OracleIndex(sh), *compile_queries(qs), k)
+    wkd, wks, wkc = oracle.knn_exact(sh.vectors, ix.SIM_COSINE, qv, k)
+    assert np.array_equal(t.docs, od) and np.array_equal(kd, wkd)
+    for q in range(nq):
+        wd, ws, wt = oracle.blend_rrf(np.stack([od[q], wkd[q]]), [oc[q], wkc[q]], [1.0, 2.0], 60, k)
+        assert bt[q] == wt and np.array_equal(bd[q, :bc[q]], wd) and np.array_equal(bs[q, :bc[q]].view(np.uint32), ws.view(np.uint32))
