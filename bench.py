@@ -58,30 +58,47 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (rows are time-stamped on arrival;
+    mark() brackets the region)."""
 
     def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+        self.rows, self.proc, self.device, self.t0, self.t1 = [], None, device, None, None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "25",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                         bufsize=1)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def ready(self):
+        return self.proc is None or len(self.rows) > 0
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
+        t0 = self.t0 or 0.0
+        t1 = self.t1 or time.time()
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03]
+        if not inside and self.rows:   # region shorter than one sampling period: take the sample closest to it
+            inside = [min(self.rows, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[1]]
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -127,13 +144,18 @@ def run_knn(args):
     def call():
         _native.check(lib.nrtgpu_search_knn_timed(gix.handle, queries.ctypes.data, nq, k, ctypes.c_void_p(stream), docs.ctypes.data,
                                                   scores.ctypes.data, counts.ctypes.data, stage))
+    sampler = ClockSampler(0); sampler.start()
     for _ in range(args.warmup):
         call()
-    sampler = ClockSampler(0); sampler.start()
+    t_wait = time.time()
+    while not sampler.ready() and time.time() - t_wait < 1.5:
+        call()
     gemm, sel, resc, wall = [], [], [], []
+    sampler.mark_begin()
     for _ in range(args.steps):
         t0 = time.perf_counter(); call(); wall.append(time.perf_counter() - t0)
         gemm.append(stage[0]); sel.append(stage[1]); resc.append(stage[2])
+    sampler.mark_end()
     clocks = sampler.stop()
     ns = min(32, nq)
     wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries[:ns], k, n_threads=os.cpu_count() or 1)
@@ -365,20 +387,27 @@ def main():
             assert np.array_equal(got_docs, ref[0]), "bench: GPU top-k doc ids differ from the CPU oracle"
             assert np.array_equal(got_scores.view(np.uint32), ref[1].view(np.uint32)), "bench: GPU scores differ from the oracle"
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    batch.reset_timing()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if rank == 0:   # keep the GPU under the same load until the clock sampler delivers (at most ~1.5 s of extra warm-up)
+        t_wait = time.time()
+        while not sampler.ready() and time.time() - t_wait < 1.5:
+            batch.run(stream); torch.cuda.synchronize()
+    barrier()
+    batch.reset_timing()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     kernel_ms = batch.stage_ms(0)
