@@ -275,13 +275,17 @@ static void search_one_pruned_disjunction(const orc_index* ix, cl_t* cl, int ncl
   for (int i = 0; i < n; ++i) order[i] = i;
   for (int i = 1; i < n; ++i) { int x = order[i], j = i - 1; while (j >= 0 && cl[order[j]].max_score > cl[x].max_score) { order[j + 1] = order[j]; --j; } order[j + 1] = x; }
   int pruned = 0;
-  /* DAAT over essential lists */
+  /* DAAT over essential lists; the essential split is recomputed only when theta changes */
+  float last_theta = -INFINITY;
+  int first_ess = 0;
   for (;;) {
     float theta = (col->total_hits > threshold) ? collector_min_competitive(col) : -INFINITY;
-    /* essential split: largest prefix (in ascending max-score order) whose double sum of bounds cannot
-     * exceed theta on its own */
-    int first_ess = 0; double pre = 0.0;
-    if (theta > -INFINITY) {
+    if (theta != last_theta) {
+      /* essential split: largest prefix (in ascending max-score order) whose double sum of bounds cannot
+       * exceed theta on its own */
+      last_theta = theta;
+      first_ess = 0;
+      double pre = 0.0;
       while (first_ess < n) {
         double s2 = pre + (double)cl[order[first_ess]].max_score;
         if ((float)s2 > theta) break; /* a doc only in the prefix scores <= theta: not competitive (ties lose: later doc) */
@@ -294,9 +298,7 @@ static void search_one_pruned_disjunction(const orc_index* ix, cl_t* cl, int ncl
     int32_t d = INT32_MAX;
     for (int i = first_ess; i < n; ++i) { cl_t* c = &cl[order[i]]; if (c->cur < c->n && c->docs[c->cur] < d) d = c->docs[c->cur]; }
     if (d == INT32_MAX) break;
-    /* score in CLAUSE order (double sum), probing non-essential lists by galloping advance */
-    double sum = 0.0; int matched = 0;
-    /* advance non-essential cursors lazily to >= d */
+    /* advance non-essential cursors lazily to >= d (galloping) */
     for (int i = 0; i < first_ess; ++i) {
       cl_t* c = &cl[order[i]];
       if (c->cur < c->n && c->docs[c->cur] < d) {
@@ -306,7 +308,9 @@ static void search_one_pruned_disjunction(const orc_index* ix, cl_t* cl, int ncl
         c->cur = lower_bound_i32(c->docs, lo, hi, d);
       }
     }
-    for (int i = 0; i < n; ++i) { /* clause order */
+    /* score in CLAUSE order (double sum) */
+    double sum = 0.0; int matched = 0;
+    for (int i = 0; i < n; ++i) {
       cl_t* c = &cl[i];
       if (c->cur < c->n && c->docs[c->cur] == d) { sum += (double)clause_term_score(c, d, c->freqs[c->cur]); matched++; }
     }
