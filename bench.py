@@ -481,6 +481,14 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = alg_postings_total / world * ALG_BYTES_PER_POSTING + nq * k * 8   # per launch (per GPU)
+        traffic = None   # physical DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["posting_stream_kernel"]
+            if (world == 1 and args.workload == "bm25" and args.docs == 10_000_000 and args.vocab == 1_000_000 and nq == 1024
+                    and k == 100 and args.threshold == 1000):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "BM25 queries/sec (batch 1024, 10M docs)", "value": qps, "unit": "queries/s", "n_gpus": world,
@@ -490,7 +498,7 @@ def main():
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": stats["launches_per_run"] * args.steps + (args.steps if world > 1 else 0),
             "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel (TMA-streamed posting traversal + BM25 + exact top-k)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
                          "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world,
                          "mode": "TOP_SCORES (totalHitsThreshold %d: MAXSCORE may stop lists from driving)" % args.threshold
