@@ -199,14 +199,16 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
 
 // exact score of a doc of a PURE DISJUNCTION over one text field (every slot SHOULD): double sum in slot
 // (= clause) order of the table floats; tf > kTfTab goes through the generic path
-__device__ __noinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
-                                                uint32_t v) {
+__device__ __noinline__ float score_disjunction_slow(const StreamLaunch& L, const StreamSmem& sm, int32_t doc, uint32_t v) {
+  float s = 0.0f;
+  evaluate_doc_generic(L, sm, doc, v, &s);
+  return s;
+}
+
+__device__ __forceinline__ float score_disjunction(const StreamLaunch& L, const StreamSmem& sm, const uint8_t* norms0, int32_t doc,
+                                                   uint32_t v) {
   const uint32_t b0 = v & 0xffu, b1 = (v >> 8) & 0xffu, b2 = (v >> 16) & 0xffu, b3 = v >> 24;
-  if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) {
-    float s = 0.0f;
-    evaluate_doc_generic(L, sm, doc, v, &s);
-    return s;
-  }
+  if (max(max(b0, b1), max(b2, b3)) > (uint32_t)kTfTab) return score_disjunction_slow(L, sm, doc, v);
   const uint32_t nb = norms0 ? (uint32_t)__ldg(norms0 + doc) : 1u;
   double sum = (double)sm.tbl[0][b0][nb];   // rows tf = 0 hold +0.0f: adding them leaves the sum bit-identical
   sum += (double)sm.tbl[1][b1][nb];
