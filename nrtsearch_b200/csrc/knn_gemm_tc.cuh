@@ -76,6 +76,42 @@ struct GemmParams {
   const int32_t* vec_docs;  // ordinal -> doc or NULL
 };
 
+// one 32-column slice of an accumulator row: store the approximate scores (unfused) or keep the survivors (fused)
+__device__ __forceinline__ void epilogue_slice(const GemmParams& P, const uint32_t (&v)[32], int gq, int n0, int c) {
+  if (gq < P.M) {
+    if (P.S) {   // unfused: store the approximate scores
+      float* out = P.S + (size_t)gq * P.ldS + n0 + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gd = n0 + c * 32 + j;
+        if (gd < P.N) {
+          float x = __uint_as_float(v[j]);
+          if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(P.dnorm2[gd], 1e-30f));
+          else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - P.dnorm2[gd];
+          out[j] = x;
+        }
+      }
+    } else {     // fused top-k': keep only values that can still enter the query's best k'
+      const float th = P.theta[gq];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gd = n0 + c * 32 + j;
+        const float2 ab = __ldg(P.ab + min(gd, P.N - 1));
+        const float x = fmaf(ab.x, __uint_as_float(v[j]), ab.y);
+        if (gd < P.N && x >= th) {
+          const int ord = P.n_base + gd;
+          bool ok = true;
+          if (P.filter) ok = P.filter[P.vec_docs ? P.vec_docs[ord] : ord] != 0;
+          if (ok) {
+            const int pos = atomicAdd(P.cc_cnt + gq, 1);
+            if (pos < P.cc_cap) P.cc[(size_t)gq * P.cc_cap + pos] = make_key(x, ord);
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, kGemmCtasPerSm)
 knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
   extern __shared__ uint8_t gemm_raw[];
@@ -155,38 +191,7 @@ knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (gq < P.M) {
-        if (P.S) {   // unfused: store the approximate scores
-          float* out = P.S + (size_t)gq * P.ldS + n0 + c * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gd = n0 + c * 32 + j;
-            if (gd < P.N) {
-              float x = __uint_as_float(v[j]);
-              if (P.sim == NRTGPU_SIM_COSINE) x = x * rsqrtf(fmaxf(P.dnorm2[gd], 1e-30f));
-              else if (P.sim == NRTGPU_SIM_L2) x = 2.0f * x - P.dnorm2[gd];
-              out[j] = x;
-            }
-          }
-        } else {     // fused top-k': keep only values that can still enter the query's best k'
-          const float th = P.theta[gq];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gd = n0 + c * 32 + j;
-            const float2 ab = __ldg(P.ab + min(gd, P.N - 1));
-            const float x = fmaf(ab.x, __uint_as_float(v[j]), ab.y);
-            if (gd < P.N && x >= th) {
-              const int ord = P.n_base + gd;
-              bool ok = true;
-              if (P.filter) ok = P.filter[P.vec_docs ? P.vec_docs[ord] : ord] != 0;
-              if (ok) {
-                const int pos = atomicAdd(P.cc_cnt + gq, 1);
-                if (pos < P.cc_cap) P.cc[(size_t)gq * P.cc_cap + pos] = make_key(x, ord);
-              }
-            }
-          }
-        }
-      }
+      epilogue_slice(P, v, gq, n0, c);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -194,6 +199,121 @@ knn_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- persistent variant: one CTA per SM loops over output tiles; the TMA ring keeps streaming across tiles and the
+// accumulator is double buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
+constexpr int kPStages = 4;
+constexpr uint32_t kPTmemCols = 512;
+constexpr size_t kPGemmSmem = (size_t)kPStages * kStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+knn_gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
+  extern __shared__ uint8_t gemm_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)gemm_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)kPStages * kABytes;
+  uint64_t* full_bar = (uint64_t*)(base + (size_t)kPStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kPStages;
+  uint64_t* tmem_full = empty_bar + kPStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (P.M + BM - 1) / BM, n_tiles = (P.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int num_kb = (P.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kPStages; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "r"(kPTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer: one continuous stream of k-blocks over all tiles of this CTA
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * BM, n0 = (t / m_tiles) * BN;   // query tiles vary fastest (corpus tile shared via L2)
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          bar_wait(&empty_bar[s], ((it / kPStages) & 1) ^ 1);
+          bar_expect_tx(&full_bar[s], kStageBytes);
+          tma_load_2d(smA + (size_t)s * kABytes, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(smB + (size_t)s * kBBytes, &tmB, &full_bar[s], kb * BK, P.n_base + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        bar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          bar_wait(&full_bar[s], (it / kPStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smA + (size_t)s * kABytes), db = make_smem_desc(smB + (size_t)s * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / kUmmaK; ++k)
+            umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue warps
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const int m0 = (t % m_tiles) * BM, n0 = (t / m_tiles) * BN;
+      const int gq = m0 + row;
+      bar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == BN / 32 - 1) {   // every column of this accumulator is in registers: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tmem_empty[acc])) : "memory");
+        }
+        epilogue_slice(P, v, gq, n0, c);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kPTmemCols) : "memory");
   }
 }
 

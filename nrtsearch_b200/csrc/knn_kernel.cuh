@@ -307,8 +307,16 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
-      dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
-      tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
+      static const bool simple_gemm = getenv("NRTGPU_KNN_GEMM_SIMPLE") != nullptr;
+      const int tiles = ((nq + tc::BM - 1) / tc::BM) * ((nc + tc::BN - 1) / tc::BN);
+      if (simple_gemm) {
+        dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
+        tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
+      } else {
+        static int sm_count = 0;
+        if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+        tc::knn_gemm_bf16_persistent_kernel<<<tiles < sm_count ? tiles : sm_count, tc::kGemmThreads, tc::kPGemmSmem, st>>>(tmQ, *tm_corpus, G);
+      }
     } else {
       dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
       knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim, dS, chunk);

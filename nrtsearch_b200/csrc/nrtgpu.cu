@@ -224,6 +224,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kPGemmSmem));
   *out = c;
   return NRTGPU_OK;
 }
