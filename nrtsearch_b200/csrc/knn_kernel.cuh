@@ -307,7 +307,9 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
-      static const bool simple_gemm = getenv("NRTGPU_KNN_GEMM_SIMPLE") != nullptr;
+      // default: one tile per CTA, 2 CTAs/SM (measured 4.9 ms at C4); the persistent double-buffered variant measured
+      // 7.5 ms -- both are bound by L2 -> SM operand traffic (48 KB per 128x256x64 k-block), see DESIGN.md 4.3
+      static const bool simple_gemm = getenv("NRTGPU_KNN_GEMM_PERSISTENT") == nullptr;
       const int tiles = ((nq + tc::BM - 1) / tc::BM) * ((nc + tc::BN - 1) / tc::BN);
       if (simple_gemm) {
         dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
