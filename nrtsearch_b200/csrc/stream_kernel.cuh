@@ -484,7 +484,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       const int32_t* rd = sm.pool_docs + rbase[t];
       const uint8_t* rf = sm.pool_f8 + rbase[t];
       unsigned char* sb = slot_bytes + t - 4 * wbase;
-      for (int32_t i = tid; i < cnt[t]; i += kThreads) {
+#pragma unroll 1
+      for (int32_t i = tid; i < cnt[t]; i += kThreads) {   // short trip counts (a few postings per thread): no unrolling
         const int idx = (r_cur[t] + i) & rmask[t];
         sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1;
       }
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
               uint32_t* sl = sm.slots - wbase;
               int32_t i = it[t];
               if (simple) {
+#pragma unroll 1
                 for (; i < cnt[t]; i += kThreads) {
                   const int32_t doc = rd[(r_cur[t] + i) & rmask[t]];
                   const uint32_t v = sl[doc];
