@@ -82,7 +82,8 @@ struct alignas(128) StreamSmem {
   float tbl[kT][kTfTab + 1][256];        // 20 KB
   float ubt[kUbt];                       //  5 KB
   uint64_t full_bar[kPool];
-  uint32_t gb[kT][kSliceDocs / kGran + 1];   // 8 KB granule bounds of this slice
+  uint4 gb4[kSliceDocs / kGran + 1];      // 8 KB granule bounds of this slice, one 16-byte row {slot 0..3} per granule
+  uint16_t nextg[kSliceDocs / kGran + 2]; // 1 KB window table: the window that starts at granule g ends at nextg[g]
   DevClause cl[kMaxClauses];
   DevQuery q;
   // per-slot stream descriptors (static after set-up; s_issued is owned by thread 0)
@@ -308,12 +309,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
       v = p[min(g, g_count)];
     }
-    sm.gb[t][g] = v;
+    reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = v;
   }
   __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
-    const int64_t g0 = sm.cl[tid].post_base + sm.gb[s][0], g1 = sm.cl[tid].post_base + sm.gb[s][g_count];
+    const int64_t g0 = sm.cl[tid].post_base + reinterpret_cast<const uint32_t*>(&sm.gb4[0])[s],
+                  g1 = sm.cl[tid].post_base + reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[s];
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
@@ -351,31 +353,48 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   __syncthreads();
 
   // ---- CTA-uniform per-slot registers
-  int32_t r_cur[kT], rbase[kT], rmask[kT], rlog[kT];
+  int32_t r_cur[kT], rbase[kT], rmask[kT], issued[kT], waited[kT];
 #pragma unroll
   for (int t = 0; t < kT; ++t) {
     r_cur[t] = sm.s_r_begin[t];
     rbase[t] = sm.s_ring_base[t] << kLogCH;
     rmask[t] = (sm.s_ring_nch[t] << kLogCH) - 1;
-    rlog[t] = 31 - __clz(sm.s_ring_nch[t]);
+    issued[t] = 0;   // chunks handed to the TMA so far (CTA-uniform, every thread tracks it)
+    waited[t] = 0;   // chunks whose arrival this warp has already observed
   }
-  auto issue_chunks = [&]() {  // thread 0 only: fill every free ring slot
+  // the window table: from granule g the window runs to nextg[g] = the farthest granule (<= g + kWinGran) whose
+  // postings fit every ring with one chunk of alignment slack. One granule always fits (<= kGran postings).
+  for (int g = tid; g < g_count; g += kThreads) {
+    int g1 = min(g_count, g + kWinGran);
+    const uint4 a = sm.gb4[g];
+    for (;;) {
+      const uint4 b = sm.gb4[g1];
+      const bool fits = (int32_t)(b.x - a.x) <= rmask[0] + 1 - kCH && (int32_t)(b.y - a.y) <= rmask[1] + 1 - kCH &&
+                        (int32_t)(b.z - a.z) <= rmask[2] + 1 - kCH && (int32_t)(b.w - a.w) <= rmask[3] + 1 - kCH;
+      if (fits || g1 == g + 1) break;
+      --g1;
+    }
+    sm.nextg[g] = (uint16_t)g1;
+  }
+  // warp 0 fills every free ring slot, one chunk per lane (each chunk: expect_tx + two bulk copies on its mbarrier)
+  auto issue_chunks = [&]() {
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
-      const int nch = sm.s_ring_nch[t];
-      const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + nch);
-      int j = sm.s_issued[t];
-      for (; j < lim; ++j) {
-        const int slot = sm.s_ring_base[t] + (j & (nch - 1));
-        uint64_t* bar = &sm.full_bar[slot];
-        mbar_arrive_expect_tx(bar, kChunkBytes);
-        bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
-        bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
+      const int nchm = rmask[t] >> kLogCH;
+      const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + nchm + 1);
+      if (tid < 32) {
+        for (int j = issued[t] + lane; j < lim; j += 32) {
+          const int slot = (rbase[t] >> kLogCH) + (j & nchm);
+          uint64_t* bar = &sm.full_bar[slot];
+          mbar_arrive_expect_tx(bar, kChunkBytes);
+          bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
+          bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
+        }
       }
-      sm.s_issued[t] = j;
+      issued[t] = max(issued[t], lim);
     }
   };
-  if (tid == 0) issue_chunks();
+  issue_chunks();
 
   // ---- exact BM25 table tbl[slot][tf][norm byte] (row tf = 0 is +0.0f)
   for (int i = tid; i < kT * (kTfTab + 1) * 256; i += kThreads) {
@@ -425,13 +444,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
   for (int t = 0; t < kT; ++t) scoring_bits |= (sm.s_scoring[t] ? 1u : 0u) << t;
   // word bytes of the driver slots below each slot (ownership test)
-  uint32_t below[kT];
-#pragma unroll
-  for (int t = 0; t < kT; ++t) {
-    below[t] = 0;
-#pragma unroll
-    for (int j = 0; j < kT; ++j) if (j < t && ((driver_mask >> j) & 1u)) below[t] |= 0xffu << (8 * j);
-  }
+  const uint32_t drv_bytes = ((driver_mask & 1u) ? 0xffu : 0u) | ((driver_mask & 2u) ? 0xff00u : 0u) |
+                             ((driver_mask & 4u) ? 0xff0000u : 0u) | ((driver_mask & 8u) ? 0xff000000u : 0u);
   unsigned int my_hits = 0;
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
@@ -439,17 +453,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (n_term > 0 && ne_mask == ((1u << n_term) - 1u)) g0 = g_count;   // every list is non-essential: skip the slice
   while (g0 < g_count) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
-    int g1 = min(g_count, g0 + kWinGran);
+    const int g1 = sm.nextg[g0];
     int32_t cnt[kT];
-    for (;;) {
-      bool fits = true;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        cnt[t] = (int32_t)(sm.gb[t][g1] - sm.gb[t][g0]);
-        fits = fits && cnt[t] <= rmask[t] + 1 - kCH;
-      }
-      if (fits || g1 == g0 + 1) break;   // one granule always fits (<= 2048 postings, ring >= kMinNCH chunks)
-      --g1;
+    {
+      const uint4 a = sm.gb4[g0], b = sm.gb4[g1];
+      cnt[0] = (int32_t)(b.x - a.x); cnt[1] = (int32_t)(b.y - a.y); cnt[2] = (int32_t)(b.z - a.z); cnt[3] = (int32_t)(b.w - a.w);
     }
     const int32_t wbase = slice_base + (g0 << kLogGran);
     const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
@@ -461,20 +469,38 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       if (!dense && ess == 0) {   // no posting of an essential list in these granules: just advance the streams
 #pragma unroll
         for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
-        if (tid == 0) issue_chunks();
+        issue_chunks();
         continue;
       }
     }
 
     // ---------------- residency: every warp waits for the chunks that hold [r_cur, r_cur + cnt)
+    // (each chunk is awaited once per warp: `waited` remembers how far this warp has looked; lanes take one chunk each)
+    {
+      int need[kT], total = 0;
 #pragma unroll
-    for (int t = 0; t < kT; ++t) {
-      if (t < n_term && cnt[t] > 0) {
-        const int j = (r_cur[t] >> kLogCH) + lane, jl = (r_cur[t] + cnt[t] - 1) >> kLogCH;   // <= 32 chunks
-        if (j <= jl) mbar_wait(&sm.full_bar[(rbase[t] >> kLogCH) + (j & (rmask[t] >> kLogCH))], (j >> rlog[t]) & 1);
+      for (int t = 0; t < kT; ++t) {
+        const int jl1 = (cnt[t] > 0) ? ((r_cur[t] + cnt[t] - 1) >> kLogCH) + 1 : 0;   // one past the last chunk needed
+        waited[t] = max(waited[t], r_cur[t] >> kLogCH);   // chunks of skipped windows are never looked at
+        need[t] = max(jl1 - waited[t], 0);
+        total += need[t];
+      }
+      if (total > 0) {
+        for (int l = lane; l < total; l += 32) {
+          int t = 0, k = l;
+          if (k >= need[0]) { k -= need[0]; t = 1;
+            if (k >= need[1]) { k -= need[1]; t = 2;
+              if (k >= need[2]) { k -= need[2]; t = 3; } } }
+          const int w0 = t == 0 ? waited[0] : t == 1 ? waited[1] : t == 2 ? waited[2] : waited[3];
+          const int nch = sm.s_ring_nch[t];
+          const int j = w0 + k;
+          mbar_wait(&sm.full_bar[sm.s_ring_base[t] + (j & (nch - 1))], (j >> (31 - __clz(nch))) & 1);
+        }
+#pragma unroll
+        for (int t = 0; t < kT; ++t) waited[t] += need[t];
+        __syncwarp();
       }
     }
-    __syncwarp();
 
     // ---------------- pass 1: scatter tf bytes
 #pragma unroll
@@ -516,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
             for (int t = 0; t < kT; ++t) {
               if (t >= n_term || pending) break;
               if (!((driver_mask >> t) & 1u)) continue;
-              const uint32_t own = 0xffu << (8 * t), bel = below[t];
+              const uint32_t own = 0xffu << (8 * t), bel = drv_bytes & ((1u << (8 * t)) - 1u);
               const int32_t* rd = sm.pool_docs + rbase[t];
               uint32_t* sl = sm.slots - wbase;
               int32_t i = it[t];
@@ -582,20 +608,30 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       }
     }
     // ---------------- pass 3: clear the words pass 2 did not visit
+    // (by posting when the non-driver lists are sparse here, else one 128-bit sweep over the window's words)
     if (!dense && has_non_driver) {
+      int32_t nd = 0;
 #pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        if (t >= n_term) break;
-        if ((driver_mask >> t) & 1u) continue;
-        for (int32_t i = tid; i < cnt[t]; i += kThreads)
-          sm.slots[sm.pool_docs[rbase[t] + ((r_cur[t] + i) & rmask[t])] - wbase] = 0u;
+      for (int t = 0; t < kT; ++t) if (!((driver_mask >> t) & 1u)) nd += cnt[t];
+      if (nd > 2 * kThreads) {
+        uint4* s4 = reinterpret_cast<uint4*>(sm.slots);
+        const int n4 = (wend - wbase + 3) >> 2;
+        for (int i = tid; i < n4; i += kThreads) s4[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else if (nd > 0) {
+#pragma unroll
+        for (int t = 0; t < kT; ++t) {
+          if (t >= n_term) break;
+          if ((driver_mask >> t) & 1u) continue;
+          for (int32_t i = tid; i < cnt[t]; i += kThreads)
+            sm.slots[sm.pool_docs[rbase[t] + ((r_cur[t] + i) & rmask[t])] - wbase] = 0u;
+        }
       }
-      __syncthreads();
+      if (nd > 0) __syncthreads();
     }
     // ---------------- advance the streams, refill freed ring slots
 #pragma unroll
     for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
-    if (tid == 0) issue_chunks();
+    issue_chunks();
   }
 
   // ---------------- finish the work item: the slice merge sorts, so only a full buffer needs ordering here
