@@ -94,6 +94,7 @@ struct alignas(128) StreamSmem {
   int32_t s_ring_base[kT], s_ring_nch[kT];   // first pool chunk and ring length (chunks, power of two) per slot
   uint32_t s_scoring[kT];
   int cand_count;
+  int n_keys;                       // entries [0, n_keys) of cand are keys kept by the last flush
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
   unsigned long long theta;
 };
@@ -218,17 +219,39 @@ __device__ __forceinline__ float score_disjunction(const StreamLaunch& L, const 
   return (float)sum;
 }
 
-__device__ __forceinline__ void compact_candidates_v2(StreamSmem& sm, int top_k, uint64_t* g_theta) {
+// Candidate buffer flush. Entries [0, n_keys) are keys kept by the previous flush; the entries appended since are
+// keys (generic queries, scored in pass 2) or, for pure disjunctions (`raw`), unscored (tf word << 32 | doc) pairs:
+// pass 2 only tests the tf-pattern bound, the exact scores are computed here, one entry per thread, so the norm
+// loads of a whole buffer overlap instead of stalling one warp at a time inside pass 2. Then sort, keep the best
+// top_k, publish the k-th key as the query's threshold.
+__device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, StreamSmem& sm, const uint8_t* norms0, bool raw,
+                                                      bool has_after, uint64_t after_key, int top_k, uint64_t* g_theta) {
   __syncthreads();
   int n = sm.cand_count;
   if (n > kCand) n = kCand;
+  if (raw) {
+    const unsigned long long theta = sm.theta;
+    for (int i = sm.n_keys + threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t e = sm.cand[i];
+      const int32_t doc = (int32_t)(uint32_t)e;
+      uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, (uint32_t)(e >> 32)), doc);
+      if (!(key > theta) || (has_after && !(key < after_key))) key = 0ull;   // a real key is never 0 (low word = ~doc)
+      sm.cand[i] = key;
+    }
+  }
   int m = next_pow2(n < 2 ? 2 : n);
   for (int i = n + threadIdx.x; i < m; i += blockDim.x) sm.cand[i] = 0ull;
   __syncthreads();
   block_bitonic_sort_desc(sm.cand, m);
   if (threadIdx.x == 0) {
     int keep = n < top_k ? n : top_k;
+    if (raw && keep > 0 && sm.cand[keep - 1] == 0ull) {   // rejected entries sorted last: keep = first zero
+      int lo = 0, hi = keep - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.cand[mid] == 0ull) hi = mid; else lo = mid + 1; }
+      keep = lo;
+    }
     sm.cand_count = keep;
+    sm.n_keys = keep;
     if (keep == top_k) {
       unsigned long long kth = sm.cand[top_k - 1];
       unsigned long long old = atomicMax((unsigned long long*)g_theta, kth);
@@ -255,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (tid == 0) {
     sm.q = L.queries[qi];
     sm.cand_count = 0;
+    sm.n_keys = 0;
     sm.theta = *(volatile unsigned long long*)&L.theta[qi];
     for (int j = 0; j < kPool; ++j) mbar_init(&sm.full_bar[j], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     r_cur[t] = sm.s_r_begin[t];
     rbase[t] = sm.s_ring_base[t] << kLogCH;
     rmask[t] = (sm.s_ring_nch[t] << kLogCH) - 1;
-    issued[t] = 0;   // chunks handed to the TMA so far (CTA-uniform, every thread tracks it)
+    issued[t] = 0;   // chunks handed to the TMA so far (tracked by warp 0, the issuing warp)
     waited[t] = 0;   // chunks whose arrival this warp has already observed
   }
   // the window table: from granule g the window runs to nextg[g] = the farthest granule (<= g + kWinGran) whose
@@ -378,18 +402,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   }
   // warp 0 fills every free ring slot, one chunk per lane (each chunk: expect_tx + two bulk copies on its mbarrier)
   auto issue_chunks = [&]() {
+    if (tid >= 32) return;
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       const int nchm = rmask[t] >> kLogCH;
       const int lim = min(sm.s_n_chunks[t], (r_cur[t] >> kLogCH) + nchm + 1);
-      if (tid < 32) {
-        for (int j = issued[t] + lane; j < lim; j += 32) {
-          const int slot = (rbase[t] >> kLogCH) + (j & nchm);
-          uint64_t* bar = &sm.full_bar[slot];
-          mbar_arrive_expect_tx(bar, kChunkBytes);
-          bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
-          bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
-        }
+      for (int j = issued[t] + lane; j < lim; j += 32) {
+        const int slot = (rbase[t] >> kLogCH) + (j & nchm);
+        uint64_t* bar = &sm.full_bar[slot];
+        mbar_arrive_expect_tx(bar, kChunkBytes);
+        bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
+        bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
       }
       issued[t] = max(issued[t], lim);
     }
@@ -531,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         const float theta_s = theta ? key_score(theta) : -INFINITY;
         if (pending) {
           pending = false;
-          if (pkey > theta) {
+          if (simple || pkey > theta) {
             const int p = atomicAdd(&sm.cand_count, 1);
             if (p < kCand) sm.cand[p] = pkey; else pending = true;
           }
@@ -554,15 +577,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
                   if ((v & bel) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
                   sl[doc] = 0u;
                   ++my_hits;
-                  const uint32_t ui = min(v & 0xffu, 5u) + 6u * min((v >> 8) & 0xffu, 5u) + 36u * min((v >> 16) & 0xffu, 5u) +
-                                      216u * min(v >> 24, 5u);
+                  const uint32_t ui = __dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u);   // sum min(tf_s, 5) * 6^s
                   if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                  const uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, v), doc);
-                  if (key > theta && (!has_after || key < after_key)) {
-                    const int p = atomicAdd(&sm.cand_count, 1);
-                    if (p < kCand) sm.cand[p] = key;
-                    else { pending = true; pkey = key; i += kThreads; break; }
-                  }
+                  const uint64_t raw = ((uint64_t)v << 32) | (uint32_t)doc;   // scored at the next flush
+                  const int p = atomicAdd(&sm.cand_count, 1);
+                  if (p < kCand) sm.cand[p] = raw;
+                  else { pending = true; pkey = raw; i += kThreads; break; }
                 }
               } else {
                 for (; i < cnt[t]; i += kThreads) {
@@ -604,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         }
         __syncthreads();
         if (sm.cand_count <= kCand) break;                 // nobody is parked
-        compact_candidates_v2(sm, L.top_k, &L.theta[qi]);  // raises theta, frees the buffer
+        compact_candidates_v2(L, sm, norms0, simple, has_after, after_key, L.top_k, &L.theta[qi]);  // raises theta, frees the buffer
       }
     }
     // ---------------- pass 3: clear the words pass 2 did not visit
@@ -636,7 +656,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 
   // ---------------- finish the work item: the slice merge sorts, so only a full buffer needs ordering here
   __syncthreads();
-  if (sm.cand_count > L.top_k) compact_candidates_v2(sm, L.top_k, &L.theta[qi]);
+  if (simple ? sm.cand_count > sm.n_keys : sm.cand_count > L.top_k)
+    compact_candidates_v2(L, sm, norms0, simple, has_after, after_key, L.top_k, &L.theta[qi]);
   const int keep = min(sm.cand_count, L.top_k);
   uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
   for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
