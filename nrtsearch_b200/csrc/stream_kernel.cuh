@@ -51,6 +51,7 @@ constexpr int kMaxTopKStream = kCand / 2;   // larger top_k goes through bool_wi
 #endif
 constexpr int kThreads = NRT_STREAM_THREADS;   // one CTA per SM
 constexpr int kGran = 1 << kLogGran;
+static_assert((kThreads & (kThreads - 1)) == 0, "the round-robin posting deal masks with kThreads - 1");
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
@@ -230,14 +231,31 @@ __device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, Str
   int n = sm.cand_count;
   if (n > kCand) n = kCand;
   if (raw) {
+    // score, then re-append only the entries that beat theta: the sort below usually sees a few hundred keys
     const unsigned long long theta = sm.theta;
-    for (int i = sm.n_keys + threadIdx.x; i < n; i += blockDim.x) {
-      const uint64_t e = sm.cand[i];
-      const int32_t doc = (int32_t)(uint32_t)e;
-      uint64_t key = make_key(score_disjunction(L, sm, norms0, doc, (uint32_t)(e >> 32)), doc);
-      if (!(key > theta) || (has_after && !(key < after_key))) key = 0ull;   // a real key is never 0 (low word = ~doc)
-      sm.cand[i] = key;
+    const int n_keys = sm.n_keys;
+    constexpr int kPer = (kCand + kThreads - 1) / kThreads;
+    uint64_t mine[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = n_keys + (int)threadIdx.x + j * kThreads;
+      uint64_t key = 0ull;
+      if (i < n) {
+        const uint64_t e = sm.cand[i];
+        const int32_t doc = (int32_t)(uint32_t)e;
+        key = make_key(score_disjunction(L, sm, norms0, doc, (uint32_t)(e >> 32)), doc);
+        if (!(key > theta) || (has_after && !(key < after_key))) key = 0ull;   // a real key is never 0 (low word = ~doc)
+      }
+      mine[j] = key;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.cand_count = n_keys;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+      if (mine[j]) sm.cand[atomicAdd(&sm.cand_count, 1)] = mine[j];
+    __syncthreads();
+    n = sm.cand_count;
   }
   int m = next_pow2(n < 2 ? 2 : n);
   for (int i = n + threadIdx.x; i < m; i += blockDim.x) sm.cand[i] = 0ull;
@@ -245,11 +263,6 @@ __device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, Str
   block_bitonic_sort_desc(sm.cand, m);
   if (threadIdx.x == 0) {
     int keep = n < top_k ? n : top_k;
-    if (raw && keep > 0 && sm.cand[keep - 1] == 0ull) {   // rejected entries sorted last: keep = first zero
-      int lo = 0, hi = keep - 1;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.cand[mid] == 0ull) hi = mid; else lo = mid + 1; }
-      keep = lo;
-    }
     sm.cand_count = keep;
     sm.n_keys = keep;
     if (keep == top_k) {
@@ -525,6 +538,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       }
     }
 
+    // the window's postings are dealt round-robin over the threads ACROSS the clauses (clause t starts where
+    // clause t-1 stopped), so short lists do not pile onto the first warps
+    int32_t rot[kT];
+    rot[0] = 0;
+#pragma unroll
+    for (int t = 1; t < kT; ++t) rot[t] = (rot[t - 1] + cnt[t - 1]) & (kThreads - 1);
     // ---------------- pass 1: scatter tf bytes
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
@@ -534,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       const uint8_t* rf = sm.pool_f8 + rbase[t];
       unsigned char* sb = slot_bytes + t - 4 * wbase;
 #pragma unroll 1
-      for (int32_t i = tid; i < cnt[t]; i += kThreads) {   // short trip counts (a few postings per thread): no unrolling
+      for (int32_t i = (tid - rot[t]) & (kThreads - 1); i < cnt[t]; i += kThreads) {   // a few postings per thread
         const int idx = (r_cur[t] + i) & rmask[t];
         sb[4 * rd[idx]] = scoring ? rf[idx] : (unsigned char)1;
       }
@@ -545,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     {
       int32_t it[kT];
 #pragma unroll
-      for (int t = 0; t < kT; ++t) it[t] = tid;
+      for (int t = 0; t < kT; ++t) it[t] = (tid - rot[t]) & (kThreads - 1);
       int32_t idense = tid;
       bool pending = false;
       uint64_t pkey = 0;
