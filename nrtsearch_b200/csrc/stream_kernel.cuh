@@ -22,7 +22,7 @@ namespace v2 {
 
 constexpr int kT = 4;
 #ifndef NRT_STREAM_CTAS
-#define NRT_STREAM_CTAS 1
+#define NRT_STREAM_CTAS 2   // two independent CTAs per SM: one CTA's barrier waits are filled by the other's warps
 #endif
 constexpr int kCtasPerSm = NRT_STREAM_CTAS;
 constexpr int kLogCH = 9;
@@ -47,7 +47,7 @@ constexpr int kTfTab = 2;
 #endif
 constexpr int kMaxTopKStream = kCand / 2;   // larger top_k goes through bool_window_kernel
 #ifndef NRT_STREAM_THREADS
-#define NRT_STREAM_THREADS 512
+#define NRT_STREAM_THREADS (NRT_STREAM_CTAS == 1 ? 512 : 256)   // 64K registers per SM / 128 per thread
 #endif
 constexpr int kThreads = NRT_STREAM_THREADS;   // one CTA per SM
 constexpr int kGran = 1 << kLogGran;
@@ -498,18 +498,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     const int32_t wbase = slice_base + (g0 << kLogGran);
     const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
     g0 = g1;
-    {
-      int32_t ess = 0;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) if (!((ne_mask >> t) & 1u)) ess |= cnt[t];
-      if (!dense && ess == 0) {   // no posting of an essential list in these granules: just advance the streams
-#pragma unroll
-        for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
-        issue_chunks();
-        continue;
-      }
-    }
-
     // ---------------- residency: every warp waits for the chunks that hold [r_cur, r_cur + cnt)
     // (each chunk is awaited once per warp: `waited` remembers how far this warp has looked; lanes take one chunk each)
     {
@@ -517,7 +505,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
         const int jl1 = (cnt[t] > 0) ? ((r_cur[t] + cnt[t] - 1) >> kLogCH) + 1 : 0;   // one past the last chunk needed
-        waited[t] = max(waited[t], r_cur[t] >> kLogCH);   // chunks of skipped windows are never looked at
         need[t] = max(jl1 - waited[t], 0);
         total += need[t];
       }
@@ -535,6 +522,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
         for (int t = 0; t < kT; ++t) waited[t] += need[t];
         __syncwarp();
+      }
+    }
+
+    {
+      int32_t ess = 0;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) if (!((ne_mask >> t) & 1u)) ess |= cnt[t];
+      if (!dense && ess == 0) {   // no posting of an essential list in these granules: just advance the streams
+#pragma unroll
+        for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
+        __syncthreads();   // every warp has seen these chunks land (mbarrier phases only tell odd from even: a ring
+        issue_chunks();    // slot is re-armed only after ALL warps observed its previous phase)
+        continue;
       }
     }
 
