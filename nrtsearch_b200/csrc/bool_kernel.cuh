@@ -43,7 +43,7 @@ struct DevClause {
   float weight;       // boost*idf (term) or constant score = boost (range / match-all)
   int32_t scoring;    // 1 if the clause contributes to the score (MUST / SHOULD)
   float ub;           // term clauses: largest score of any posting of the list (index-time max of tf*cache[norm])
-  int32_t pad_;
+  int32_t plane;      // term clauses: dense tf plane of the term (DevIndexView::dense_tf), -1 if the term has none
   int64_t lo, hi;
 };
 
@@ -82,6 +82,8 @@ struct DevIndexView {
   const int32_t* const* col32;   // [n_columns] (NULL if stored as int64)
   const uint8_t* const* col_has; // [n_columns] (NULL = all)
   const uint32_t* live_bits;     // bitmap or NULL
+  const uint8_t* dense_tf;       // [n_planes][dense_stride] min(freq, 255) per doc for the densest terms (0 = absent)
+  int64_t dense_stride;
 };
 
 struct BoolLaunch {

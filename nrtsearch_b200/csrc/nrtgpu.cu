@@ -50,6 +50,13 @@ __global__ void term_max_x_kernel(const int64_t* __restrict__ term_off, int n_te
   atomicMax(out_bits + t, __float_as_uint(x));   // x > 0: float order == unsigned order
 }
 
+// dense tf plane of one term: plane[doc] = min(freq, 255) for every posting of the term (the plane is zeroed first)
+__global__ void plane_fill_kernel(const int32_t* __restrict__ docs, const uint8_t* __restrict__ f8, int64_t n,
+                                  uint8_t* __restrict__ plane) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) plane[docs[i]] = f8[i];
+}
+
 namespace {
 
 // ---- SmallFloat.byte4ToInt (Lucene) : norm byte -> field length, for the BM25 length table ----
@@ -114,6 +121,7 @@ struct nrtgpu_index {
   std::vector<int32_t> term_field;
   std::vector<int64_t> term_df;
   std::vector<float> term_max_x;
+  std::vector<int32_t> term_plane;   // dense tf plane per term, -1 for all but the densest terms
   std::vector<int64_t> field_doc_count, field_sum_ttf;
   std::vector<uint8_t> field_has_norms;
   // device image
@@ -124,6 +132,9 @@ struct nrtgpu_index {
   std::vector<std::unique_ptr<DevBuf<uint8_t>>> norms;
   DevBuf<const uint8_t*> norms_ptrs;
   DevBuf<float> caches;
+  DevBuf<uint8_t> dense_tf;         // [n_planes][dense_stride]: direct-address tf bytes of the densest terms
+  int64_t dense_stride = 0;
+  int32_t n_planes = 0;
   DevBuf<uint8_t> field_min_norm;   // smallest non-zero norm byte per field (0 byte = doc lacks the field)
   std::vector<std::unique_ptr<DevBuf<int64_t>>> col64;
   std::vector<std::unique_ptr<DevBuf<int32_t>>> col32;
@@ -155,6 +166,7 @@ struct nrtgpu_index {
     v.norms = norms_ptrs.p; v.caches = caches.p;
     v.col64 = col64_ptrs.p; v.col32 = col32_ptrs.p; v.col_has = col_has_ptrs.p;
     v.live_bits = live_bits.p;
+    v.dense_tf = dense_tf.p; v.dense_stride = dense_stride;
     return v;
   }
 };
@@ -274,6 +286,35 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if ((rc = ix->exc_pos.upload(epos.data(), epos.size()))) return rc;
     if ((rc = ix->exc_freq.upload(efreq.data(), efreq.size()))) return rc;
   }
+  // dense tf planes: a term present in >= 1/16 of the docs also gets a direct-address byte per doc (like the bit-set
+  // blocks Lucene's postings format keeps for dense blocks). A list that only needs LOOKUPS in a window (a
+  // non-essential MAXSCORE list) is then one TMA copy of the window's bytes instead of a scatter of its postings.
+  ix->term_plane.assign((size_t)d->n_terms, -1);
+  if (d->n_docs >= 4096) {
+    std::vector<int32_t> dense_terms;
+    for (int32_t t = 0; t < d->n_terms; ++t)
+      if ((d->term_off[t + 1] - d->term_off[t]) * 16 >= (int64_t)d->n_docs) dense_terms.push_back(t);
+    const int64_t stride = (((int64_t)d->n_docs + 15) / 16) * 16 + 16;
+    const size_t max_planes = std::min<size_t>(1024, (size_t)((8ll << 30) / stride));
+    if (dense_terms.size() > max_planes) {   // keep the densest
+      std::sort(dense_terms.begin(), dense_terms.end(), [&](int32_t a, int32_t b) {
+        return d->term_off[a + 1] - d->term_off[a] > d->term_off[b + 1] - d->term_off[b]; });
+      dense_terms.resize(max_planes);
+    }
+    if (!dense_terms.empty()) {
+      ix->dense_stride = stride; ix->n_planes = (int32_t)dense_terms.size();
+      if ((rc = ix->dense_tf.alloc((size_t)stride * dense_terms.size()))) return rc;
+      NRT_CUDA_TRY(cudaMemset(ix->dense_tf.p, 0, ix->dense_tf.bytes()));
+      for (size_t k = 0; k < dense_terms.size(); ++k) {
+        const int32_t t = dense_terms[k];
+        const int64_t off = d->term_off[t], n = d->term_off[t + 1] - off;
+        ix->term_plane[(size_t)t] = (int32_t)k;
+        plane_fill_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ix->post_docs.p + off, ix->post_f8.p + off, n,
+                                                                 ix->dense_tf.p + (size_t)k * stride);
+      }
+      NRT_CUDA_TRY(cudaGetLastError());
+    }
+  }
   // norms + BM25 caches
   {
     std::vector<const uint8_t*> ptrs((size_t)d->n_fields, nullptr);
@@ -368,7 +409,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       ix->vec_tc = true;
     }
   }
-  ix->device_bytes = (int64_t)(ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
+  ix->device_bytes = (int64_t)(ix->dense_tf.bytes() + ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
                                ix->caches.bytes() + ix->live_bits.bytes() + ix->vectors.bytes() + ix->vec_norm2.bytes() +
                                ix->vec_docs.bytes() + ix->vec_bf16.bytes());
   for (auto& b : ix->norms) ix->device_bytes += (int64_t)b->bytes();
@@ -433,7 +474,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
       if (c.occur < NRTGPU_SHOULD || c.occur > NRTGPU_MUST_NOT) NRT_FAIL(NRTGPU_ERR_INVALID, "bad occur");
       if (c.boost < 0.0f) NRT_FAIL(NRTGPU_ERR_INVALID, "Boost must be a positive number");  // QueryNodeMapper.java:127
       DevClause x; std::memset(&x, 0, sizeof(x));
-      x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.lo = c.lo; x.hi = c.hi;
+      x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.plane = -1; x.lo = c.lo; x.hi = c.hi;
       x.scoring = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_SHOULD) ? 1 : 0;
       bool required = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER);
       if (c.kind == NRTGPU_TERM) {
@@ -442,7 +483,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
         int f = ix->term_field[c.id];
         x.post_base = ix->term_off[c.id];
         x.n_post = (int32_t)(ix->term_off[c.id + 1] - ix->term_off[c.id]);
-        x.slot = n_term; x.field = f;
+        x.slot = n_term; x.field = f; x.plane = ix->term_plane[c.id];
         int64_t df = ix->term_df[c.id];
         // BM25Scorer: weight = boost * idf
         x.weight = c.boost * bm25_idf(df > 0 ? df : 1, ix->field_doc_count[f]);

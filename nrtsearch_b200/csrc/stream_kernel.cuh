@@ -55,6 +55,7 @@ static_assert((kThreads & (kThreads - 1)) == 0, "the round-robin posting deal ma
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
+constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
   DevIndexView ix;
@@ -97,6 +98,8 @@ struct alignas(128) StreamSmem {
   int cand_count;
   int n_keys;                       // entries [0, n_keys) of cand are keys kept by the last flush
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
+  int plane_slot;                   // non-essential slot served from its dense tf plane (-1: none)
+  uint64_t plane_bar[2];
   unsigned long long theta;
 };
 static_assert(sizeof(StreamSmem) <= (kCtasPerSm == 1 ? 232448 : 115712), "StreamSmem exceeds the shared memory budget of sm_100");
@@ -294,6 +297,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     sm.n_keys = 0;
     sm.theta = *(volatile unsigned long long*)&L.theta[qi];
     for (int j = 0; j < kPool; ++j) mbar_init(&sm.full_bar[j], 1);
+    mbar_init(&sm.plane_bar[0], 1);
+    mbar_init(&sm.plane_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -333,16 +338,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     }
     sm.ne_mask = ne;
     if (ne) L.pruned[qi] = 1;
+    // the densest non-essential list that has a dense tf plane is not streamed as postings at all: each window's
+    // bytes of the plane are copied in by the TMA and the owners of pass 2 look their doc up (two ring-less lists
+    // would not leave enough pool for the plane buffers, so queries of up to three terms only)
+    int ps = -1;
+    if (ne && q.n_term <= 3 && L.ix.dense_tf != nullptr) {
+      float best = INFINITY;
+      for (int i = 0; i < q.n_clauses; ++i) {
+        const DevClause& c = sm.cl[i];
+        if (c.kind == NRTGPU_TERM && ((ne >> c.slot) & 1u) && c.plane >= 0 && c.ub < best) { best = c.ub; ps = c.slot; }
+      }
+    }
+    sm.plane_slot = ps;
   }
   __syncthreads();
   const uint32_t ne_mask = sm.ne_mask;
+  const int pslot = sm.plane_slot;
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
   for (int i = tid; i < kT * (gran_per_slice + 1); i += kThreads) {
     const int t = i / (gran_per_slice + 1), g = i % (gran_per_slice + 1);
     uint32_t v = 0;
-    if (t < n_term) {
+    if (t < n_term && t != pslot) {   // the plane-served list has no postings in the rings: empty column
       const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
       v = p[min(g, g_count)];
     }
@@ -369,15 +387,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     // list if shorter); the list with the most chunks still to stream per ring chunk is doubled while
     // the pool allows (dense lists get long rings = deep TMA prefetch)
     int nch[kT], used = 0;
+    const int pool_lim = pslot >= 0 ? kPool - kPlaneChunks : kPool;   // the tail of the pool holds the plane buffers
     for (int t = 0; t < kT; ++t) {
       nch[t] = 0;
-      if (t < n_term) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
+      if (t < n_term && t != pslot) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
       used += nch[t];
     }
     for (;;) {
       int best = -1; float best_ratio = 0.5f;
       for (int t = 0; t < n_term; ++t) {
-        if (nch[t] >= kMaxNCH || used + nch[t] > kPool) continue;
+        if (nch[t] == 0 || nch[t] >= kMaxNCH || used + nch[t] > pool_lim) continue;
         float ratio = (float)sm.s_n_chunks[t] / (float)nch[t];
         if (ratio > best_ratio) { best_ratio = ratio; best = t; }
       }
@@ -487,6 +506,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 
   int g0 = 0;   // next granule of the slice
   if (n_term > 0 && ne_mask == ((1u << n_term) - 1u)) g0 = g_count;   // every list is non-essential: skip the slice
+  // ---- tf plane of the plane-served list: window n's bytes live in buffer n & 1 (filled two windows ahead)
+  uint8_t* const pb = reinterpret_cast<uint8_t*>(sm.pool_docs + (kPool - kPlaneChunks) * kCH);
+  const uint8_t* const psrc =
+      pslot >= 0 ? L.ix.dense_tf + (size_t)sm.cl[sm.s_clause[pslot]].plane * (size_t)L.ix.dense_stride : nullptr;
+  const uint32_t pshift = pslot >= 0 ? 8u * (uint32_t)pslot : 0u;
+  auto issue_plane = [&](int n, int ga, int gb) {   // one thread: granules [ga, gb) of the slice
+    const int32_t wb = slice_base + (ga << kLogGran);
+    const int32_t we = min(slice_end, slice_base + (gb << kLogGran));
+    const uint32_t bytes = (uint32_t)(we - wb + 15) & ~15u;   // the plane is padded past n_docs
+    uint64_t* bar = &sm.plane_bar[n & 1];
+    mbar_arrive_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 4096u)
+      bulk_g2s(pb + (n & 1) * kW + o, psrc + wb + o, min(4096u, bytes - o), bar);
+  };
+  if (pslot >= 0 && tid == 0 && g0 < g_count) {
+    const int ga = sm.nextg[g0];
+    issue_plane(0, g0, ga);
+    if (ga < g_count) issue_plane(1, ga, sm.nextg[ga]);
+  }
+  int wn = 0;   // window counter (skipped windows count too: each has its plane copy)
   while (g0 < g_count) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
     const int g1 = sm.nextg[g0];
@@ -525,6 +564,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       }
     }
 
+    if (pslot >= 0) {
+      if (lane == 0) mbar_wait(&sm.plane_bar[wn & 1], (wn >> 1) & 1);
+      __syncwarp();
+    }
+    auto next_plane = [&]() {   // after the window's last barrier: buffer wn & 1 is free for window wn + 2
+      if (pslot >= 0 && tid == 0 && g1 < g_count) {
+        const int g2 = sm.nextg[g1];
+        if (g2 < g_count) issue_plane(wn + 2, g2, sm.nextg[g2]);
+      }
+      ++wn;
+    };
     {
       int32_t ess = 0;
 #pragma unroll
@@ -534,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
         __syncthreads();   // every warp has seen these chunks land (mbarrier phases only tell odd from even: a ring
         issue_chunks();    // slot is re-armed only after ALL warps observed its previous phase)
+        next_plane();
         continue;
       }
     }
@@ -565,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       int32_t it[kT];
 #pragma unroll
       for (int t = 0; t < kT; ++t) it[t] = (tid - rot[t]) & (kThreads - 1);
+      const uint8_t* const pbw = pb + (wn & 1) * kW - wbase;   // plane byte of doc d: pbw[d]
       int32_t idense = tid;
       bool pending = false;
       uint64_t pkey = 0;
@@ -596,9 +648,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
                   if ((v & bel) != 0 || (v & own) == 0) continue;   // a lower driver slot owns this doc
                   sl[doc] = 0u;
                   ++my_hits;
-                  const uint32_t ui = __dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u);   // sum min(tf_s, 5) * 6^s
+                  const uint32_t vv = pslot >= 0 ? (v | ((uint32_t)pbw[doc] << pshift)) : v;   // + the plane-served list's tf
+                  const uint32_t ui = __dp4a(__vminu4(vv, 0x05050505u), 0xD8240601u, 0u);   // sum min(tf_s, 5) * 6^s
                   if (sm.ubt[ui] < theta_s) continue;               // cannot reach the top-k
-                  const uint64_t raw = ((uint64_t)v << 32) | (uint32_t)doc;   // scored at the next flush
+                  const uint64_t raw = ((uint64_t)vv << 32) | (uint32_t)doc;   // scored at the next flush
                   const int p = atomicAdd(&sm.cand_count, 1);
                   if (p < kCand) sm.cand[p] = raw;
                   else { pending = true; pkey = raw; i += kThreads; break; }
@@ -671,6 +724,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
 #pragma unroll
     for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
     issue_chunks();
+    next_plane();
   }
 
   // ---------------- finish the work item: the slice merge sorts, so only a full buffer needs ordering here
