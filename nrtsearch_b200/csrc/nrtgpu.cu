@@ -286,14 +286,14 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if ((rc = ix->exc_pos.upload(epos.data(), epos.size()))) return rc;
     if ((rc = ix->exc_freq.upload(efreq.data(), efreq.size()))) return rc;
   }
-  // dense tf planes: a term present in >= 1/16 of the docs also gets a direct-address byte per doc (like the bit-set
+  // dense tf planes: a term present in >= 1/64 of the docs also gets a direct-address byte per doc (like the bit-set
   // blocks Lucene's postings format keeps for dense blocks). A list that only needs LOOKUPS in a window (a
   // non-essential MAXSCORE list) is then one TMA copy of the window's bytes instead of a scatter of its postings.
   ix->term_plane.assign((size_t)d->n_terms, -1);
   if (d->n_docs >= 4096) {
     std::vector<int32_t> dense_terms;
     for (int32_t t = 0; t < d->n_terms; ++t)
-      if ((d->term_off[t + 1] - d->term_off[t]) * 16 >= (int64_t)d->n_docs) dense_terms.push_back(t);
+      if ((d->term_off[t + 1] - d->term_off[t]) * 64 >= (int64_t)d->n_docs) dense_terms.push_back(t);
     const int64_t stride = (((int64_t)d->n_docs + 15) / 16) * 16 + 16;
     const size_t max_planes = std::min<size_t>(1024, (size_t)((8ll << 30) / stride));
     if (dense_terms.size() > max_planes) {   // keep the densest

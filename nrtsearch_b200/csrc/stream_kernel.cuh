@@ -55,6 +55,7 @@ static_assert((kThreads & (kThreads - 1)) == 0, "the round-robin posting deal ma
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
+constexpr int kSparseCap = 16384;   // a list with at most this many postings in the slice can be merged by binary search
 constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
@@ -99,6 +100,8 @@ struct alignas(128) StreamSmem {
   int n_keys;                       // entries [0, n_keys) of cand are keys kept by the last flush
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
   int plane_slot;                   // non-essential slot served from its dense tf plane (-1: none)
+  int sparse;                       // 1: sparse mode (no window array: lists merged by binary search, planes read from L2)
+  uint32_t pserve_mask;             // sparse mode: non-essential slots read from their plane instead of being streamed
   uint64_t plane_bar[2];
   unsigned long long theta;
 };
@@ -341,8 +344,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     // the densest non-essential list that has a dense tf plane is not streamed as postings at all: each window's
     // bytes of the plane are copied in by the TMA and the owners of pass 2 look their doc up (two ring-less lists
     // would not leave enough pool for the plane buffers, so queries of up to three terms only)
+    // Sparse mode: when every list is either short in this slice or a non-essential list with a plane, the window
+    // array is not needed at all -- the short lists are merged by binary search of each other's ring segments and the
+    // plane bytes are read straight from L2. Windows then span as many granules as the rings hold (often the slice).
+    int sp = 0; uint32_t pm = 0;
+    if (simple_q) {
+      const int gps = L.slice_docs >> kLogGran, gf = slice * gps, gc = min(gps, L.n_gran - gf);
+      sp = 1;
+      for (int i = 0; i < q.n_clauses && sp; ++i) {
+        const DevClause& c = sm.cl[i];
+        if (c.kind != NRTGPU_TERM) continue;
+        if (((ne >> c.slot) & 1u) && c.plane >= 0 && L.ix.dense_tf != nullptr) { pm |= 1u << c.slot; continue; }
+        const uint32_t* p = L.gbounds + ((size_t)qi * kT + c.slot) * (L.n_gran + 1) + gf;
+        if (p[gc] - p[0] > (uint32_t)kSparseCap) sp = 0;
+      }
+      if (!sp) pm = 0;
+    }
+    sm.sparse = sp; sm.pserve_mask = pm;
     int ps = -1;
-    if (ne && q.n_term <= 3 && L.ix.dense_tf != nullptr) {
+    if (!sp && ne && q.n_term <= 3 && L.ix.dense_tf != nullptr) {
       float best = INFINITY;
       for (int i = 0; i < q.n_clauses; ++i) {
         const DevClause& c = sm.cl[i];
@@ -354,13 +374,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   __syncthreads();
   const uint32_t ne_mask = sm.ne_mask;
   const int pslot = sm.plane_slot;
+  const bool sparse = sm.sparse != 0;
+  const uint32_t pserve_mask = sm.pserve_mask;
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
   for (int i = tid; i < kT * (gran_per_slice + 1); i += kThreads) {
     const int t = i / (gran_per_slice + 1), g = i % (gran_per_slice + 1);
     uint32_t v = 0;
-    if (t < n_term && t != pslot) {   // the plane-served list has no postings in the rings: empty column
+    if (t < n_term && t != pslot && !((pserve_mask >> t) & 1u)) {   // plane-served lists have no postings in the rings
       const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
       v = p[min(g, g_count)];
     }
@@ -390,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     const int pool_lim = pslot >= 0 ? kPool - kPlaneChunks : kPool;   // the tail of the pool holds the plane buffers
     for (int t = 0; t < kT; ++t) {
       nch[t] = 0;
-      if (t < n_term && t != pslot) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
+      if (t < n_term && t != pslot && !((pserve_mask >> t) & 1u)) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
       used += nch[t];
     }
     for (;;) {
@@ -420,17 +442,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   }
   // the window table: from granule g the window runs to nextg[g] = the farthest granule (<= g + kWinGran) whose
   // postings fit every ring with one chunk of alignment slack. One granule always fits (<= kGran postings).
+  // (sparse mode has no window array, so only the rings bound the run)
   for (int g = tid; g < g_count; g += kThreads) {
-    int g1 = min(g_count, g + kWinGran);
     const uint4 a = sm.gb4[g];
-    for (;;) {
+    auto fits = [&](int g1) {
       const uint4 b = sm.gb4[g1];
-      const bool fits = (int32_t)(b.x - a.x) <= rmask[0] + 1 - kCH && (int32_t)(b.y - a.y) <= rmask[1] + 1 - kCH &&
-                        (int32_t)(b.z - a.z) <= rmask[2] + 1 - kCH && (int32_t)(b.w - a.w) <= rmask[3] + 1 - kCH;
-      if (fits || g1 == g + 1) break;
-      --g1;
+      return (int32_t)(b.x - a.x) <= rmask[0] + 1 - kCH && (int32_t)(b.y - a.y) <= rmask[1] + 1 - kCH &&
+             (int32_t)(b.z - a.z) <= rmask[2] + 1 - kCH && (int32_t)(b.w - a.w) <= rmask[3] + 1 - kCH;
+    };
+    int hi = sparse ? g_count : min(g_count, g + kWinGran);
+    int lo = g + 1;                     // always accepted
+    if (hi > lo && !fits(hi)) {         // posting counts grow with g1: binary search the last run that fits
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (fits(mid)) lo = mid; else hi = mid; }
+      hi = lo;
     }
-    sm.nextg[g] = (uint16_t)g1;
+    sm.nextg[g] = (uint16_t)hi;
   }
   // warp 0 fills every free ring slot, one chunk per lane (each chunk: expect_tx + two bulk copies on its mbarrier)
   auto issue_chunks = [&]() {
@@ -595,6 +621,79 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     rot[0] = 0;
 #pragma unroll
     for (int t = 1; t < kT; ++t) rot[t] = (rot[t - 1] + cnt[t - 1]) & (kThreads - 1);
+    if (sparse) {
+      // ---------------- sparse mode: one pass, no window array. Every posting of a driver list looks its doc up in
+      // the other streamed lists' ring segments (binary search); the lowest driver list that holds the doc owns it.
+      int32_t it[kT];
+#pragma unroll
+      for (int t = 0; t < kT; ++t) it[t] = (tid - rot[t]) & (kThreads - 1);
+      bool pending = false;
+      uint64_t pkey = 0;
+      for (;;) {
+        const unsigned long long theta = sm.theta;
+        const float theta_s = theta ? key_score(theta) : -INFINITY;
+        if (pending) {
+          pending = false;
+          const int p = atomicAdd(&sm.cand_count, 1);
+          if (p < kCand) sm.cand[p] = pkey; else pending = true;
+        }
+        if (!pending) {
+#pragma unroll
+          for (int t = 0; t < kT; ++t) {
+            if (t >= n_term || pending) break;
+            if (!((driver_mask >> t) & 1u)) continue;
+            const int32_t* rd = sm.pool_docs + rbase[t];
+            const uint8_t* rf = sm.pool_f8 + rbase[t];
+            int32_t i = it[t];
+#pragma unroll 1
+            for (; i < cnt[t]; i += kThreads) {
+              const int idx = (r_cur[t] + i) & rmask[t];
+              const int32_t doc = rd[idx];
+              uint32_t v = (uint32_t)rf[idx] << (8 * t);
+              bool owner = true;
+#pragma unroll
+              for (int u = 0; u < kT; ++u) {
+                if (u == t || u >= n_term || cnt[u] == 0 || !owner) continue;
+                const int32_t* ud = sm.pool_docs + rbase[u];
+                int32_t lo = 0, hi = cnt[u];
+                while (lo < hi) {
+                  const int32_t mid = (lo + hi) >> 1;
+                  if (ud[(r_cur[u] + mid) & rmask[u]] < doc) lo = mid + 1; else hi = mid;
+                }
+                if (lo < cnt[u]) {
+                  const int uidx = (r_cur[u] + lo) & rmask[u];
+                  if (ud[uidx] == doc) {
+                    if (u < t && ((driver_mask >> u) & 1u)) owner = false;   // counted and emitted by list u's thread
+                    else v |= (uint32_t)sm.pool_f8[rbase[u] + uidx] << (8 * u);
+                  }
+                }
+              }
+              if (!owner) continue;
+              ++my_hits;
+#pragma unroll
+              for (int u = 0; u < kT; ++u)
+                if ((pserve_mask >> u) & 1u)
+                  v |= (uint32_t)__ldg(L.ix.dense_tf + (size_t)sm.cl[sm.s_clause[u]].plane * (size_t)L.ix.dense_stride + doc) << (8 * u);
+              const uint32_t ui = __dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u);
+              if (sm.ubt[ui] < theta_s) continue;
+              const uint64_t raw = ((uint64_t)v << 32) | (uint32_t)doc;
+              const int p = atomicAdd(&sm.cand_count, 1);
+              if (p < kCand) sm.cand[p] = raw;
+              else { pending = true; pkey = raw; i += kThreads; break; }
+            }
+            it[t] = i;
+          }
+        }
+        __syncthreads();
+        if (sm.cand_count <= kCand) break;
+        compact_candidates_v2(L, sm, norms0, true, has_after, after_key, L.top_k, &L.theta[qi]);
+      }
+#pragma unroll
+      for (int t = 0; t < kT; ++t) r_cur[t] += cnt[t];
+      issue_chunks();
+      next_plane();
+      continue;
+    }
     // ---------------- pass 1: scatter tf bytes
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
