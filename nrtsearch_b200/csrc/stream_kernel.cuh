@@ -55,7 +55,11 @@ static_assert((kThreads & (kThreads - 1)) == 0, "the round-robin posting deal ma
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
-constexpr int kSparseCap = 16384;   // a list with at most this many postings in the slice can be merged by binary search
+#ifndef NRT_SPARSE_CAP
+#define NRT_SPARSE_CAP 32768
+#endif
+constexpr int kSparseCap = NRT_SPARSE_CAP;   // (measured: 8K 7.6 ms, 16K 7.0, 32K 6.7, 64K 6.9)
+constexpr int kSparseCapAll = 8192;          // ... when every list drives (no pruning): each posting pays the searches   // a list with at most this many postings in the slice can be merged by binary search
 constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
@@ -96,6 +100,7 @@ struct alignas(128) StreamSmem {
   int32_t s_field[kT], s_clause[kT];
   int32_t s_ring_base[kT], s_ring_nch[kT];   // first pool chunk and ring length (chunks, power of two) per slot
   uint32_t s_scoring[kT];
+  const uint8_t* s_plane[kT];       // dense tf plane of the slot's term (NULL: none)
   int cand_count;
   int n_keys;                       // entries [0, n_keys) of cand are keys kept by the last flush
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   const int n_term = sm.q.n_term;
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
                   sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
-                  sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; }
+                  sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; sm.s_plane[tid] = nullptr; }
   __syncthreads();
   // ---- MAXSCORE split (pure term disjunctions, once the query has collected more than totalHitsThreshold hits):
   // the lists whose list-wide score bounds sum (in double, ascending) to less than theta.score are non-essential --
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
         if (c.kind != NRTGPU_TERM) continue;
         if (((ne >> c.slot) & 1u) && c.plane >= 0 && L.ix.dense_tf != nullptr) { pm |= 1u << c.slot; continue; }
         const uint32_t* p = L.gbounds + ((size_t)qi * kT + c.slot) * (L.n_gran + 1) + gf;
-        if (p[gc] - p[0] > (uint32_t)kSparseCap) sp = 0;
+        if (p[gc] - p[0] > (uint32_t)(ne ? kSparseCap : kSparseCapAll)) sp = 0;
       }
       if (!sp) pm = 0;
     }
@@ -402,6 +407,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     sm.s_scoring[s] = sm.cl[tid].scoring != 0;
     sm.s_field[s] = sm.cl[tid].field;
     sm.s_clause[s] = tid;
+    sm.s_plane[s] = (sm.cl[tid].plane >= 0 && L.ix.dense_tf != nullptr)
+                        ? L.ix.dense_tf + (size_t)sm.cl[tid].plane * (size_t)L.ix.dense_stride : nullptr;
   }
   __syncthreads();
   if (tid == 0) {
@@ -556,9 +563,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
     const int g1 = sm.nextg[g0];
     int32_t cnt[kT];
+    const uint4 gb_w = sm.gb4[g0];   // postings of every list below the window's first granule
     {
-      const uint4 a = sm.gb4[g0], b = sm.gb4[g1];
-      cnt[0] = (int32_t)(b.x - a.x); cnt[1] = (int32_t)(b.y - a.y); cnt[2] = (int32_t)(b.z - a.z); cnt[3] = (int32_t)(b.w - a.w);
+      const uint4 b = sm.gb4[g1];
+      cnt[0] = (int32_t)(b.x - gb_w.x); cnt[1] = (int32_t)(b.y - gb_w.y); cnt[2] = (int32_t)(b.z - gb_w.z); cnt[3] = (int32_t)(b.w - gb_w.w);
     }
     const int32_t wbase = slice_base + (g0 << kLogGran);
     const int32_t wend = min(slice_end, slice_base + (g1 << kLogGran));
@@ -650,17 +658,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
               const int idx = (r_cur[t] + i) & rmask[t];
               const int32_t doc = rd[idx];
               uint32_t v = (uint32_t)rf[idx] << (8 * t);
+              // plane bytes first (L2 latency overlaps the searches below)
+#pragma unroll
+              for (int u = 0; u < kT; ++u)
+                if ((pserve_mask >> u) & 1u) v |= (uint32_t)__ldg(sm.s_plane[u] + doc) << (8 * u);
+              // the granule bounds narrow every search to the postings of the doc's own 1024-doc granule
+              const int g = (doc - slice_base) >> kLogGran;
+              const uint4 glo = sm.gb4[g], ghi = sm.gb4[g + 1];
+              const uint32_t glo_a[kT] = {glo.x - gb_w.x, glo.y - gb_w.y, glo.z - gb_w.z, glo.w - gb_w.w};
+              const uint32_t ghi_a[kT] = {ghi.x - gb_w.x, ghi.y - gb_w.y, ghi.z - gb_w.z, ghi.w - gb_w.w};
               bool owner = true;
 #pragma unroll
               for (int u = 0; u < kT; ++u) {
                 if (u == t || u >= n_term || cnt[u] == 0 || !owner) continue;
                 const int32_t* ud = sm.pool_docs + rbase[u];
-                int32_t lo = 0, hi = cnt[u];
+                int32_t lo = (int32_t)glo_a[u];
+                const int32_t end = (int32_t)ghi_a[u];
+                int32_t hi = end;
                 while (lo < hi) {
                   const int32_t mid = (lo + hi) >> 1;
                   if (ud[(r_cur[u] + mid) & rmask[u]] < doc) lo = mid + 1; else hi = mid;
                 }
-                if (lo < cnt[u]) {
+                if (lo < end) {
                   const int uidx = (r_cur[u] + lo) & rmask[u];
                   if (ud[uidx] == doc) {
                     if (u < t && ((driver_mask >> u) & 1u)) owner = false;   // counted and emitted by list u's thread
@@ -670,10 +689,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
               }
               if (!owner) continue;
               ++my_hits;
-#pragma unroll
-              for (int u = 0; u < kT; ++u)
-                if ((pserve_mask >> u) & 1u)
-                  v |= (uint32_t)__ldg(L.ix.dense_tf + (size_t)sm.cl[sm.s_clause[u]].plane * (size_t)L.ix.dense_stride + doc) << (8 * u);
               const uint32_t ui = __dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u);
               if (sm.ubt[ui] < theta_s) continue;
               const uint64_t raw = ((uint64_t)v << 32) | (uint32_t)doc;
