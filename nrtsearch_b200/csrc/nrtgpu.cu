@@ -176,6 +176,7 @@ static void free_batch(nrtgpu_batch* b);
 struct nrtgpu_batch {
   nrtgpu_index* ix = nullptr;
   int32_t nq = 0, top_k = 0, n_slices = 0, n_work = 0;
+  int32_t n_work_simple = 0;   // the first n_work_simple work items belong to pure single-field term disjunctions
   bool wide_slots = false;
   bool exhaustive = true;
   int64_t alg_postings = 0;
@@ -183,6 +184,7 @@ struct nrtgpu_batch {
   DevBuf<DevQuery> queries;
   DevBuf<int32_t> work_query, work_slice;
   DevBuf<uint32_t> gbounds;  // stream kernel: [nq][4][n_gran+1]
+  DevBuf<float> qtables;     // stream kernel: [nq][kQTabFloats] score + bound tables
   DevBuf<int32_t> pruned;    // [nq] relation GTE flags
   int32_t slice_docs = 0;
   int64_t threshold = INT32_MAX;
@@ -233,7 +235,9 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(BoolSmem<uint32_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint64_t>)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(v2::StreamSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kPGemmSmem));
@@ -553,9 +557,19 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     if (dq[qi].dense_driver) cost[qi] += ix->n_docs;
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+  // pure disjunctions of scoring term clauses over one text field (no deletes) run in their own instantiation of
+  // the stream kernel: their work items come first
+  auto is_simple = [&](int qi) {
+    const DevQuery& o = dq[(size_t)qi];
+    return o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
+           o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
+  };
   std::vector<int32_t> wq, ws;
-  for (int s = 0; s < b->n_slices; ++s)
-    for (int qi : order) { wq.push_back(qi); ws.push_back(s); }
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int s = 0; s < b->n_slices; ++s)
+      for (int qi : order) if (is_simple(qi) == (pass == 0)) { wq.push_back(qi); ws.push_back(s); }
+    if (pass == 0) b->n_work_simple = (int32_t)wq.size();
+  }
   b->n_work = (int32_t)wq.size();
   int rc;
   if ((rc = b->clauses.upload_async(dc.data(), dc.size(), st))) return rc;
@@ -581,6 +595,12 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_gran = b->n_gran;
     B.gbounds = b->gbounds.p;
     v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B);
+    NRT_CUDA_TRY(cudaGetLastError());
+    if ((rc = b->qtables.alloc((size_t)nq * v2::kQTabFloats))) return rc;
+    v2::QTabLaunch Q;
+    Q.ix = B.ix; Q.clauses = B.clauses; Q.queries = B.queries; Q.field_min_norm = ix->field_min_norm.p; Q.nq = nq;
+    Q.qtables = b->qtables.p;
+    if (nq > 0) v2::query_tables_kernel<<<(unsigned)nq, 256, 0, st>>>(Q);
     NRT_CUDA_TRY(cudaGetLastError());
   }
   if (!b->ev[0][0]) for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
@@ -620,11 +640,19 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     if (!b->wide_slots) {
       v2::StreamLaunch S;
       S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
-      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.field_min_norm = b->ix->field_min_norm.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
+      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.qtables = b->qtables.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
       S.slice_docs = b->slice_docs;
       S.threshold = b->threshold; S.pruned = b->pruned.p;
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
-      v2::posting_stream_kernel<<<b->n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+      if (b->n_work_simple > 0) {
+        S.n_work = b->n_work_simple;
+        v2::posting_stream_kernel<true><<<b->n_work_simple, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+      }
+      if (b->n_work > b->n_work_simple) {
+        S.work_query = L.work_query + b->n_work_simple; S.work_slice = L.work_slice + b->n_work_simple;
+        S.n_work = b->n_work - b->n_work_simple;
+        v2::posting_stream_kernel<false><<<S.n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+      }
     } else
       bool_window_kernel<uint64_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint64_t>), st>>>(L);
     NRT_CUDA_TRY(cudaGetLastError());
@@ -684,7 +712,8 @@ int nrtgpu_batch_reset_timing(nrtgpu_batch* b) {
 int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run, int64_t* work_items) {
   if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
   if (alg_postings) *alg_postings = b->alg_postings;
-  if (launches_per_run) *launches_per_run = (b->n_work > 0 ? 1 : 0) + 1;
+  if (launches_per_run) *launches_per_run = (b->wide_slots ? (b->n_work > 0 ? 1 : 0)
+                                                           : (b->n_work_simple > 0 ? 1 : 0) + (b->n_work > b->n_work_simple ? 1 : 0)) + 1;
   if (work_items) *work_items = b->n_work;
   return NRTGPU_OK;
 }

@@ -15,6 +15,7 @@
 //     compacts once, and parked threads resume.
 // Results are bit-identical to the exhaustive oracle; totalHits stay exact (every owner is counted).
 #pragma once
+#include <cstddef>
 #include "bool_kernel.cuh"
 
 namespace nrtgpu {
@@ -55,11 +56,15 @@ static_assert((kThreads & (kThreads - 1)) == 0, "the round-robin posting deal ma
 constexpr int kWinGran = kW / kGran;  // a window spans up to 8 granules
 constexpr int kUbt = 6 * 6 * 6 * 6;   // upper-bound table over min(tf, 5) of the four slots
 constexpr uint32_t kChunkBytes = kCH * 4 + kCH;
+constexpr int kQTabFloats = kT * (kTfTab + 1) * 256 + kUbt;   // per-query score + bound tables (query_tables_kernel)
 #ifndef NRT_SPARSE_CAP
-#define NRT_SPARSE_CAP 32768
+#define NRT_SPARSE_CAP 65536
 #endif
-constexpr int kSparseCap = NRT_SPARSE_CAP;   // (measured: 8K 7.6 ms, 16K 7.0, 32K 6.7, 64K 6.9)
-constexpr int kSparseCapAll = 8192;          // ... when every list drives (no pruning): each posting pays the searches   // a list with at most this many postings in the slice can be merged by binary search
+constexpr int kSparseCap = NRT_SPARSE_CAP;   // (measured with granule-narrowed searches: 32K 5.84 ms, 64K 5.79, 128K 5.90)
+#ifndef NRT_SPARSE_CAP_ALL
+#define NRT_SPARSE_CAP_ALL 32768
+#endif
+constexpr int kSparseCapAll = NRT_SPARSE_CAP_ALL;          // ... when every list drives (no pruning): each posting pays the searches   // a list with at most this many postings in the slice can be merged by binary search
 constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
@@ -69,7 +74,7 @@ struct StreamLaunch {
   const int32_t* work_query;
   const int32_t* work_slice;
   const uint32_t* gbounds;   // [nq][kT][n_gran+1]: postings of the clause with doc < g*kGran (relative to post_base)
-  const uint8_t* field_min_norm;  // [n_fields] norm byte of the shortest field value present (tightest score bound)
+  const float* qtables;      // [nq][kQTabFloats]: tbl[slot][tf][norm] then ubt[tf pattern] of every query
   int32_t n_gran;
   int32_t n_work, n_slices, top_k;
   int32_t slice_docs;
@@ -86,8 +91,8 @@ struct alignas(128) StreamSmem {
   uint8_t pool_f8[kPool * kCH];          // 20 KB
   uint32_t slots[kW];                    // 64 KB
   uint64_t cand[kCand];                  // 16 KB
-  float tbl[kT][kTfTab + 1][256];        // 20 KB
-  float ubt[kUbt];                       //  5 KB
+  float tbl[kT][kTfTab + 1][256];        // exact BM25 floats per (slot, tf, norm byte); row tf = 0 is +0.0f
+  float ubt[kUbt];                       // score bound per tf pattern (directly after tbl: one TMA copy fills both)
   uint64_t full_bar[kPool];
   uint4 gb4[kSliceDocs / kGran + 1];      // 8 KB granule bounds of this slice, one 16-byte row {slot 0..3} per granule
   uint16_t nextg[kSliceDocs / kGran + 2]; // 1 KB window table: the window that starts at granule g ends at nextg[g]
@@ -108,6 +113,7 @@ struct alignas(128) StreamSmem {
   int sparse;                       // 1: sparse mode (no window array: lists merged by binary search, planes read from L2)
   uint32_t pserve_mask;             // sparse mode: non-essential slots read from their plane instead of being streamed
   uint64_t plane_bar[2];
+  uint64_t tab_bar;
   unsigned long long theta;
 };
 static_assert(sizeof(StreamSmem) <= (kCtasPerSm == 1 ? 232448 : 115712), "StreamSmem exceeds the shared memory budget of sm_100");
@@ -289,6 +295,10 @@ __device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, Str
   __syncthreads();
 }
 
+// kSimple: every query of the launch is a pure disjunction of scoring term clauses over one text field, no deletes
+// (the host splits the work list): only that instantiation carries the tf-pattern bound, deferred scoring, MAXSCORE,
+// tf planes and the sparse mode; the other one carries the generic clause evaluation.
+template <bool kSimple>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(StreamLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     for (int j = 0; j < kPool; ++j) mbar_init(&sm.full_bar[j], 1);
     mbar_init(&sm.plane_bar[0], 1);
     mbar_init(&sm.plane_bar[1], 1);
+    mbar_init(&sm.tab_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -328,8 +339,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (tid == 0) {
     uint32_t ne = 0;
     const DevQuery& q = sm.q;
-    const bool simple_q = q.single_field >= 0 && !q.has_nonterm && !q.nonterm_scoring && L.ix.live_bits == nullptr &&
-                          q.n_req == 0 && q.not_term_mask == 0 && q.msm <= 1;
+    const bool simple_q = kSimple;
     if (simple_q && sm.theta != 0ull && L.threshold < (int64_t)INT32_MAX &&
         (int64_t)*(volatile unsigned long long*)&L.total_hits[qi] > L.threshold) {
       const float theta_s = key_score(sm.theta);
@@ -377,21 +387,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     sm.plane_slot = ps;
   }
   __syncthreads();
-  const uint32_t ne_mask = sm.ne_mask;
-  const int pslot = sm.plane_slot;
-  const bool sparse = sm.sparse != 0;
-  const uint32_t pserve_mask = sm.pserve_mask;
+  const uint32_t ne_mask = kSimple ? sm.ne_mask : 0u;
+  const int pslot = kSimple ? sm.plane_slot : -1;
+  const bool sparse = kSimple && sm.sparse != 0;
+  const uint32_t pserve_mask = kSimple ? sm.pserve_mask : 0u;
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
-  for (int i = tid; i < kT * (gran_per_slice + 1); i += kThreads) {
-    const int t = i / (gran_per_slice + 1), g = i % (gran_per_slice + 1);
-    uint32_t v = 0;
-    if (t < n_term && t != pslot && !((pserve_mask >> t) & 1u)) {   // plane-served lists have no postings in the rings
-      const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
-      v = p[min(g, g_count)];
-    }
-    reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = v;
+#pragma unroll
+  for (int t = 0; t < kT; ++t) {
+    const bool streamed = t < n_term && t != pslot && !((pserve_mask >> t) & 1u);   // plane-served lists: empty column
+    const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
+    for (int g = tid; g <= gran_per_slice; g += kThreads)
+      reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = streamed ? p[min(g, g_count)] : 0u;
   }
   __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
@@ -484,45 +492,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   };
   issue_chunks();
 
-  // ---- exact BM25 table tbl[slot][tf][norm byte] (row tf = 0 is +0.0f)
-  for (int i = tid; i < kT * (kTfTab + 1) * 256; i += kThreads) {
-    const int s = i / ((kTfTab + 1) * 256), tf = (i / 256) % (kTfTab + 1), nb = i & 255;
-    float v = 0.0f;
-    if (s < n_term && tf > 0) {
-      const DevClause& c = sm.cl[sm.s_clause[s]];
-      if (c.scoring) v = bm25_score(c.weight, (float)tf, __ldg(&L.ix.caches[c.field * 256 + nb]));
-    }
-    sm.tbl[s][tf][nb] = v;
+  // ---- the query's tables (exact BM25 floats tbl[slot][tf][norm byte], bound per tf pattern ubt[]) were computed once
+  //      per batch by query_tables_kernel: one TMA copy brings both in
+  static_assert(offsetof(StreamSmem, ubt) == offsetof(StreamSmem, tbl) + sizeof(float) * kT * (kTfTab + 1) * 256, "tbl/ubt adjacent");
+  if (tid == 0) {
+    constexpr uint32_t kBytes = (uint32_t)kQTabFloats * 4u;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(L.qtables + (size_t)qi * kQTabFloats);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(&sm.tbl[0][0][0]);
+    mbar_arrive_expect_tx(&sm.tab_bar, kBytes);
+    for (uint32_t o = 0; o < kBytes; o += 4096u) bulk_g2s(dst + o, src + o, min(4096u, kBytes - o), &sm.tab_bar);
   }
-  const bool fast = sm.q.single_field >= 0 && !sm.q.has_nonterm && !sm.q.nonterm_scoring && L.ix.live_bits == nullptr;
-  // pure disjunction of terms over one field: every owner is a hit, score = (float) double sum of the slots
-  const bool simple = fast && sm.q.n_req == 0 && sm.q.not_term_mask == 0 && sm.q.msm <= 1;
-  __syncthreads();
-  // ---- upper bounds per tf pattern (simple queries): same double sum, each term at the shortest field
-  //      length present (largest score); tf >= 5 is bounded by the clause weight (limit tf -> inf)
-  if (simple) {
-    const uint32_t nbmin = L.field_min_norm ? (uint32_t)L.field_min_norm[sm.q.single_field] : 0u;
-    for (int i = tid; i < kUbt; i += kThreads) {
-      const int c[kT] = {i % 6, (i / 6) % 6, (i / 36) % 6, i / 216};
-      double sum = 0.0;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        float u = 0.0f;
-        if (t < n_term && c[t] > 0) {
-          const DevClause& cl = sm.cl[sm.s_clause[t]];
-          u = (c[t] <= 4) ? bm25_score(cl.weight, (float)c[t], __ldg(&L.ix.caches[cl.field * 256 + nbmin])) : cl.weight;
-        }
-        sum += (double)u;
-      }
-      sm.ubt[i] = (float)sum;
-    }
-  }
+  const bool simple = kSimple;
+  if (lane == 0) mbar_wait(&sm.tab_bar, 0);
   __syncthreads();
 
   const int32_t slice_base = slice * L.slice_docs;
   int32_t slice_end = slice_base + L.slice_docs;
   if (slice_end > L.ix.n_docs || slice_end < slice_base) slice_end = L.ix.n_docs;
-  const bool dense = sm.q.dense_driver != 0;
+  const bool dense = !kSimple && sm.q.dense_driver != 0;
   const bool has_after = sm.q.has_after != 0;
   const uint64_t after_key = sm.q.after_key;
   const uint32_t driver_mask = sm.q.driver_mask & ~ne_mask;            // non-essential lists never own a doc
@@ -851,6 +838,54 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
   for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
   if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
+}
+
+// tbl[slot][tf][norm byte] and ubt[tf pattern] of every query, once per batch (the 20 work items of a query share them)
+struct QTabLaunch {
+  DevIndexView ix;
+  const DevClause* clauses;
+  const DevQuery* queries;
+  const uint8_t* field_min_norm;  // [n_fields] norm byte of the shortest field value present (tightest score bound)
+  int32_t nq;
+  float* qtables;
+};
+
+__global__ void __launch_bounds__(256) query_tables_kernel(QTabLaunch Q) {
+  const int q = blockIdx.x;
+  if (q >= Q.nq) return;
+  __shared__ DevClause cl[kT];
+  __shared__ int have[kT];
+  const DevQuery dq = Q.queries[q];
+  if (threadIdx.x < kT) have[threadIdx.x] = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < dq.n_clauses) {
+    const DevClause c = Q.clauses[dq.clause_begin + threadIdx.x];
+    if (c.kind == NRTGPU_TERM && c.slot >= 0 && c.slot < kT) { cl[c.slot] = c; have[c.slot] = 1; }
+  }
+  __syncthreads();
+  float* out = Q.qtables + (size_t)q * kQTabFloats;
+  for (int i = threadIdx.x; i < kT * (kTfTab + 1) * 256; i += blockDim.x) {
+    const int s = i / ((kTfTab + 1) * 256), tf = (i / 256) % (kTfTab + 1), nb = i & 255;
+    float v = 0.0f;
+    if (have[s] && tf > 0 && cl[s].scoring) v = bm25_score(cl[s].weight, (float)tf, __ldg(&Q.ix.caches[cl[s].field * 256 + nb]));
+    out[i] = v;
+  }
+  // upper bounds per tf pattern (used by pure single-field disjunctions): the same double sum, each term at the
+  // shortest field length present (largest score); tf >= 5 is bounded by the clause weight (limit tf -> inf)
+  const uint32_t nbmin = (dq.single_field >= 0 && Q.field_min_norm) ? (uint32_t)Q.field_min_norm[dq.single_field] : 0u;
+  float* ub = out + kT * (kTfTab + 1) * 256;
+  for (int i = threadIdx.x; i < kUbt; i += blockDim.x) {
+    const int c[kT] = {i % 6, (i / 6) % 6, (i / 36) % 6, i / 216};
+    double sum = 0.0;
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      float u = 0.0f;
+      if (have[t] && c[t] > 0)
+        u = (c[t] <= 4) ? bm25_score(cl[t].weight, (float)c[t], __ldg(&Q.ix.caches[cl[t].field * 256 + nbmin])) : cl[t].weight;
+      sum += (double)u;
+    }
+    ub[i] = (float)sum;
+  }
 }
 
 // postings of every (query, term slot) below each 2048-doc granule boundary (relative to the clause's list)
