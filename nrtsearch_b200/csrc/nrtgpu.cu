@@ -185,6 +185,7 @@ struct nrtgpu_batch {
   DevBuf<int32_t> work_query, work_slice;
   DevBuf<uint32_t> gbounds;  // stream kernel: [nq][4][n_gran+1]
   DevBuf<float> qtables;     // stream kernel: [nq][kQTabFloats] score + bound tables
+  DevBuf<unsigned long long> mode_stats;   // NRTGPU_DEBUG_MODES=1: cycles / work items per kernel mode
   DevBuf<int32_t> pruned;    // [nq] relation GTE flags
   int32_t slice_docs = 0;
   int64_t threshold = INT32_MAX;
@@ -643,6 +644,12 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.qtables = b->qtables.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
       S.slice_docs = b->slice_docs;
       S.threshold = b->threshold; S.pruned = b->pruned.p;
+      S.mode_stats = nullptr;
+      if (getenv("NRTGPU_DEBUG_MODES")) {
+        if (!b->mode_stats.p && b->mode_stats.alloc(6)) return NRTGPU_ERR_CUDA;
+        NRT_CUDA_TRY(cudaMemsetAsync(b->mode_stats.p, 0, 6 * sizeof(unsigned long long), st));
+        S.mode_stats = b->mode_stats.p;
+      }
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
       if (b->n_work_simple > 0) {
         S.n_work = b->n_work_simple;
@@ -658,6 +665,13 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     NRT_CUDA_TRY(cudaGetLastError());
   }
   NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
+  if (b->mode_stats.p && getenv("NRTGPU_DEBUG_MODES")) {
+    unsigned long long h[6];
+    NRT_CUDA_TRY(cudaMemcpyAsync(h, b->mode_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NRT_CUDA_TRY(cudaStreamSynchronize(st));
+    fprintf(stderr, "[nrtgpu modes] window: %llu items %.0f cyc/item | window+maxscore: %llu items %.0f | sparse: %llu items %.0f\n",
+            h[1], h[1] ? (double)h[0] / h[1] : 0.0, h[3], h[3] ? (double)h[2] / h[3] : 0.0, h[5], h[5] ? (double)h[4] / h[5] : 0.0);
+  }
   MergeLaunch M;
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
   M.n_lists = b->n_slices; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;

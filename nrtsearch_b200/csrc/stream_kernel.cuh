@@ -74,6 +74,7 @@ struct StreamLaunch {
   const int32_t* work_query;
   const int32_t* work_slice;
   const uint32_t* gbounds;   // [nq][kT][n_gran+1]: postings of the clause with doc < g*kGran (relative to post_base)
+  unsigned long long* mode_stats;  // optional (NRTGPU_DEBUG_MODES): [mode 0 window / 1 window+MAXSCORE / 2 sparse][cycles, items]
   const float* qtables;      // [nq][kQTabFloats]: tbl[slot][tf][norm] then ubt[tf pattern] of every query
   int32_t n_gran;
   int32_t n_work, n_slices, top_k;
@@ -273,6 +274,15 @@ __device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, Str
       if (mine[j]) sm.cand[atomicAdd(&sm.cand_count, 1)] = mine[j];
     __syncthreads();
     n = sm.cand_count;
+    if (n < top_k) {   // fewer than top_k keys in all: nothing to drop, no k-th key to publish, and the slice merge sorts
+      if (threadIdx.x == 0) {
+        sm.n_keys = n;
+        const unsigned long long g = *(volatile unsigned long long*)g_theta;
+        if (g > sm.theta) sm.theta = g;
+      }
+      __syncthreads();
+      return;
+    }
   }
   int m = next_pow2(n < 2 ? 2 : n);
   for (int i = n + threadIdx.x; i < m; i += blockDim.x) sm.cand[i] = 0ull;
@@ -308,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (wi >= L.n_work) return;
   const int qi = L.work_query[wi];
   const int slice = L.work_slice[wi];
+  const long long t_start = L.mode_stats ? clock64() : 0ll;
 
   if (tid == 0) {
     sm.q = L.queries[qi];
@@ -320,12 +331,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     mbar_init(&sm.tab_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the query's tables (exact BM25 floats tbl[slot][tf][norm byte], bound per tf pattern ubt[]) were computed once
+    // per batch by query_tables_kernel: one TMA copy brings both in while the rest of the set-up runs
+    constexpr uint32_t kBytes = (uint32_t)kQTabFloats * 4u;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(L.qtables + (size_t)qi * kQTabFloats);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(&sm.tbl[0][0][0]);
+    mbar_arrive_expect_tx(&sm.tab_bar, kBytes);
+    for (uint32_t o = 0; o < kBytes; o += 4096u) bulk_g2s(dst + o, src + o, min(4096u, kBytes - o), &sm.tab_bar);
   }
   __syncthreads();
   const int ncl = sm.q.n_clauses;
   if (tid < ncl) sm.cl[tid] = L.clauses[sm.q.clause_begin + tid];
-  for (int i = tid; i < kW; i += kThreads) sm.slots[i] = 0u;
+  for (int i = tid; i < kW / 4; i += kThreads) reinterpret_cast<uint4*>(sm.slots)[i] = make_uint4(0u, 0u, 0u, 0u);
   const int n_term = sm.q.n_term;
+  // granule bounds of the slice (every list; lists served from their plane get their column cleared below)
+  const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
+  const int g_first = slice * gran_per_slice;
+  const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
+#pragma unroll
+  for (int t = 0; t < kT; ++t) {
+    const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
+    for (int g = tid; g <= gran_per_slice; g += kThreads)
+      reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = (t < n_term) ? p[min(g, g_count)] : 0u;
+  }
   if (tid < kT) { sm.s_r_begin[tid] = 0; sm.s_r_end[tid] = 0; sm.s_n_chunks[tid] = 0; sm.s_issued[tid] = 0; sm.s_scoring[tid] = 0;
                   sm.s_gdocs[tid] = nullptr; sm.s_gf8[tid] = nullptr; sm.s_field[tid] = 0; sm.s_clause[tid] = 0;
                   sm.s_ring_base[tid] = 0; sm.s_ring_nch[tid] = 2; sm.s_plane[tid] = nullptr; }
@@ -364,14 +392,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     // plane bytes are read straight from L2. Windows then span as many granules as the rings hold (often the slice).
     int sp = 0; uint32_t pm = 0;
     if (simple_q) {
-      const int gps = L.slice_docs >> kLogGran, gf = slice * gps, gc = min(gps, L.n_gran - gf);
       sp = 1;
       for (int i = 0; i < q.n_clauses && sp; ++i) {
         const DevClause& c = sm.cl[i];
         if (c.kind != NRTGPU_TERM) continue;
         if (((ne >> c.slot) & 1u) && c.plane >= 0 && L.ix.dense_tf != nullptr) { pm |= 1u << c.slot; continue; }
-        const uint32_t* p = L.gbounds + ((size_t)qi * kT + c.slot) * (L.n_gran + 1) + gf;
-        if (p[gc] - p[0] > (uint32_t)(ne ? kSparseCap : kSparseCapAll)) sp = 0;
+        const uint32_t n_slice = reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[c.slot] -
+                                 reinterpret_cast<const uint32_t*>(&sm.gb4[0])[c.slot];
+        if (n_slice > (uint32_t)(ne ? kSparseCap : kSparseCapAll)) sp = 0;
       }
       if (!sp) pm = 0;
     }
@@ -391,21 +419,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   const int pslot = kSimple ? sm.plane_slot : -1;
   const bool sparse = kSimple && sm.sparse != 0;
   const uint32_t pserve_mask = kSimple ? sm.pserve_mask : 0u;
-  const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
-  const int g_first = slice * gran_per_slice;
-  const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
-#pragma unroll
-  for (int t = 0; t < kT; ++t) {
-    const bool streamed = t < n_term && t != pslot && !((pserve_mask >> t) & 1u);   // plane-served lists: empty column
-    const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
-    for (int g = tid; g <= gran_per_slice; g += kThreads)
-      reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = streamed ? p[min(g, g_count)] : 0u;
-  }
-  __syncthreads();
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
-    const int64_t g0 = sm.cl[tid].post_base + reinterpret_cast<const uint32_t*>(&sm.gb4[0])[s],
-                  g1 = sm.cl[tid].post_base + reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[s];
+    const bool served = s == pslot || ((pserve_mask >> s) & 1u);   // plane-served lists are not streamed: no postings
+    const int64_t g0 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[0])[s]),
+                  g1 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[s]);
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
@@ -417,6 +435,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     sm.s_clause[s] = tid;
     sm.s_plane[s] = (sm.cl[tid].plane >= 0 && L.ix.dense_tf != nullptr)
                         ? L.ix.dense_tf + (size_t)sm.cl[tid].plane * (size_t)L.ix.dense_stride : nullptr;
+  }
+  if (pslot >= 0 || pserve_mask != 0u) {   // plane-served lists have no postings in the rings: empty column
+#pragma unroll
+    for (int t = 0; t < kT; ++t)
+      if (t == pslot || ((pserve_mask >> t) & 1u))
+        for (int g = tid; g <= gran_per_slice; g += kThreads) reinterpret_cast<uint32_t*>(&sm.gb4[g])[t] = 0u;
   }
   __syncthreads();
   if (tid == 0) {
@@ -492,16 +516,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   };
   issue_chunks();
 
-  // ---- the query's tables (exact BM25 floats tbl[slot][tf][norm byte], bound per tf pattern ubt[]) were computed once
-  //      per batch by query_tables_kernel: one TMA copy brings both in
   static_assert(offsetof(StreamSmem, ubt) == offsetof(StreamSmem, tbl) + sizeof(float) * kT * (kTfTab + 1) * 256, "tbl/ubt adjacent");
-  if (tid == 0) {
-    constexpr uint32_t kBytes = (uint32_t)kQTabFloats * 4u;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(L.qtables + (size_t)qi * kQTabFloats);
-    unsigned char* dst = reinterpret_cast<unsigned char*>(&sm.tbl[0][0][0]);
-    mbar_arrive_expect_tx(&sm.tab_bar, kBytes);
-    for (uint32_t o = 0; o < kBytes; o += 4096u) bulk_g2s(dst + o, src + o, min(4096u, kBytes - o), &sm.tab_bar);
-  }
   const bool simple = kSimple;
   if (lane == 0) mbar_wait(&sm.tab_bar, 0);
   __syncthreads();
@@ -618,70 +633,87 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     for (int t = 1; t < kT; ++t) rot[t] = (rot[t - 1] + cnt[t - 1]) & (kThreads - 1);
     if (sparse) {
       // ---------------- sparse mode: one pass, no window array. Every posting of a driver list looks its doc up in
-      // the other streamed lists' ring segments (binary search); the lowest driver list that holds the doc owns it.
+      // the other streamed lists' ring segments (binary search, narrowed to the doc's own 1024-doc granule by the
+      // granule bounds); the lowest driver list that holds the doc owns it. A thread works on TWO postings at a time
+      // (a CTA stride apart): their plane gathers and search chains are independent and overlap.
       int32_t it[kT];
 #pragma unroll
       for (int t = 0; t < kT; ++t) it[t] = (tid - rot[t]) & (kThreads - 1);
-      bool pending = false;
-      uint64_t pkey = 0;
+      int npend = 0;
+      uint64_t pk0 = 0, pk1 = 0;
+      auto push = [&](uint64_t raw) {
+        const int p = atomicAdd(&sm.cand_count, 1);
+        if (p < kCand) sm.cand[p] = raw;
+        else { if (npend == 0) pk0 = raw; else pk1 = raw; ++npend; }
+      };
       for (;;) {
         const unsigned long long theta = sm.theta;
         const float theta_s = theta ? key_score(theta) : -INFINITY;
-        if (pending) {
-          pending = false;
-          const int p = atomicAdd(&sm.cand_count, 1);
-          if (p < kCand) sm.cand[p] = pkey; else pending = true;
+        if (npend) {   // parked by the last flush: append again
+          const int n = npend; const uint64_t a = pk0, b = pk1;
+          npend = 0;
+          push(a);
+          if (n > 1) push(b);
         }
-        if (!pending) {
+        if (!npend) {
 #pragma unroll
           for (int t = 0; t < kT; ++t) {
-            if (t >= n_term || pending) break;
+            if (t >= n_term || npend) break;
             if (!((driver_mask >> t) & 1u)) continue;
             const int32_t* rd = sm.pool_docs + rbase[t];
             const uint8_t* rf = sm.pool_f8 + rbase[t];
             int32_t i = it[t];
 #pragma unroll 1
-            for (; i < cnt[t]; i += kThreads) {
-              const int idx = (r_cur[t] + i) & rmask[t];
-              const int32_t doc = rd[idx];
-              uint32_t v = (uint32_t)rf[idx] << (8 * t);
-              // plane bytes first (L2 latency overlaps the searches below)
+            for (; i < cnt[t]; i += 2 * kThreads) {
+              const bool hasB = i + kThreads < cnt[t];
+              const int idxA = (r_cur[t] + i) & rmask[t], idxB = (r_cur[t] + i + kThreads) & rmask[t];
+              const int32_t docA = rd[idxA], docB = hasB ? rd[idxB] : docA;
+              uint32_t vA = (uint32_t)rf[idxA] << (8 * t), vB = (uint32_t)rf[idxB] << (8 * t);
 #pragma unroll
               for (int u = 0; u < kT; ++u)
-                if ((pserve_mask >> u) & 1u) v |= (uint32_t)__ldg(sm.s_plane[u] + doc) << (8 * u);
-              // the granule bounds narrow every search to the postings of the doc's own 1024-doc granule
-              const int g = (doc - slice_base) >> kLogGran;
-              const uint4 glo = sm.gb4[g], ghi = sm.gb4[g + 1];
-              const uint32_t glo_a[kT] = {glo.x - gb_w.x, glo.y - gb_w.y, glo.z - gb_w.z, glo.w - gb_w.w};
-              const uint32_t ghi_a[kT] = {ghi.x - gb_w.x, ghi.y - gb_w.y, ghi.z - gb_w.z, ghi.w - gb_w.w};
-              bool owner = true;
+                if ((pserve_mask >> u) & 1u) {
+                  const uint8_t* pl = sm.s_plane[u];
+                  const uint32_t a = __ldg(pl + docA), b = __ldg(pl + docB);
+                  vA |= a << (8 * u); vB |= b << (8 * u);
+                }
+              const int gA = (docA - slice_base) >> kLogGran, gB = (docB - slice_base) >> kLogGran;
+              bool ownA = true, ownB = hasB;
 #pragma unroll
               for (int u = 0; u < kT; ++u) {
-                if (u == t || u >= n_term || cnt[u] == 0 || !owner) continue;
+                if (u == t || u >= n_term || cnt[u] == 0) continue;
                 const int32_t* ud = sm.pool_docs + rbase[u];
-                int32_t lo = (int32_t)glo_a[u];
-                const int32_t end = (int32_t)ghi_a[u];
-                int32_t hi = end;
-                while (lo < hi) {
-                  const int32_t mid = (lo + hi) >> 1;
-                  if (ud[(r_cur[u] + mid) & rmask[u]] < doc) lo = mid + 1; else hi = mid;
+                const uint32_t w0 = reinterpret_cast<const uint32_t*>(&gb_w)[u];
+                int32_t loA = (int32_t)(reinterpret_cast<const uint32_t*>(&sm.gb4[gA])[u] - w0);
+                int32_t loB = (int32_t)(reinterpret_cast<const uint32_t*>(&sm.gb4[gB])[u] - w0);
+                const int32_t endA = (int32_t)(reinterpret_cast<const uint32_t*>(&sm.gb4[gA + 1])[u] - w0);
+                const int32_t endB = (int32_t)(reinterpret_cast<const uint32_t*>(&sm.gb4[gB + 1])[u] - w0);
+                int32_t hiA = endA, hiB = endB;
+                while ((loA < hiA) | (loB < hiB)) {
+                  const int32_t midA = (loA + hiA) >> 1, midB = (loB + hiB) >> 1;
+                  const int32_t dA = ud[(r_cur[u] + midA) & rmask[u]], dB = ud[(r_cur[u] + midB) & rmask[u]];
+                  if (loA < hiA) { if (dA < docA) loA = midA + 1; else hiA = midA; }
+                  if (loB < hiB) { if (dB < docB) loB = midB + 1; else hiB = midB; }
                 }
-                if (lo < end) {
-                  const int uidx = (r_cur[u] + lo) & rmask[u];
-                  if (ud[uidx] == doc) {
-                    if (u < t && ((driver_mask >> u) & 1u)) owner = false;   // counted and emitted by list u's thread
-                    else v |= (uint32_t)sm.pool_f8[rbase[u] + uidx] << (8 * u);
-                  }
+                const int uA = (r_cur[u] + loA) & rmask[u], uB = (r_cur[u] + loB) & rmask[u];
+                const bool lower_driver = u < t && ((driver_mask >> u) & 1u);
+                if (loA < endA && ud[uA] == docA) {
+                  if (lower_driver) ownA = false;   // counted and emitted by list u's thread
+                  else vA |= (uint32_t)sm.pool_f8[rbase[u] + uA] << (8 * u);
+                }
+                if (loB < endB && ud[uB] == docB) {
+                  if (lower_driver) ownB = false;
+                  else vB |= (uint32_t)sm.pool_f8[rbase[u] + uB] << (8 * u);
                 }
               }
-              if (!owner) continue;
-              ++my_hits;
-              const uint32_t ui = __dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u);
-              if (sm.ubt[ui] < theta_s) continue;
-              const uint64_t raw = ((uint64_t)v << 32) | (uint32_t)doc;
-              const int p = atomicAdd(&sm.cand_count, 1);
-              if (p < kCand) sm.cand[p] = raw;
-              else { pending = true; pkey = raw; i += kThreads; break; }
+              if (ownA) {
+                ++my_hits;
+                if (!(sm.ubt[__dp4a(__vminu4(vA, 0x05050505u), 0xD8240601u, 0u)] < theta_s)) push(((uint64_t)vA << 32) | (uint32_t)docA);
+              }
+              if (ownB) {
+                ++my_hits;
+                if (!(sm.ubt[__dp4a(__vminu4(vB, 0x05050505u), 0xD8240601u, 0u)] < theta_s)) push(((uint64_t)vB << 32) | (uint32_t)docB);
+              }
+              if (npend) { i += 2 * kThreads; break; }
             }
             it[t] = i;
           }
@@ -838,6 +870,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
   if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
   for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
   if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
+  if (L.mode_stats && tid == 0) {
+    const int mode = sparse ? 2 : (ne_mask ? 1 : 0);
+    atomicAdd(&L.mode_stats[2 * mode], (unsigned long long)(clock64() - t_start));
+    atomicAdd(&L.mode_stats[2 * mode + 1], 1ull);
+  }
 }
 
 // tbl[slot][tf][norm byte] and ubt[tf pattern] of every query, once per batch (the 20 work items of a query share them)
