@@ -44,6 +44,8 @@ struct DevClause {
   int32_t scoring;    // 1 if the clause contributes to the score (MUST / SHOULD)
   float ub;           // term clauses: largest score of any posting of the list (index-time max of tf*cache[norm])
   int32_t plane;      // term clauses: dense tf plane of the term (DevIndexView::dense_tf), -1 if the term has none
+  int32_t gran_row;   // term clauses: row of the index-time granule offset table (DevIndexView::gran_tab), -1 if none
+  int32_t pad_;
   int64_t lo, hi;
 };
 
@@ -82,6 +84,8 @@ struct DevIndexView {
   const int32_t* const* col32;   // [n_columns] (NULL if stored as int64)
   const uint8_t* const* col_has; // [n_columns] (NULL = all)
   const uint32_t* live_bits;     // bitmap or NULL
+  const uint32_t* gran_tab;      // [n_rows][n_gran + 1] postings of the term below each stream-kernel granule (skip data)
+  int32_t n_gran;
   const uint8_t* dense_tf;       // [n_planes][dense_stride] min(freq, 255) per doc for the densest terms (0 = absent)
   int64_t dense_stride;
 };

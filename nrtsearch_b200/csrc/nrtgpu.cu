@@ -122,6 +122,7 @@ struct nrtgpu_index {
   std::vector<int64_t> term_df;
   std::vector<float> term_max_x;
   std::vector<int32_t> term_plane;   // dense tf plane per term, -1 for all but the densest terms
+  std::vector<int32_t> term_gran;    // row of the granule offset table per term, -1 for short lists
   std::vector<int64_t> field_doc_count, field_sum_ttf;
   std::vector<uint8_t> field_has_norms;
   // device image
@@ -132,6 +133,8 @@ struct nrtgpu_index {
   std::vector<std::unique_ptr<DevBuf<uint8_t>>> norms;
   DevBuf<const uint8_t*> norms_ptrs;
   DevBuf<float> caches;
+  DevBuf<uint32_t> gran_tab;        // [n_rows][n_gran + 1] index-time granule offsets (skip data) of the long lists
+  int32_t gran_n = 0;
   DevBuf<uint8_t> dense_tf;         // [n_planes][dense_stride]: direct-address tf bytes of the densest terms
   int64_t dense_stride = 0;
   int32_t n_planes = 0;
@@ -167,6 +170,7 @@ struct nrtgpu_index {
     v.col64 = col64_ptrs.p; v.col32 = col32_ptrs.p; v.col_has = col_has_ptrs.p;
     v.live_bits = live_bits.p;
     v.dense_tf = dense_tf.p; v.dense_stride = dense_stride;
+    v.gran_tab = gran_tab.p; v.n_gran = gran_n;
     return v;
   }
 };
@@ -320,6 +324,32 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       NRT_CUDA_TRY(cudaGetLastError());
     }
   }
+  // skip data: posting offsets at every stream-kernel granule boundary for the lists long enough to make the
+  // per-batch lower_bound searches expensive (>= 4096 postings); a batch then copies the row instead of searching
+  ix->term_gran.assign((size_t)d->n_terms, -1);
+  {
+    const int32_t n_gran = std::max<int32_t>(1, (int32_t)(((int64_t)d->n_docs + v2::kGran - 1) / v2::kGran));
+    std::vector<int64_t> row_off; std::vector<int32_t> row_n;
+    const size_t max_rows = (size_t)((2ll << 30) / ((int64_t)(n_gran + 1) * 4));
+    for (int32_t t = 0; t < d->n_terms && row_off.size() < max_rows; ++t) {
+      const int64_t n = d->term_off[t + 1] - d->term_off[t];
+      if (n >= 4096) { ix->term_gran[(size_t)t] = (int32_t)row_off.size(); row_off.push_back(d->term_off[t]); row_n.push_back((int32_t)n); }
+    }
+    ix->gran_n = n_gran;
+    if (!row_off.empty()) {
+      DevBuf<int64_t> d_ro; DevBuf<int32_t> d_rn;
+      if ((rc = d_ro.upload(row_off.data(), row_off.size()))) return rc;
+      if ((rc = d_rn.upload(row_n.data(), row_n.size()))) return rc;
+      const int64_t total = (int64_t)row_off.size() * (n_gran + 1);
+      if ((rc = ix->gran_tab.alloc((size_t)total))) return rc;
+      v2::GranTabLaunch G;
+      G.post_docs = ix->post_docs.p; G.row_off = d_ro.p; G.row_n = d_rn.p; G.n_rows = (int32_t)row_off.size();
+      G.n_gran = n_gran; G.n_docs = d->n_docs; G.tab = ix->gran_tab.p;
+      v2::gran_table_kernel<<<(unsigned)((total + 255) / 256), 256>>>(G);
+      NRT_CUDA_TRY(cudaGetLastError());
+      NRT_CUDA_TRY(cudaDeviceSynchronize());
+    }
+  }
   // norms + BM25 caches
   {
     std::vector<const uint8_t*> ptrs((size_t)d->n_fields, nullptr);
@@ -414,7 +444,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       ix->vec_tc = true;
     }
   }
-  ix->device_bytes = (int64_t)(ix->dense_tf.bytes() + ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
+  ix->device_bytes = (int64_t)(ix->gran_tab.bytes() + ix->dense_tf.bytes() + ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
                                ix->caches.bytes() + ix->live_bits.bytes() + ix->vectors.bytes() + ix->vec_norm2.bytes() +
                                ix->vec_docs.bytes() + ix->vec_bf16.bytes());
   for (auto& b : ix->norms) ix->device_bytes += (int64_t)b->bytes();
@@ -479,7 +509,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
       if (c.occur < NRTGPU_SHOULD || c.occur > NRTGPU_MUST_NOT) NRT_FAIL(NRTGPU_ERR_INVALID, "bad occur");
       if (c.boost < 0.0f) NRT_FAIL(NRTGPU_ERR_INVALID, "Boost must be a positive number");  // QueryNodeMapper.java:127
       DevClause x; std::memset(&x, 0, sizeof(x));
-      x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.plane = -1; x.lo = c.lo; x.hi = c.hi;
+      x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.plane = -1; x.gran_row = -1; x.lo = c.lo; x.hi = c.hi;
       x.scoring = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_SHOULD) ? 1 : 0;
       bool required = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER);
       if (c.kind == NRTGPU_TERM) {
@@ -488,7 +518,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
         int f = ix->term_field[c.id];
         x.post_base = ix->term_off[c.id];
         x.n_post = (int32_t)(ix->term_off[c.id + 1] - ix->term_off[c.id]);
-        x.slot = n_term; x.field = f; x.plane = ix->term_plane[c.id];
+        x.slot = n_term; x.field = f; x.plane = ix->term_plane[c.id]; x.gran_row = ix->term_gran[c.id];
         int64_t df = ix->term_df[c.id];
         // BM25Scorer: weight = boost * idf
         x.weight = c.boost * bm25_idf(df > 0 ? df : 1, ix->field_doc_count[f]);

@@ -944,6 +944,7 @@ __global__ void granule_bounds_kernel(BoundsLaunch B) {
   for (int c = 0; c < dq.n_clauses; ++c) {
     const DevClause cl = B.clauses[dq.clause_begin + c];
     if (cl.kind != NRTGPU_TERM || cl.slot != s) continue;
+    if (cl.gran_row >= 0) { out = __ldg(B.ix.gran_tab + (size_t)cl.gran_row * (B.n_gran + 1) + g); break; }   // index-time skip data
     const int64_t target64 = (int64_t)g << kLogGran;
     const int32_t target = target64 > (int64_t)B.ix.n_docs ? B.ix.n_docs : (int32_t)target64;
     const int32_t* docs = B.ix.post_docs + cl.post_base;
@@ -952,6 +953,27 @@ __global__ void granule_bounds_kernel(BoundsLaunch B) {
     out = (uint32_t)lo;
   }
   B.gbounds[i] = out;
+}
+
+// index-time skip data: for every term with a long list, the number of its postings below each granule boundary
+struct GranTabLaunch {
+  const int32_t* post_docs;
+  const int64_t* row_off;   // [n_rows] first posting of the row's term
+  const int32_t* row_n;     // [n_rows] postings of the row's term
+  int32_t n_rows, n_gran, n_docs;
+  uint32_t* tab;            // [n_rows][n_gran + 1]
+};
+
+__global__ void gran_table_kernel(GranTabLaunch G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)G.n_rows * (G.n_gran + 1)) return;
+  const int r = (int)(i / (G.n_gran + 1)), g = (int)(i % (G.n_gran + 1));
+  const int64_t target64 = (int64_t)g << kLogGran;
+  const int32_t target = target64 > (int64_t)G.n_docs ? G.n_docs : (int32_t)target64;
+  const int32_t* docs = G.post_docs + G.row_off[r];
+  int lo = 0, hi = G.row_n[r];
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(docs + mid) < target) lo = mid + 1; else hi = mid; }
+  G.tab[i] = (uint32_t)lo;
 }
 
 }  // namespace v2
