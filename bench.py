@@ -497,11 +497,11 @@ def main():
             "config": workload_config(args),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": stats["launches_per_run"] * args.steps + (args.steps if world > 1 else 0),
-            "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel (TMA-streamed posting traversal + BM25 + exact top-k)",
+            "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel<simple> (TMA-streamed posting traversal: window scatter / tf-plane / sparse merge modes + BM25 + exact top-k)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
                          "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world,
-                         "mode": "TOP_SCORES (totalHitsThreshold %d: MAXSCORE may stop lists from driving)" % args.threshold
+                         "mode": "TOP_SCORES (totalHitsThreshold %d, the reference default: once a query has that many hits, lists whose score bounds sum below theta stop driving and are only looked up -- MAXSCORE, as Lucene does; achieved/frac here divide the ALGORITHMIC bytes of every posting of the batch by the kernel time, the every-posting-swept figure is under exhaustive)" % args.threshold
                                  if args.threshold != 2**31 - 1 else "COMPLETE (every posting swept)",
                          "exhaustive": None if exh_ms is None else
                                        {"kernel_ms": exh_ms, "achieved": alg_bytes / (exh_ms * 1e-3) / 1e9,

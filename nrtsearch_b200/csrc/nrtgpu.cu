@@ -676,8 +676,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       S.threshold = b->threshold; S.pruned = b->pruned.p;
       S.mode_stats = nullptr;
       if (getenv("NRTGPU_DEBUG_MODES")) {
-        if (!b->mode_stats.p && b->mode_stats.alloc(6)) return NRTGPU_ERR_CUDA;
-        NRT_CUDA_TRY(cudaMemsetAsync(b->mode_stats.p, 0, 6 * sizeof(unsigned long long), st));
+        if (!b->mode_stats.p && b->mode_stats.alloc(13)) return NRTGPU_ERR_CUDA;
+        NRT_CUDA_TRY(cudaMemsetAsync(b->mode_stats.p, 0, 13 * sizeof(unsigned long long), st));
         S.mode_stats = b->mode_stats.p;
       }
       S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
@@ -696,11 +696,12 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   }
   NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
   if (b->mode_stats.p && getenv("NRTGPU_DEBUG_MODES")) {
-    unsigned long long h[6];
+    unsigned long long h[13];
     NRT_CUDA_TRY(cudaMemcpyAsync(h, b->mode_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     NRT_CUDA_TRY(cudaStreamSynchronize(st));
-    fprintf(stderr, "[nrtgpu modes] window: %llu items %.0f cyc/item | window+maxscore: %llu items %.0f | sparse: %llu items %.0f\n",
-            h[1], h[1] ? (double)h[0] / h[1] : 0.0, h[3], h[3] ? (double)h[2] / h[3] : 0.0, h[5], h[5] ? (double)h[4] / h[5] : 0.0);
+    fprintf(stderr, "[nrtgpu modes] window: %llu items %.0f cyc/item %llu driver postings | window+maxscore: %llu items %.0f %llu | sparse: %llu items %.0f %llu\n",
+            h[1], h[1] ? (double)h[0] / h[1] : 0.0, h[6], h[3], h[3] ? (double)h[2] / h[3] : 0.0, h[7], h[5], h[5] ? (double)h[4] / h[5] : 0.0, h[8]);
+    if (h[5]) fprintf(stderr, "[nrtgpu modes] sparse items: set-up %.0f cyc, sweep %.0f, flush+output %.0f, %.2f runs/item\n", (double)h[9] / h[5], (double)h[10] / h[5], (double)h[11] / h[5], (double)h[12] / h[5]);
   }
   MergeLaunch M;
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;

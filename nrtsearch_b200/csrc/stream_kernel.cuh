@@ -560,6 +560,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     issue_plane(0, g0, ga);
     if (ga < g_count) issue_plane(1, ga, sm.nextg[ga]);
   }
+  unsigned long long dbg_postings = 0;   // driver postings visited (NRTGPU_DEBUG_MODES)
+  const long long t_loop = L.mode_stats ? clock64() : 0ll;
+  unsigned long long dbg_windows = 0;
   int wn = 0;   // window counter (skipped windows count too: each has its plane copy)
   while (g0 < g_count) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
@@ -625,6 +628,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
       }
     }
 
+    if (L.mode_stats) {
+      ++dbg_windows;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) if ((driver_mask >> t) & 1u) dbg_postings += (unsigned long long)cnt[t];
+    }
     // the window's postings are dealt round-robin over the threads ACROSS the clauses (clause t starts where
     // clause t-1 stopped), so short lists do not pile onto the first warps
     int32_t rot[kT];
@@ -860,6 +868,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     next_plane();
   }
 
+  const long long t_flush = L.mode_stats ? clock64() : 0ll;
   // ---------------- finish the work item: the slice merge sorts, so only a full buffer needs ordering here
   __syncthreads();
   if (simple ? sm.cand_count > sm.n_keys : sm.cand_count > L.top_k)
@@ -874,6 +883,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(St
     const int mode = sparse ? 2 : (ne_mask ? 1 : 0);
     atomicAdd(&L.mode_stats[2 * mode], (unsigned long long)(clock64() - t_start));
     atomicAdd(&L.mode_stats[2 * mode + 1], 1ull);
+    atomicAdd(&L.mode_stats[6 + mode], dbg_postings);
+    if (mode == 2) {
+      atomicAdd(&L.mode_stats[9], (unsigned long long)(t_loop - t_start));
+      atomicAdd(&L.mode_stats[10], (unsigned long long)(t_flush - t_loop));
+      atomicAdd(&L.mode_stats[11], (unsigned long long)(clock64() - t_flush));
+      atomicAdd(&L.mode_stats[12], dbg_windows);
+    }
   }
 }
 

@@ -228,3 +228,36 @@ def test_top_scores_mode_skips_lists_but_keeps_topk(gpu_ctx):
     assert np.array_equal(res.total_hits[eq], want[3][eq])
     assert (res.total_hits[~eq] <= want[3][~eq]).all() and (res.total_hits[~eq] > 1000).all()
     assert (~eq).any(), "expected at least one query to skip a non-essential list"
+
+
+def test_top_scores_mixed_term_counts_and_search_after(gpu_ctx):
+    """TOP_SCORES mode over 1..4-term disjunctions of dense (plane-served), medium and rare terms: window mode, tf-plane
+    mode and sparse (binary-search merge) mode all appear inside one batch; paging with searchAfter on top. The
+    (doc, score) lists must equal the exhaustive oracle bit for bit."""
+    sh = ix.synth_text_shard(1_300_000, 30_000, min_len=4, poisson_mean=14.0)   # 3 slices of 524,288 docs
+    rng = np.random.default_rng(5)
+    qs = []
+    for n_terms in (1, 2, 3, 4):
+        for _ in range(96):   # 386 queries x 3 slices > the 296 CTAs resident at once: later work items see a warm theta
+            ranks = np.unique(np.floor(10 ** rng.uniform(0.0, 4.2, size=n_terms)).astype(np.int64).clip(1, 29_999))
+            qs.append(disj(ranks))
+    qs.append(disj([1, 2, 3]))          # three very dense lists
+    qs.append(disj([1, 20_000, 25_000]))  # one dense + two rare lists
+    gix = GpuIndex(gpu_ctx, sh)
+    s = GpuIndexSearcher(gix)
+    res = s.search_batch(qs, RelevanceCollector(50, 200))
+    carr, ncl, qarr, nq = compile_queries(qs)
+    want = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, nq, 50)
+    got = (res.docs, res.scores, res.counts, res.total_hits, res.relation)
+    assert_same_hits(got, want, check_total=False, what="TOP_SCORES mixed")
+    assert (res.relation != 0).any()
+    # second page after the 50th hit of every query that has one
+    after = [ScoreDoc(int(res.docs[q, res.counts[q] - 1]), float(res.scores[q, res.counts[q] - 1])) if res.counts[q] == 50 else None
+             for q in range(len(qs))]
+    sel = [q for q in range(len(qs)) if after[q] is not None]
+    res2 = s.search_batch([qs[q] for q in sel], RelevanceCollector(50, 200), search_after=[after[q] for q in sel])
+    gix.close()
+    carr, ncl, qarr, nq = compile_queries([qs[q] for q in sel], [after[q] for q in sel])
+    want2 = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, nq, 50)
+    got2 = (res2.docs, res2.scores, res2.counts, res2.total_hits, res2.relation)
+    assert_same_hits(got2, want2, check_total=False, what="TOP_SCORES mixed page 2")
