@@ -240,7 +240,24 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
   if (i < n) p[i] = v;
 }
 
-struct CudaFreeGuard { void* p; ~CudaFreeGuard() { if (p) cudaFree(p); } };
+// device scratch of one kNN call: slots grow on demand and are kept between calls (no cudaMalloc / cudaFree, which
+// synchronise the device, on the request path). The index owns one and serialises the calls that use it.
+struct KnnScratch {
+  static constexpr int kSlots = 16;
+  void* p[kSlots] = {};
+  size_t cap[kSlots] = {};
+  ~KnnScratch() { for (auto q : p) if (q) cudaFree(q); }
+  int get(int i, size_t bytes, void** out) {
+    if (bytes > cap[i]) {
+      if (p[i]) { cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+      NRT_CUDA_TRY(cudaMalloc(&p[i], bytes));
+      cap[i] = bytes;
+    }
+    *out = p[i];
+    return 0;
+  }
+};
+#define NRT_KNN_GET(slot, ptr, bytes) do { int rc_ = sc->get((slot), (bytes), (void**)&(ptr)); if (rc_) return rc_; } while (0)
 
 // d_vec_bf16 / tm_corpus: bf16 copy of the corpus and its TMA tensor map (NULL => SIMT fp32 candidate stage).
 // stage_ms (optional): [0] = candidate GEMM kernels, [1] = select kernels, [2] = exact re-score (CUDA events on st).
@@ -248,7 +265,10 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
                            int doc_base, int n_docs, const float* h_queries, int nq, int k, const float* h_boosts,
                            const uint8_t* h_filter, cudaStream_t st, int32_t* out_docs, float* out_scores,
                            int32_t* out_counts, const __nv_bfloat16* d_vec_bf16 = nullptr,
-                           const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr, const float2* d_ab = nullptr) {
+                           const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr, const float2* d_ab = nullptr,
+                           KnnScratch* sc = nullptr) {
+  KnnScratch local_scratch;   // only when the caller brings none (freed on return)
+  if (!sc) sc = &local_scratch;
   const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr && d_ab != nullptr;
   int kprime = use_tc ? (4 * k < 128 ? 128 : 4 * k) : (2 * k < 64 ? 64 : 2 * k);
   if (kprime > kKnnCandCap - kKnnSelThreads) kprime = kKnnCandCap - kKnnSelThreads;
@@ -258,37 +278,34 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   uint64_t* dC = nullptr; int32_t *dCn = nullptr, *dOD = nullptr, *dOC = nullptr;
   const int chunk_max = use_tc ? 65536 : kKnnChunk;
   float* dTheta = nullptr; uint64_t* dCC = nullptr; int *dCCn = nullptr, *dOvf = nullptr;
-  CudaFreeGuard g11{nullptr}, g12{nullptr}, g13{nullptr}, g14{nullptr};
   if (fused) {
-    NRT_CUDA_TRY(cudaMalloc((void**)&dTheta, (size_t)nq * sizeof(float))); g11.p = dTheta;
-    NRT_CUDA_TRY(cudaMalloc((void**)&dCC, (size_t)nq * cc_cap * sizeof(uint64_t))); g12.p = dCC;
-    NRT_CUDA_TRY(cudaMalloc((void**)&dCCn, (size_t)nq * sizeof(int))); g13.p = dCCn;
-    NRT_CUDA_TRY(cudaMalloc((void**)&dOvf, sizeof(int))); g14.p = dOvf;
+    NRT_KNN_GET(0, dTheta, (size_t)nq * sizeof(float));
+    NRT_KNN_GET(1, dCC, (size_t)nq * cc_cap * sizeof(uint64_t));
+    NRT_KNN_GET(2, dCCn, (size_t)nq * sizeof(int));
+    NRT_KNN_GET(3, dOvf, sizeof(int));
     NRT_CUDA_TRY(cudaMemsetAsync(dCCn, 0, (size_t)nq * sizeof(int), st));
     NRT_CUDA_TRY(cudaMemsetAsync(dOvf, 0, sizeof(int), st));
     fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(dTheta, nq, -INFINITY);
   }
   int chunk = n < chunk_max ? n : chunk_max;
   chunk = (chunk + 3) & ~3;   // keep score rows 16-byte aligned
-  NRT_CUDA_TRY(cudaMalloc((void**)&dQ, (size_t)nq * dims * sizeof(float))); CudaFreeGuard g1{dQ};
-  if (!fused) NRT_CUDA_TRY(cudaMalloc((void**)&dS, (size_t)nq * chunk * sizeof(float)));
-  CudaFreeGuard g2{dS};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dC, (size_t)nq * kprime * sizeof(uint64_t))); CudaFreeGuard g3{dC};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dCn, (size_t)nq * sizeof(int32_t))); CudaFreeGuard g4{dCn};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dOD, (size_t)nq * k * sizeof(int32_t))); CudaFreeGuard g5{dOD};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dOS, (size_t)nq * k * sizeof(float))); CudaFreeGuard g6{dOS};
-  NRT_CUDA_TRY(cudaMalloc((void**)&dOC, (size_t)nq * sizeof(int32_t))); CudaFreeGuard g7{dOC};
-  CudaFreeGuard g8{nullptr}, g9{nullptr};
-  if (h_boosts) { NRT_CUDA_TRY(cudaMalloc((void**)&dB, (size_t)nq * sizeof(float))); g8.p = dB;
+  NRT_KNN_GET(4, dQ, (size_t)nq * dims * sizeof(float));
+  if (!fused) NRT_KNN_GET(5, dS, (size_t)nq * chunk * sizeof(float));
+  NRT_KNN_GET(6, dC, (size_t)nq * kprime * sizeof(uint64_t));
+  NRT_KNN_GET(7, dCn, (size_t)nq * sizeof(int32_t));
+  NRT_KNN_GET(8, dOD, (size_t)nq * k * sizeof(int32_t));
+  NRT_KNN_GET(9, dOS, (size_t)nq * k * sizeof(float));
+  NRT_KNN_GET(10, dOC, (size_t)nq * sizeof(int32_t));
+  if (h_boosts) { NRT_KNN_GET(11, dB, (size_t)nq * sizeof(float));
                   NRT_CUDA_TRY(cudaMemcpyAsync(dB, h_boosts, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st)); }
-  if (h_filter) { NRT_CUDA_TRY(cudaMalloc((void**)&dF, (size_t)n_docs)); g9.p = dF;
+  if (h_filter) { NRT_KNN_GET(12, dF, (size_t)n_docs);
                   NRT_CUDA_TRY(cudaMemcpyAsync(dF, h_filter, (size_t)n_docs, cudaMemcpyHostToDevice, st)); }
   NRT_CUDA_TRY(cudaMemcpyAsync(dQ, h_queries, (size_t)nq * dims * sizeof(float), cudaMemcpyHostToDevice, st));
   NRT_CUDA_TRY(cudaMemsetAsync(dCn, 0, (size_t)nq * sizeof(int32_t), st));
-  __nv_bfloat16* dQb = nullptr; CudaFreeGuard g10{nullptr};
+  __nv_bfloat16* dQb = nullptr;
   CUtensorMap tmQ;
   if (use_tc) {
-    NRT_CUDA_TRY(cudaMalloc((void**)&dQb, (size_t)nq * dims * sizeof(__nv_bfloat16))); g10.p = dQb;
+    NRT_KNN_GET(13, dQb, (size_t)nq * dims * sizeof(__nv_bfloat16));
     tc::f32_to_bf16_kernel<<<256, 256, 0, st>>>(dQ, dQb, (size_t)nq * dims);
     NRT_CUDA_TRY(cudaGetLastError());
     int rc = tc::make_tensor_map_bf16(&tmQ, dQb, (uint64_t)nq, (uint64_t)dims, tc::BM);
@@ -350,7 +367,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     if (ovf) {
       if (stage_ms) for (auto& e : ev) cudaEventDestroy(e);
       return knn_search_host(d_vec, d_norm2, d_vec_docs, n, dims, sim, doc_base, n_docs, h_queries, nq, k, h_boosts, h_filter, st,
-                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms);
+                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms, nullptr, sc);
     }
   }
   if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
