@@ -309,7 +309,7 @@ __device__ __forceinline__ void compact_candidates_v2(const StreamLaunch& L, Str
 // (the host splits the work list): only that instantiation carries the tf-pattern bound, deferred scoring, MAXSCORE,
 // tf planes and the sparse mode; the other one carries the generic clause evaluation.
 template <bool kSimple>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(StreamLaunch L) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(const __grid_constant__ StreamLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>(smem_raw);
   const int tid = threadIdx.x;
