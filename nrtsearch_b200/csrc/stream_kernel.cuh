@@ -108,6 +108,7 @@ struct alignas(128) StreamSmem {
   uint32_t s_scoring[kT];
   const uint8_t* s_plane[kT];       // dense tf plane of the slot's term (NULL: none)
   int cand_count;
+  unsigned long long hits0;         // the query's hit count when the work item started
   int n_keys;                       // entries [0, n_keys) of cand are keys kept by the last flush
   uint32_t ne_mask;                 // non-essential slots of this work item (MAXSCORE)
   int plane_slot;                   // non-essential slot served from its dense tf plane (-1: none)
@@ -320,6 +321,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   const int slice = L.work_slice[wi];
   const long long t_start = L.mode_stats ? clock64() : 0ll;
 
+  // every thread reads the three query fields the loads below depend on straight from global memory (one broadcast
+  // transaction per warp), so the clause / granule-bound loads do not wait for thread 0's part of the set-up
+  const int ncl = L.queries[qi].n_clauses, cbeg = L.queries[qi].clause_begin, n_term = L.queries[qi].n_term;
+  if (tid == 32) sm.hits0 = *(volatile unsigned long long*)&L.total_hits[qi];
   if (tid == 0) {
     sm.q = L.queries[qi];
     sm.cand_count = 0;
@@ -339,11 +344,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
     mbar_arrive_expect_tx(&sm.tab_bar, kBytes);
     for (uint32_t o = 0; o < kBytes; o += 4096u) bulk_g2s(dst + o, src + o, min(4096u, kBytes - o), &sm.tab_bar);
   }
-  __syncthreads();
-  const int ncl = sm.q.n_clauses;
-  if (tid < ncl) sm.cl[tid] = L.clauses[sm.q.clause_begin + tid];
+  if (tid < ncl) sm.cl[tid] = L.clauses[cbeg + tid];
   for (int i = tid; i < kW / 4; i += kThreads) reinterpret_cast<uint4*>(sm.slots)[i] = make_uint4(0u, 0u, 0u, 0u);
-  const int n_term = sm.q.n_term;
   // granule bounds of the slice (every list; lists served from their plane get their column cleared below)
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
     const DevQuery& q = sm.q;
     const bool simple_q = kSimple;
     if (simple_q && sm.theta != 0ull && L.threshold < (int64_t)INT32_MAX &&
-        (int64_t)*(volatile unsigned long long*)&L.total_hits[qi] > L.threshold) {
+        (int64_t)sm.hits0 > L.threshold) {
       const float theta_s = key_score(sm.theta);
       float ub[kT]; int ord[kT]; int n = 0;
       for (int i = 0; i < q.n_clauses; ++i)
