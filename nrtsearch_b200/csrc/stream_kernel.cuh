@@ -1,19 +1,22 @@
-// posting_stream_kernel -- streaming version of the batched BooleanQuery engine (<= 4 term clauses per query).
+// posting_stream_kernel -- the batched BooleanQuery engine for queries of <= 4 term clauses.
 //
-// Same algorithm as bool_window_kernel (scatter tf bytes -> owner emits -> exact top-k, see
-// bool_kernel.cuh) but built so that the per-posting instruction count is small:
+// One work item = (query, 524,288-doc slice). Everything a work item reads arrives by TMA or is index-time data:
 //   * posting lists are STREAMED through per-clause rings in shared memory filled by 1-D TMA bulk copies
-//     (cp.async.bulk.shared.global + mbarrier complete_tx, SASS UBLKCP) issued by one elected thread;
-//   * window boundaries come from per-batch granule bounds (granule_bounds_kernel: one lower_bound per
-//     (query, clause, 2048-doc granule)), so the sweep never searches posting data;
-//   * term scores for tf <= kTfTab are read from a per-CTA table tbl[clause][tf][norm] of exact BM25
-//     floats (Lucene's formula evaluated once per work item): no IEEE division per posting;
-//   * for pure disjunctions an upper-bound table ubt[tf pattern] rejects, with one shared-memory load,
-//     every doc whose best possible score is below the running threshold theta (rank-safe: the bound is
-//     the same float expression evaluated at the shortest field length present in the index);
-//   * pass 2 has no barrier inside: a thread whose candidate does not fit the buffer parks it, the CTA
-//     compacts once, and parked threads resume.
-// Results are bit-identical to the exhaustive oracle; totalHits stay exact (every owner is counted).
+//     (cp.async.bulk.shared.global + mbarrier complete_tx, SASS UBLKCP) issued by the lanes of warp 0;
+//   * run boundaries come from granule bounds (postings of every list below each 1024-doc granule: index-time skip
+//     data for long lists, one lower_bound per granule for short ones), so the sweep never searches to find them;
+//   * exact BM25 floats tbl[slot][tf][norm] and the tf-pattern bound ubt[] are computed once per batch and query
+//     (query_tables_kernel) and pulled in with one TMA copy: no IEEE division per posting;
+//   * for pure disjunctions ubt[] rejects, with one shared-memory load, every doc whose best possible score is below
+//     the running threshold theta (rank-safe: the bound is the same float expression at the shortest field length
+//     present in the index); survivors are appended unscored and scored together at the buffer flush;
+//   * no barrier inside a pass: a thread whose candidate does not fit the buffer parks it, the CTA flushes once, and
+//     parked threads resume.
+// Three sweep modes per work item: window (scatter tf bytes into an 8K-doc word array -> owners emit), tf-plane (a
+// dense non-essential list is a TMA copy of its direct-address bytes instead of a scatter) and sparse (short lists
+// merged by granule-narrowed binary search of each other's ring segments, plane bytes gathered from L2).
+// Results are bit-identical to the exhaustive oracle; totalHits are exact until MAXSCORE prunes (then a lower bound
+// with relation GREATER_THAN_OR_EQUAL_TO, as in the reference).
 #pragma once
 #include <cstddef>
 #include "bool_kernel.cuh"
