@@ -68,6 +68,12 @@ constexpr int kSparseCap = NRT_SPARSE_CAP;   // (measured with granule-narrowed 
 #define NRT_SPARSE_CAP_ALL 32768
 #endif
 constexpr int kSparseCapAll = NRT_SPARSE_CAP_ALL;          // ... when every list drives (no pruning): each posting pays the searches   // a list with at most this many postings in the slice can be merged by binary search
+// sparse mode: doc chunks = pool_docs + the first kSparseExtra chunks' worth of the window array; their tf bytes = the rest
+// of the window array + pool_f8
+constexpr int kSparseExtra = (kW * 4) / (kCH * 4 + kCH) < 14 ? (kW * 4) / (kCH * 4 + kCH) : 14;
+constexpr int kPoolSparse = kPool + kSparseExtra;
+constexpr int kSparseF8Off = kSparseExtra * kCH * 4;   // byte offset of the sparse tf region inside the window array
+static_assert(kW * 4 - kSparseF8Off + kPool * kCH >= kPoolSparse * kCH, "sparse tf chunks must fit behind the extra doc chunks");
 constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
@@ -91,13 +97,16 @@ struct StreamLaunch {
 };
 
 struct alignas(128) StreamSmem {
-  int32_t pool_docs[kPool * kCH];        // 80 KB  ring pool (TMA destinations: 2 KB aligned chunks)
-  uint8_t pool_f8[kPool * kCH];          // 20 KB
-  uint32_t slots[kW];                    // 64 KB
+  // ring pool (TMA destinations: 2 KB aligned doc chunks, 512 B tf chunks). Sparse mode has no window array and
+  // extends the pool over it: doc chunks run on from pool_docs into slots, tf chunks start inside slots and run on
+  // into pool_f8 -- the three arrays must stay in this order.
+  int32_t pool_docs[kPool * kCH];
+  uint32_t slots[kW];                    // window array: one 32-bit word (four tf bytes) per doc
+  uint8_t pool_f8[kPool * kCH];
   uint64_t cand[kCand];                  // 16 KB
   float tbl[kT][kTfTab + 1][256];        // exact BM25 floats per (slot, tf, norm byte); row tf = 0 is +0.0f
   float ubt[kUbt];                       // score bound per tf pattern (directly after tbl: one TMA copy fills both)
-  uint64_t full_bar[kPool];
+  uint64_t full_bar[kPoolSparse];
   uint4 gb4[kSliceDocs / kGran + 1];      // 8 KB granule bounds of this slice, one 16-byte row {slot 0..3} per granule
   uint16_t nextg[kSliceDocs / kGran + 2]; // 1 KB window table: the window that starts at granule g ends at nextg[g]
   DevClause cl[kMaxClauses];
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
     sm.cand_count = 0;
     sm.n_keys = 0;
     sm.theta = *(volatile unsigned long long*)&L.theta[qi];
-    for (int j = 0; j < kPool; ++j) mbar_init(&sm.full_bar[j], 1);
+    for (int j = 0; j < kPoolSparse; ++j) mbar_init(&sm.full_bar[j], 1);
     mbar_init(&sm.plane_bar[0], 1);
     mbar_init(&sm.plane_bar[1], 1);
     mbar_init(&sm.tab_bar, 1);
@@ -453,7 +462,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
     // list if shorter); the list with the most chunks still to stream per ring chunk is doubled while
     // the pool allows (dense lists get long rings = deep TMA prefetch)
     int nch[kT], used = 0;
-    const int pool_lim = pslot >= 0 ? kPool - kPlaneChunks : kPool;   // the tail of the pool holds the plane buffers
+    // (window mode with a plane: the tail of the pool holds the plane buffers; sparse mode: the pool runs on over the window array)
+    const int pool_lim = sparse ? kPoolSparse : (pslot >= 0 ? kPool - kPlaneChunks : kPool);
     for (int t = 0; t < kT; ++t) {
       nch[t] = 0;
       if (t < n_term && t != pslot && !((pserve_mask >> t) & 1u)) { nch[t] = 2; while (nch[t] < kMinNCH && nch[t] < sm.s_n_chunks[t] + 1) nch[t] *= 2; }
@@ -474,6 +484,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   }
   __syncthreads();
 
+  // tf bytes of ring chunk s live at pf8 + s * kCH
+  uint8_t* const pf8 = sparse ? reinterpret_cast<uint8_t*>(sm.slots) + kSparseF8Off : sm.pool_f8;
+  static_assert(offsetof(StreamSmem, slots) == offsetof(StreamSmem, pool_docs) + sizeof(int32_t) * kPool * kCH &&
+                offsetof(StreamSmem, pool_f8) == offsetof(StreamSmem, slots) + sizeof(uint32_t) * kW, "pool_docs / slots / pool_f8 contiguous");
   // ---- CTA-uniform per-slot registers
   int32_t r_cur[kT], rbase[kT], rmask[kT], issued[kT], waited[kT];
 #pragma unroll
@@ -514,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
         uint64_t* bar = &sm.full_bar[slot];
         mbar_arrive_expect_tx(bar, kChunkBytes);
         bulk_g2s(&sm.pool_docs[slot << kLogCH], sm.s_gdocs[t] + ((size_t)j << kLogCH), kCH * 4, bar);
-        bulk_g2s(&sm.pool_f8[slot << kLogCH], sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
+        bulk_g2s(pf8 + (slot << kLogCH), sm.s_gf8[t] + ((size_t)j << kLogCH), kCH, bar);
       }
       issued[t] = max(issued[t], lim);
     }
@@ -674,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
             if (t >= n_term || npend) break;
             if (!((driver_mask >> t) & 1u)) continue;
             const int32_t* rd = sm.pool_docs + rbase[t];
-            const uint8_t* rf = sm.pool_f8 + rbase[t];
+            const uint8_t* rf = pf8 + rbase[t];
             int32_t i = it[t];
 #pragma unroll 1
             for (; i < cnt[t]; i += 2 * kThreads) {
@@ -711,11 +725,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
                 const bool lower_driver = u < t && ((driver_mask >> u) & 1u);
                 if (loA < endA && ud[uA] == docA) {
                   if (lower_driver) ownA = false;   // counted and emitted by list u's thread
-                  else vA |= (uint32_t)sm.pool_f8[rbase[u] + uA] << (8 * u);
+                  else vA |= (uint32_t)pf8[rbase[u] + uA] << (8 * u);
                 }
                 if (loB < endB && ud[uB] == docB) {
                   if (lower_driver) ownB = false;
-                  else vB |= (uint32_t)sm.pool_f8[rbase[u] + uB] << (8 * u);
+                  else vB |= (uint32_t)pf8[rbase[u] + uB] << (8 * u);
                 }
               }
               if (ownA) {
