@@ -182,6 +182,7 @@ static void free_batch(nrtgpu_batch* b);
 struct nrtgpu_batch {
   nrtgpu_index* ix = nullptr;
   int32_t nq = 0, top_k = 0, n_slices = 0, n_work = 0;
+  int32_t n_lists = 0;         // per-query candidate lists the kernels fill: n_slices (+1: warm-up items of the stream path)
   int32_t n_work_simple = 0;   // the first n_work_simple work items belong to pure single-field term disjunctions
   bool wide_slots = false;
   bool exhaustive = true;
@@ -598,9 +599,26 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
            o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
   };
   std::vector<int32_t> wq, ws;
+  // warm-up items (stream path, TOP_SCORES mode, large shards): a query with a dense list first sweeps the leading
+  // kWarmGran granules of slice 0 as a work item of its own, ahead of everything else, so that its other work items
+  // start with a threshold and a hit count (MAXSCORE can prune from the first slice on)
+  const bool warm_ok = !b->wide_slots && b->threshold < (int64_t)INT32_MAX &&
+                       (int64_t)ix->n_docs >= 8ll * v2::kWarmGran * v2::kGran;
+  std::vector<uint8_t> has_warm((size_t)nq, 0);
+  if (warm_ok) {
+    for (int qi : order) {
+      if (!is_simple(qi)) continue;
+      for (int c = 0; c < dq[qi].n_clauses; ++c) {
+        const DevClause& x = dc[(size_t)dq[qi].clause_begin + c];
+        if (x.kind == NRTGPU_TERM && (int64_t)x.n_post * 64 >= (int64_t)ix->n_docs) has_warm[(size_t)qi] = 1;
+      }
+      if (has_warm[(size_t)qi]) { wq.push_back(qi); ws.push_back(0 | (1 << 24)); }
+    }
+  }
+  b->n_lists = b->n_slices + (warm_ok ? 1 : 0);
   for (int pass = 0; pass < 2; ++pass) {
     for (int s = 0; s < b->n_slices; ++s)
-      for (int qi : order) if (is_simple(qi) == (pass == 0)) { wq.push_back(qi); ws.push_back(s); }
+      for (int qi : order) if (is_simple(qi) == (pass == 0)) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
     if (pass == 0) b->n_work_simple = (int32_t)wq.size();
   }
   b->n_work = (int32_t)wq.size();
@@ -612,8 +630,8 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   NRT_CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
   if ((rc = b->theta.alloc((size_t)nq))) return rc;
   if ((rc = b->total_hits.alloc((size_t)nq))) return rc;
-  if ((rc = b->slice_keys.alloc((size_t)nq * b->n_slices * top_k))) return rc;
-  if ((rc = b->slice_cnt.alloc((size_t)nq * b->n_slices))) return rc;
+  if ((rc = b->slice_keys.alloc((size_t)nq * b->n_lists * top_k))) return rc;
+  if ((rc = b->slice_cnt.alloc((size_t)nq * b->n_lists))) return rc;
   if ((rc = b->out_docs.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
@@ -667,7 +685,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     L.ix = b->ix->view();
     L.clauses = b->clauses.p; L.queries = b->queries.p;
     L.work_query = b->work_query.p; L.work_slice = b->work_slice.p;
-    L.n_work = b->n_work; L.n_slices = b->n_slices; L.top_k = b->top_k;
+    L.n_work = b->n_work; L.n_slices = b->n_lists; L.top_k = b->top_k;
     L.theta = b->theta.p; L.total_hits = b->total_hits.p;
     L.slice_keys = b->slice_keys.p; L.slice_cnt = b->slice_cnt.p;
     if (!b->wide_slots) {
@@ -707,7 +725,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   }
   MergeLaunch M;
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
-  M.n_lists = b->n_slices; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;
+  M.n_lists = b->n_lists; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;
   M.out_docs = b->o_docs(); M.out_scores = b->o_scores(); M.out_counts = b->o_counts();
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());

@@ -74,6 +74,7 @@ constexpr int kSparseExtra = (kW * 4) / (kCH * 4 + kCH) < 14 ? (kW * 4) / (kCH *
 constexpr int kPoolSparse = kPool + kSparseExtra;
 constexpr int kSparseF8Off = kSparseExtra * kCH * 4;   // byte offset of the sparse tf region inside the window array
 static_assert(kW * 4 - kSparseF8Off + kPool * kCH >= kPoolSparse * kCH, "sparse tf chunks must fit behind the extra doc chunks");
+constexpr int kWarmGran = 32;   // granules (32K docs) of the warm-up work item of a query
 constexpr int kPlaneChunks = (2 * kW + kCH * 4 - 1) / (kCH * 4);   // pool chunks (doc part) lent to the two tf-plane buffers
 
 struct StreamLaunch {
@@ -330,7 +331,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   const int wi = blockIdx.x;
   if (wi >= L.n_work) return;
   const int qi = L.work_query[wi];
-  const int slice = L.work_slice[wi];
+  // work_slice: slice | flags << 24. Flag 1 = warm-up item: only the first kWarmGran granules of slice 0, its own output
+  // list (index n_slices - 1), scheduled before every other item so that the query's other work items start with a
+  // threshold; flag 2 = the slice-0 item of such a query: starts behind those granules.
+  const int slice_raw = L.work_slice[wi];
+  const int slice = slice_raw & 0xffffff;
+  const int wflags = slice_raw >> 24;
   const long long t_start = L.mode_stats ? clock64() : 0ll;
 
   // every thread reads the three query fields the loads below depend on straight from global memory (one broadcast
@@ -362,6 +368,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   const int gran_per_slice = L.slice_docs >> kLogGran;           // 512
   const int g_first = slice * gran_per_slice;
   const int g_count = min(gran_per_slice, L.n_gran - g_first);     // granules of this slice
+  const int g_lo = (wflags & 2) ? min(g_count, kWarmGran) : 0;     // granules [g_lo, g_hi) are this work item's
+  const int g_hi = (wflags & 1) ? min(g_count, kWarmGran) : g_count;
 #pragma unroll
   for (int t = 0; t < kT; ++t) {
     const uint32_t* p = L.gbounds + ((size_t)qi * kT + t) * (L.n_gran + 1) + g_first;
@@ -411,8 +419,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
         const DevClause& c = sm.cl[i];
         if (c.kind != NRTGPU_TERM) continue;
         if (((ne >> c.slot) & 1u) && c.plane >= 0 && L.ix.dense_tf != nullptr) { pm |= 1u << c.slot; continue; }
-        const uint32_t n_slice = reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[c.slot] -
-                                 reinterpret_cast<const uint32_t*>(&sm.gb4[0])[c.slot];
+        const uint32_t n_slice = reinterpret_cast<const uint32_t*>(&sm.gb4[g_hi])[c.slot] -
+                                 reinterpret_cast<const uint32_t*>(&sm.gb4[g_lo])[c.slot];
         if (n_slice > (uint32_t)(ne ? kSparseCap : kSparseCapAll)) sp = 0;
       }
       if (!sp) pm = 0;
@@ -436,8 +444,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
     const int s = sm.cl[tid].slot;
     const bool served = s == pslot || ((pserve_mask >> s) & 1u);   // plane-served lists are not streamed: no postings
-    const int64_t g0 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[0])[s]),
-                  g1 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[g_count])[s]);
+    const int64_t g0 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[g_lo])[s]),
+                  g1 = sm.cl[tid].post_base + (served ? 0u : reinterpret_cast<const uint32_t*>(&sm.gb4[g_hi])[s]);
     const int64_t base_g = (g0 >> kLogCH) << kLogCH;
     sm.s_r_begin[s] = (int32_t)(g0 - base_g);
     sm.s_r_end[s] = (int32_t)(g1 - base_g);
@@ -501,14 +509,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   // the window table: from granule g the window runs to nextg[g] = the farthest granule (<= g + kWinGran) whose
   // postings fit every ring with one chunk of alignment slack. One granule always fits (<= kGran postings).
   // (sparse mode has no window array, so only the rings bound the run)
-  for (int g = tid; g < g_count; g += kThreads) {
+  for (int g = g_lo + tid; g < g_hi; g += kThreads) {
     const uint4 a = sm.gb4[g];
     auto fits = [&](int g1) {
       const uint4 b = sm.gb4[g1];
       return (int32_t)(b.x - a.x) <= rmask[0] + 1 - kCH && (int32_t)(b.y - a.y) <= rmask[1] + 1 - kCH &&
              (int32_t)(b.z - a.z) <= rmask[2] + 1 - kCH && (int32_t)(b.w - a.w) <= rmask[3] + 1 - kCH;
     };
-    int hi = sparse ? g_count : min(g_count, g + kWinGran);
+    int hi = sparse ? g_hi : min(g_hi, g + kWinGran);
     int lo = g + 1;                     // always accepted
     if (hi > lo && !fits(hi)) {         // posting counts grow with g1: binary search the last run that fits
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (fits(mid)) lo = mid; else hi = mid; }
@@ -558,8 +566,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   unsigned int my_hits = 0;
   unsigned char* slot_bytes = reinterpret_cast<unsigned char*>(sm.slots);
 
-  int g0 = 0;   // next granule of the slice
-  if (n_term > 0 && ne_mask == ((1u << n_term) - 1u)) g0 = g_count;   // every list is non-essential: skip the slice
+  int g0 = g_lo;   // next granule of the slice
+  if (n_term > 0 && ne_mask == ((1u << n_term) - 1u)) g0 = g_hi;   // every list is non-essential: skip the slice
   // ---- tf plane of the plane-served list: window n's bytes live in buffer n & 1 (filled two windows ahead)
   uint8_t* const pb = reinterpret_cast<uint8_t*>(sm.pool_docs + (kPool - kPlaneChunks) * kCH);
   const uint8_t* const psrc =
@@ -574,16 +582,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
     for (uint32_t o = 0; o < bytes; o += 4096u)
       bulk_g2s(pb + (n & 1) * kW + o, psrc + wb + o, min(4096u, bytes - o), bar);
   };
-  if (pslot >= 0 && tid == 0 && g0 < g_count) {
+  if (pslot >= 0 && tid == 0 && g0 < g_hi) {
     const int ga = sm.nextg[g0];
     issue_plane(0, g0, ga);
-    if (ga < g_count) issue_plane(1, ga, sm.nextg[ga]);
+    if (ga < g_hi) issue_plane(1, ga, sm.nextg[ga]);
   }
   unsigned long long dbg_postings = 0;   // driver postings visited (NRTGPU_DEBUG_MODES)
   const long long t_loop = L.mode_stats ? clock64() : 0ll;
   unsigned long long dbg_windows = 0;
   int wn = 0;   // window counter (skipped windows count too: each has its plane copy)
-  while (g0 < g_count) {
+  while (g0 < g_hi) {
     // ---------------- window = the longest run of granules (<= kWinGran) whose postings fit every ring
     const int g1 = sm.nextg[g0];
     int32_t cnt[kT];
@@ -627,9 +635,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
       __syncwarp();
     }
     auto next_plane = [&]() {   // after the window's last barrier: buffer wn & 1 is free for window wn + 2
-      if (pslot >= 0 && tid == 0 && g1 < g_count) {
+      if (pslot >= 0 && tid == 0 && g1 < g_hi) {
         const int g2 = sm.nextg[g1];
-        if (g2 < g_count) issue_plane(wn + 2, g2, sm.nextg[g2]);
+        if (g2 < g_hi) issue_plane(wn + 2, g2, sm.nextg[g2]);
       }
       ++wn;
     };
@@ -893,9 +901,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   if (simple ? sm.cand_count > sm.n_keys : sm.cand_count > L.top_k)
     compact_candidates_v2(L, sm, norms0, simple, has_after, after_key, L.top_k, &L.theta[qi]);
   const int keep = min(sm.cand_count, L.top_k);
-  uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + slice) * L.top_k;
+  const int out_list = (wflags & 1) ? L.n_slices - 1 : slice;
+  uint64_t* out = L.slice_keys + ((size_t)qi * L.n_slices + out_list) * L.top_k;
   for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
-  if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + slice] = keep;
+  if (tid == 0) L.slice_cnt[(size_t)qi * L.n_slices + out_list] = keep;
   for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
   if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
   if (L.mode_stats && tid == 0) {
