@@ -382,10 +382,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_stream_kernel(co
   __syncthreads();
   // ---- MAXSCORE split (pure term disjunctions, once the query has collected more than totalHitsThreshold hits):
   // the lists whose list-wide score bounds sum (in double, ascending) to less than theta.score are non-essential --
-  // a doc found only in them cannot beat theta. They are still streamed and scattered (so the owners of the
-  // essential lists see their exact tf -- no probing), but they do not drive pass 2: their postings are only cleared
-  // in pass 3 (~half the per-posting work). Rank-safe; docs matching only non-essential lists are not counted, so
-  // totalHits becomes a lower bound (relation GREATER_THAN_OR_EQUAL_TO).
+  // a doc found only in them cannot beat theta. They never own a doc; the owners of the essential lists still see
+  // their exact tf: from the list's dense tf plane when it has one (window mode: TMA copy per window; sparse mode:
+  // byte gathers), else from its postings (scattered in window mode and cleared in pass 3, searched in sparse mode).
+  // Rank-safe; docs matching only non-essential lists are not counted, so totalHits becomes a lower bound (relation
+  // GREATER_THAN_OR_EQUAL_TO). Then the sweep mode of the work item is chosen.
   if (tid == 0) {
     uint32_t ne = 0;
     const DevQuery& q = sm.q;
