@@ -3,6 +3,7 @@
 #include "../../include/nrtgpu.h"
 #include "bool_kernel.cuh"
 #include "stream_kernel.cuh"
+#include "probe_kernel.cuh"
 #include "knn_kernel.cuh"
 #include "hybrid_kernel.cuh"
 
@@ -25,6 +26,8 @@ using namespace nrtgpu;
 struct nrtgpu_ctx {
   int device = 0;
   int sm_count = 0;
+  bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
+  bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
 };
 
 // index-time impacts: max over a term's postings of x = tf * cache[norm] (what Lucene keeps as competitive (freq, norm)
@@ -184,6 +187,12 @@ struct nrtgpu_batch {
   int32_t nq = 0, top_k = 0, n_slices = 0, n_work = 0;
   int32_t n_lists = 0;         // per-query candidate lists the kernels fill: n_slices (+1: warm-up items of the stream path)
   int32_t n_work_simple = 0;   // the first n_work_simple work items belong to pure single-field term disjunctions
+  // work list layout (<= 4-term batches): [probe simple | probe generic | stream (window kernel: no posting list can lead)]
+  int32_t n_probe_simple = 0, n_probe_generic = 0, n_stream = 0;
+  bool use_probe = false;
+  DevBuf<uint32_t> sbounds;            // probe kernel: [nq][4][n_slices + 2] slice-boundary posting offsets
+  DevBuf<unsigned int> work_counter;   // probe kernel: queue heads [2]
+  DevBuf<unsigned long long> probe_stats;
   bool wide_slots = false;
   bool exhaustive = true;
   int64_t alg_postings = 0;
@@ -194,6 +203,10 @@ struct nrtgpu_batch {
   DevBuf<float> qtables;     // stream kernel: [nq][kQTabFloats] score + bound tables
   DevBuf<unsigned long long> mode_stats;   // NRTGPU_DEBUG_MODES=1: cycles / work items per kernel mode
   DevBuf<int32_t> pruned;    // [nq] relation GTE flags
+  DevBuf<int32_t> terminated; // [nq] terminateAfter cut the query short
+  DevBuf<int32_t> abort_flag; // [1] device abort word polled at work-item boundaries (deadline / cancellation), or NULL
+  DevBuf<int64_t> terminate_after;   // [nq] or NULL
+  std::vector<DevClause> h_dc; std::vector<DevQuery> h_dq; std::vector<int32_t> h_wq, h_ws;   // host copies the async uploads read
   int32_t slice_docs = 0;
   int64_t threshold = INT32_MAX;
   int32_t n_gran = 0;
@@ -236,9 +249,11 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   cudaDeviceProp prop;
   NRT_CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major < 10) NRT_FAIL(NRTGPU_ERR_CUDA, "nrtgpu_init: device is not sm_100 class (kernels are built for sm_100a only)");
-  auto* c = new nrtgpu_ctx;
+  std::unique_ptr<nrtgpu_ctx> c(new nrtgpu_ctx);   // released to the caller only when every attribute call succeeded
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
+  { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
+  c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint32_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -247,9 +262,13 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(v2::StreamSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(v3::ProbeSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(v3::ProbeSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kPGemmSmem));
-  *out = c;
+  *out = c.release();
   return NRTGPU_OK;
 }
 
@@ -577,7 +596,13 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     }
   }
   b->wide_slots = max_terms > 4 || top_k > v2::kMaxTopKStream;
-  if (!b->wide_slots) slice_docs = v2::kSliceDocs;
+  b->use_probe = !b->wide_slots && !ix->ctx->engine_stream;
+  if (!b->wide_slots) {
+    // slices of equal size, a multiple of the 1024-doc granule, at most 512K docs: a 1.25M-doc shard is 3 x 417K, not 2.38 -> 3 x 512K
+    const int64_t n_sl = std::max<int64_t>(1, ((int64_t)ix->n_docs + v2::kSliceDocs - 1) / v2::kSliceDocs);
+    slice_docs = (((int64_t)ix->n_docs + n_sl - 1) / n_sl + v2::kGran - 1) / v2::kGran * v2::kGran;
+    if (slice_docs < v2::kGran) slice_docs = v2::kGran;
+  }
   b->slice_docs = (int32_t)slice_docs;
   b->n_slices = (int32_t)std::max<int64_t>(1, ((int64_t)ix->n_docs + slice_docs - 1) / slice_docs);
   // work list, slice-major so that concurrently resident CTAs share postings of the same doc range in L2;
@@ -591,43 +616,59 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     if (dq[qi].dense_driver) cost[qi] += ix->n_docs;
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
-  // pure disjunctions of scoring term clauses over one text field (no deletes) run in their own instantiation of
-  // the stream kernel: their work items come first
+  // pure disjunctions of scoring term clauses over one text field (no deletes) run in their own kernel instantiation
+  // (tf-pattern bound, deferred scoring, MAXSCORE): their work items come first
   auto is_simple = [&](int qi) {
     const DevQuery& o = dq[(size_t)qi];
     return o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
            o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
   };
-  std::vector<int32_t> wq, ws;
-  // warm-up items (stream path, TOP_SCORES mode, large shards): a query with a dense list first sweeps the leading
-  // kWarmGran granules of slice 0 as a work item of its own, ahead of everything else, so that its other work items
-  // start with a threshold and a hit count (MAXSCORE can prune from the first slice on)
-  const bool warm_ok = !b->wide_slots && b->threshold < (int64_t)INT32_MAX &&
+  // 0: probe kernel, simple; 1: probe kernel, generic (a posting list leads); 2: window/stream kernel (no list can lead)
+  auto engine_class = [&](int qi) {
+    if (is_simple(qi)) return 0;
+    if (!b->use_probe) return 2;
+    return dq[(size_t)qi].dense_driver ? 2 : 1;
+  };
+  std::vector<int32_t>& wq = b->h_wq; std::vector<int32_t>& ws = b->h_ws;
+  wq.clear(); ws.clear();
+  // warm-up items (large shards): a query first sweeps the leading kWarmGran granules of slice 0 as a work item of its
+  // own, ahead of everything else, so that its other work items start with a threshold and a hit count (MAXSCORE can
+  // prune from the first slice on). Window kernel: TOP_SCORES mode, queries with a dense list; probe kernel: both score
+  // modes, every query whose lists are expected to hold 2 * top_k hits in those granules.
+  const bool warm_ok = !b->wide_slots && (b->use_probe || b->threshold < (int64_t)INT32_MAX) &&
                        (int64_t)ix->n_docs >= 8ll * v2::kWarmGran * v2::kGran;
   std::vector<uint8_t> has_warm((size_t)nq, 0);
   if (warm_ok) {
     for (int qi : order) {
       if (!is_simple(qi)) continue;
-      for (int c = 0; c < dq[qi].n_clauses; ++c) {
-        const DevClause& x = dc[(size_t)dq[qi].clause_begin + c];
-        if (x.kind == NRTGPU_TERM && (int64_t)x.n_post * 64 >= (int64_t)ix->n_docs) has_warm[(size_t)qi] = 1;
+      if (b->use_probe) {
+        if (cost[qi] * (int64_t)(v2::kWarmGran * v2::kGran) >= 2ll * top_k * (int64_t)ix->n_docs) has_warm[(size_t)qi] = 1;
+      } else {
+        for (int c = 0; c < dq[qi].n_clauses; ++c) {
+          const DevClause& x = dc[(size_t)dq[qi].clause_begin + c];
+          if (x.kind == NRTGPU_TERM && (int64_t)x.n_post * 64 >= (int64_t)ix->n_docs) has_warm[(size_t)qi] = 1;
+        }
       }
       if (has_warm[(size_t)qi]) { wq.push_back(qi); ws.push_back(0 | (1 << 24)); }
     }
   }
   b->n_lists = b->n_slices + (warm_ok ? 1 : 0);
-  for (int pass = 0; pass < 2; ++pass) {
+  int32_t class_end[3] = {0, 0, 0};
+  for (int cls = 0; cls < 3; ++cls) {
     for (int s = 0; s < b->n_slices; ++s)
-      for (int qi : order) if (is_simple(qi) == (pass == 0)) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
-    if (pass == 0) b->n_work_simple = (int32_t)wq.size();
+      for (int qi : order) if (engine_class(qi) == cls) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+    class_end[cls] = (int32_t)wq.size();
   }
   b->n_work = (int32_t)wq.size();
+  b->n_work_simple = class_end[0];
+  if (b->use_probe) { b->n_probe_simple = class_end[0]; b->n_probe_generic = class_end[1] - class_end[0]; b->n_stream = class_end[2] - class_end[1]; }
+  else { b->n_probe_simple = b->n_probe_generic = 0; b->n_stream = b->wide_slots ? 0 : b->n_work; }
+  b->h_dc.swap(dc); b->h_dq.swap(dq);   // kept alive until the next compilation: the uploads below are asynchronous
   int rc;
-  if ((rc = b->clauses.upload_async(dc.data(), dc.size(), st))) return rc;
-  if ((rc = b->queries.upload_async(dq.data(), dq.size(), st))) return rc;
+  if ((rc = b->clauses.upload_async(b->h_dc.data(), b->h_dc.size(), st))) return rc;
+  if ((rc = b->queries.upload_async(b->h_dq.data(), b->h_dq.size(), st))) return rc;
   if ((rc = b->work_query.upload_async(wq.data(), wq.size(), st))) return rc;
   if ((rc = b->work_slice.upload_async(ws.data(), ws.size(), st))) return rc;
-  NRT_CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
   if ((rc = b->theta.alloc((size_t)nq))) return rc;
   if ((rc = b->total_hits.alloc((size_t)nq))) return rc;
   if ((rc = b->slice_keys.alloc((size_t)nq * b->n_lists * top_k))) return rc;
@@ -636,23 +677,38 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if ((rc = b->out_scores.alloc((size_t)nq * top_k))) return rc;
   if ((rc = b->out_counts.alloc((size_t)nq))) return rc;
   if ((rc = b->pruned.alloc((size_t)nq))) return rc;
+  if ((rc = b->terminated.alloc((size_t)nq))) return rc;
   if (!b->wide_slots) {
-    // the stream kernel reads per-granule posting bounds of every (query, term clause): one lower_bound each
     b->n_gran = (int32_t)(((int64_t)ix->n_docs + v2::kGran - 1) / v2::kGran);
     if (b->n_gran < 1) b->n_gran = 1;
-    const int64_t total = (int64_t)nq * v2::kT * (b->n_gran + 1);
-    if ((rc = b->gbounds.alloc((size_t)total))) return rc;
-    v2::BoundsLaunch B;
-    B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_gran = b->n_gran;
-    B.gbounds = b->gbounds.p;
-    v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B);
-    NRT_CUDA_TRY(cudaGetLastError());
-    if ((rc = b->qtables.alloc((size_t)nq * v2::kQTabFloats))) return rc;
-    v2::QTabLaunch Q;
-    Q.ix = B.ix; Q.clauses = B.clauses; Q.queries = B.queries; Q.field_min_norm = ix->field_min_norm.p; Q.nq = nq;
-    Q.qtables = b->qtables.p;
-    if (nq > 0) v2::query_tables_kernel<<<(unsigned)nq, 256, 0, st>>>(Q);
-    NRT_CUDA_TRY(cudaGetLastError());
+    if (b->n_probe_simple + b->n_probe_generic > 0) {
+      // probe kernel: posting offsets of every (query, term slot) at the slice boundaries only (skip data for the long
+      // lists, one lower_bound for the short ones); the granule offsets inside a slice are read from gran_tab by the kernel
+      const int64_t total = (int64_t)nq * v3::kT * (b->n_slices + 2);
+      if ((rc = b->sbounds.alloc((size_t)total))) return rc;
+      if ((rc = b->work_counter.alloc(2))) return rc;
+      v3::SliceBoundsLaunch S;
+      S.ix = ix->view(); S.clauses = b->clauses.p; S.queries = b->queries.p; S.nq = nq; S.n_slices = b->n_slices;
+      S.slice_gran = b->slice_docs / v2::kGran; S.n_gran = b->n_gran; S.sbounds = b->sbounds.p;
+      v3::slice_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S);
+      NRT_CUDA_TRY(cudaGetLastError());
+    }
+    if (b->n_stream > 0) {
+      // the window/stream kernel reads per-granule posting bounds of every (query, term clause) and per-query score tables
+      const int64_t total = (int64_t)nq * v2::kT * (b->n_gran + 1);
+      if ((rc = b->gbounds.alloc((size_t)total))) return rc;
+      v2::BoundsLaunch B;
+      B.ix = ix->view(); B.clauses = b->clauses.p; B.queries = b->queries.p; B.nq = nq; B.n_gran = b->n_gran;
+      B.gbounds = b->gbounds.p;
+      v2::granule_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B);
+      NRT_CUDA_TRY(cudaGetLastError());
+      if ((rc = b->qtables.alloc((size_t)nq * v2::kQTabFloats))) return rc;
+      v2::QTabLaunch Q;
+      Q.ix = B.ix; Q.clauses = B.clauses; Q.queries = B.queries; Q.field_min_norm = ix->field_min_norm.p; Q.nq = nq;
+      Q.qtables = b->qtables.p;
+      if (nq > 0) v2::query_tables_kernel<<<(unsigned)nq, 256, 0, st>>>(Q);
+      NRT_CUDA_TRY(cudaGetLastError());
+    }
   }
   if (!b->ev[0][0]) for (auto& r : b->ev) for (auto& e : r) NRT_CUDA_TRY(cudaEventCreate(&e));
   return NRTGPU_OK;
@@ -673,11 +729,15 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
 int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_run: NULL batch");
   cudaStream_t st = (cudaStream_t)stream_;
+  int rc_dbg = 0;
   NRT_CUDA_TRY(cudaSetDevice(b->ix->ctx->device));
   NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->slice_cnt.p, 0, b->slice_cnt.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->pruned.p, 0, b->pruned.bytes(), st));
+  NRT_CUDA_TRY(cudaMemsetAsync(b->terminated.p, 0, b->terminated.bytes(), st));
+  if (b->work_counter.p) NRT_CUDA_TRY(cudaMemsetAsync(b->work_counter.p, 0, b->work_counter.bytes(), st));
+  const bool debug = b->ix->ctx->debug_modes;
   cudaEvent_t* ev = b->ev[b->runs_recorded % nrtgpu_batch::kEvRing];
   NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
   if (b->n_work > 0) {
@@ -689,39 +749,82 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     L.theta = b->theta.p; L.total_hits = b->total_hits.p;
     L.slice_keys = b->slice_keys.p; L.slice_cnt = b->slice_cnt.p;
     if (!b->wide_slots) {
-      v2::StreamLaunch S;
-      S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries; S.work_query = L.work_query; S.work_slice = L.work_slice;
-      S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.qtables = b->qtables.p; S.n_work = L.n_work; S.n_slices = L.n_slices; S.top_k = L.top_k;
-      S.slice_docs = b->slice_docs;
-      S.threshold = b->threshold; S.pruned = b->pruned.p;
-      S.mode_stats = nullptr;
-      if (getenv("NRTGPU_DEBUG_MODES")) {
-        if (!b->mode_stats.p && b->mode_stats.alloc(13)) return NRTGPU_ERR_CUDA;
-        NRT_CUDA_TRY(cudaMemsetAsync(b->mode_stats.p, 0, 13 * sizeof(unsigned long long), st));
-        S.mode_stats = b->mode_stats.p;
+      const int n_probe = b->n_probe_simple + b->n_probe_generic;
+      if (n_probe > 0) {
+        v3::ProbeLaunch P;
+        P.ix = L.ix; P.clauses = L.clauses; P.queries = L.queries; P.sbounds = b->sbounds.p;
+        P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr;
+        P.n_lists = b->n_lists; P.n_slices = b->n_slices; P.top_k = b->top_k; P.slice_docs = b->slice_docs; P.n_gran = b->n_gran;
+        P.threshold = b->threshold; P.pruned = b->pruned.p; P.theta = L.theta; P.total_hits = L.total_hits;
+        P.slice_keys = L.slice_keys; P.slice_cnt = L.slice_cnt;
+        P.abort_flag = b->abort_flag.p; P.terminate_after = b->terminate_after.p; P.terminated = b->terminated.p;
+        if (debug) {
+          if (!b->probe_stats.p && (rc_dbg = b->probe_stats.alloc(16))) return rc_dbg;
+          NRT_CUDA_TRY(cudaMemsetAsync(b->probe_stats.p, 0, 16 * sizeof(unsigned long long), st));
+        }
+        const int resident = v3::kCtasPerSm * b->ix->ctx->sm_count;
+        if (b->n_probe_simple > 0) {
+          P.work_query = L.work_query; P.work_slice = L.work_slice; P.n_work = b->n_probe_simple; P.work_counter = b->work_counter.p;
+          P.stats = debug ? b->probe_stats.p : nullptr;
+          v3::posting_probe_kernel<true><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+        }
+        if (b->n_probe_generic > 0) {
+          P.work_query = L.work_query + b->n_probe_simple; P.work_slice = L.work_slice + b->n_probe_simple;
+          P.n_work = b->n_probe_generic; P.work_counter = b->work_counter.p + 1;
+          P.stats = debug ? b->probe_stats.p + 8 : nullptr;
+          v3::posting_probe_kernel<false><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+        }
+        NRT_CUDA_TRY(cudaGetLastError());
       }
-      S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
-      if (b->n_work_simple > 0) {
-        S.n_work = b->n_work_simple;
-        v2::posting_stream_kernel<true><<<b->n_work_simple, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
-      }
-      if (b->n_work > b->n_work_simple) {
-        S.work_query = L.work_query + b->n_work_simple; S.work_slice = L.work_slice + b->n_work_simple;
-        S.n_work = b->n_work - b->n_work_simple;
-        v2::posting_stream_kernel<false><<<S.n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+      if (b->n_stream > 0) {
+        v2::StreamLaunch S;
+        S.ix = L.ix; S.clauses = L.clauses; S.queries = L.queries;
+        S.gbounds = b->gbounds.p; S.n_gran = b->n_gran; S.qtables = b->qtables.p; S.n_slices = L.n_slices; S.top_k = L.top_k;
+        S.slice_docs = b->slice_docs;
+        S.threshold = b->threshold; S.pruned = b->pruned.p;
+        S.mode_stats = nullptr;
+        if (debug && !b->use_probe) {
+          if (!b->mode_stats.p && (rc_dbg = b->mode_stats.alloc(13))) return rc_dbg;
+          NRT_CUDA_TRY(cudaMemsetAsync(b->mode_stats.p, 0, 13 * sizeof(unsigned long long), st));
+          S.mode_stats = b->mode_stats.p;
+        }
+        S.theta = L.theta; S.total_hits = L.total_hits; S.slice_keys = L.slice_keys; S.slice_cnt = L.slice_cnt;
+        const int first = n_probe;   // stream items follow the probe items in the work list
+        const int n_simple = b->use_probe ? 0 : b->n_work_simple;
+        if (n_simple > 0) {
+          S.work_query = L.work_query + first; S.work_slice = L.work_slice + first; S.n_work = n_simple;
+          v2::posting_stream_kernel<true><<<n_simple, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+        }
+        if (b->n_stream > n_simple) {
+          S.work_query = L.work_query + first + n_simple; S.work_slice = L.work_slice + first + n_simple;
+          S.n_work = b->n_stream - n_simple;
+          v2::posting_stream_kernel<false><<<S.n_work, v2::kThreads, sizeof(v2::StreamSmem), st>>>(S);
+        }
+        NRT_CUDA_TRY(cudaGetLastError());
       }
     } else
       bool_window_kernel<uint64_t><<<b->n_work, kThreads, sizeof(BoolSmem<uint64_t>), st>>>(L);
     NRT_CUDA_TRY(cudaGetLastError());
   }
   NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
-  if (b->mode_stats.p && getenv("NRTGPU_DEBUG_MODES")) {
+  if (debug && b->mode_stats.p && !b->use_probe) {
     unsigned long long h[13];
     NRT_CUDA_TRY(cudaMemcpyAsync(h, b->mode_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     NRT_CUDA_TRY(cudaStreamSynchronize(st));
     fprintf(stderr, "[nrtgpu modes] window: %llu items %.0f cyc/item %llu driver postings | window+maxscore: %llu items %.0f %llu | sparse: %llu items %.0f %llu\n",
             h[1], h[1] ? (double)h[0] / h[1] : 0.0, h[6], h[3], h[3] ? (double)h[2] / h[3] : 0.0, h[7], h[5], h[5] ? (double)h[4] / h[5] : 0.0, h[8]);
     if (h[5]) fprintf(stderr, "[nrtgpu modes] sparse items: set-up %.0f cyc, sweep %.0f, flush+output %.0f, %.2f runs/item\n", (double)h[9] / h[5], (double)h[10] / h[5], (double)h[11] / h[5], (double)h[12] / h[5]);
+  }
+  if (debug && b->probe_stats.p && b->use_probe) {
+    unsigned long long h[16];
+    NRT_CUDA_TRY(cudaMemcpyAsync(h, b->probe_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NRT_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int k = 0; k < 2; ++k) {
+      const unsigned long long* x = h + 8 * k;
+      if (x[0]) fprintf(stderr, "[nrtgpu probe %s] %llu items, %.0f cyc/item (set-up %.0f), %.2f runs/item (%.2f staged), %.1f rounds/item, %llu driver postings (%.0f/item), %.2f flushes/item\n",
+                        k == 0 ? "simple" : "generic", x[0], (double)x[1] / x[0], (double)x[6] / x[0], (double)x[2] / x[0], (double)x[5] / x[0],
+                        (double)x[7] / x[0], x[3], (double)x[3] / x[0], (double)x[4] / x[0]);
+    }
   }
   MergeLaunch M;
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
@@ -777,8 +880,16 @@ int nrtgpu_batch_reset_timing(nrtgpu_batch* b) {
 int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run, int64_t* work_items) {
   if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
   if (alg_postings) *alg_postings = b->alg_postings;
-  if (launches_per_run) *launches_per_run = (b->wide_slots ? (b->n_work > 0 ? 1 : 0)
-                                                           : (b->n_work_simple > 0 ? 1 : 0) + (b->n_work > b->n_work_simple ? 1 : 0)) + 1;
+  if (launches_per_run) {
+    int n = 1;   // slice merge
+    if (b->wide_slots) n += b->n_work > 0 ? 1 : 0;
+    else {
+      n += (b->n_probe_simple > 0 ? 1 : 0) + (b->n_probe_generic > 0 ? 1 : 0);
+      const int n_simple = b->use_probe ? 0 : b->n_work_simple;
+      n += (n_simple > 0 ? 1 : 0) + (b->n_stream > n_simple ? 1 : 0);
+    }
+    *launches_per_run = n;
+  }
   if (work_items) *work_items = b->n_work;
   return NRTGPU_OK;
 }
