@@ -156,7 +156,11 @@ int nrtgpu_batch_stage_ms(nrtgpu_batch* b, int32_t stage, float* ms);
 int nrtgpu_batch_reset_timing(nrtgpu_batch* b);
 int nrtgpu_batch_free(nrtgpu_batch* b);
 
-/* Exact kNN (ExactVectorQuery / KnnFloatVectorQuery with exact semantics): HOST buffers. */
+/* Exact kNN (ExactVectorQuery / KnnFloatVectorQuery with exact semantics): HOST buffers. Deleted docs (live_docs of the
+ * shard) are never hits, as through IndexSearcher's acceptDocs; `filter` is ANDed on top. Exact BY CONSTRUCTION: the
+ * tensor-core candidate stage is followed by an fp64 re-score and a rank-safety certificate (every vector outside the
+ * candidate list is proven, with the bf16 error bound 2^-7 |q||d|, to score below the k-th exact score); queries the
+ * certificate rejects are re-run by exact evaluation of every vector (nrtgpu_knn_last_uncertified counts them). */
 int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k,
                       const float* boosts /*[nq] or NULL*/, const uint8_t* filter /*[n_docs] 0/1 or NULL*/,
                       void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts);
@@ -165,6 +169,9 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
  * stage_ms[0] candidate GEMM (tcgen05 bf16 when dims % 8 == 0), [1] per-query select, [2] exact fp64 re-score */
 int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream,
                             int32_t* out_docs, float* out_scores, int32_t* out_counts, float* stage_ms);
+
+/* number of queries of the most recent kNN call on this index that took the exact fallback */
+int32_t nrtgpu_knn_last_uncertified(const nrtgpu_index* ix);
 
 /* TopDocs.merge over `n_lists` per-shard lists resident on the DEVICE (the receive buffer of the NCCL
  * all-gather): docs/scores [n_lists][nq][top_k], counts [n_lists][nq]; outputs on the device. */

@@ -68,7 +68,7 @@ NRTGPU_SYMBOLS = [
     "nrtgpu_index_close", "nrtgpu_index_device_bytes", "nrtgpu_search_bool", "nrtgpu_batch_prepare",
     "nrtgpu_batch_run", "nrtgpu_batch_fetch", "nrtgpu_batch_device_results", "nrtgpu_batch_stats",
     "nrtgpu_batch_stage_ms", "nrtgpu_batch_reset_timing", "nrtgpu_batch_bind_output", "nrtgpu_batch_free", "nrtgpu_search_knn", "nrtgpu_search_knn_timed", "nrtgpu_merge_topk_device",
-    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine",
+    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified",
 ]
 
 _gpu = None
@@ -107,6 +107,8 @@ def gpu_lib() -> C.CDLL:
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nrtgpu_search_knn_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]
+        lib.nrtgpu_knn_last_uncertified.argtypes = [C.c_void_p]
+        lib.nrtgpu_knn_last_uncertified.restype = C.c_int32
         lib.nrtgpu_merge_topk_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
         lib.nrtgpu_blend_rrf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

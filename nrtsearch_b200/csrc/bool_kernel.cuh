@@ -88,6 +88,8 @@ struct DevIndexView {
   int32_t n_gran;
   const uint8_t* dense_tf;       // [n_planes][dense_stride] min(freq, 255) per doc for the densest terms (0 = absent)
   int64_t dense_stride;
+  const uint8_t* dense_tf2;      // [n_planes][dense_stride / 4] min(freq, 3) in 2 bits per doc: the planes the probe kernel gathers
+                                 // (a quarter of the L2 / DRAM footprint of the byte planes; 3 = "three or more")
 };
 
 struct BoolLaunch {

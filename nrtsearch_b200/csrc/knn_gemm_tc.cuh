@@ -74,6 +74,7 @@ struct GemmParams {
   int cc_cap;
   const uint8_t* filter;  // per DOC 0/1 or NULL
   const int32_t* vec_docs;  // ordinal -> doc or NULL
+  const uint32_t* live_bits;  // liveDocs bitmap or NULL
 };
 
 // one 32-column slice of an accumulator row: store the approximate scores (unfused) or keep the survivors (fused)
@@ -101,7 +102,11 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& P, const uint32
         if (gd < P.N && x >= th) {
           const int ord = P.n_base + gd;
           bool ok = true;
-          if (P.filter) ok = P.filter[P.vec_docs ? P.vec_docs[ord] : ord] != 0;
+          if (P.filter || P.live_bits) {
+            const int doc = P.vec_docs ? P.vec_docs[ord] : ord;
+            if (P.filter) ok = P.filter[doc] != 0;
+            if (ok && P.live_bits) ok = (P.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+          }
           if (ok) {
             const int pos = atomicAdd(P.cc_cnt + gq, 1);
             if (pos < P.cc_cap) P.cc[(size_t)gq * P.cc_cap + pos] = make_key(x, ord);

@@ -9,7 +9,11 @@
 //      Lucene score mapping in float, then the final (score desc, doc asc) top-k.
 // Stage A is the GEMM-shaped part (the tensor-core version replaces only that stage).
 #pragma once
+#include <algorithm>
+#include <cstring>
+#include <vector>
 #include "common.cuh"
+#include "bool_kernel.cuh"
 #include "knn_gemm_tc.cuh"
 #include "../../include/nrtgpu.h"
 
@@ -30,6 +34,13 @@ __global__ void knn_norm2_kernel(const float* __restrict__ v, int n, int dims, f
   for (int i = lane; i < dims; i += 32) { double x = p[i]; s += x * x; }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[warp] = (float)s;
+}
+
+__global__ void knn_max_norm2_kernel(const float* __restrict__ norm2, int n, unsigned int* __restrict__ out_bits) {
+  float m = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, norm2[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // m >= 0: float order == unsigned order
 }
 
 // (a, b) with approximate score = a * dot + b, monotone in the final Lucene score of the similarity
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(256) knn_dot_tile_kernel(const float* __restri
 struct KnnSelectLaunch {
   const float* S; int ldS; int n_chunk; int chunk_base;  // ordinal of S[:,0]
   const uint8_t* filter;   // per DOC 0/1 or NULL
+  const uint32_t* live_bits;  // liveDocs bitmap or NULL (deleted docs are never hits: IndexSearcher acceptDocs)
   const int32_t* vec_docs; // ord -> doc or NULL
   int kprime; int nq;
   uint64_t* cand;          // [nq][kprime] sorted desc keys (approx score, ord)
@@ -116,15 +128,17 @@ __global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLau
   if (tid == 0) { count = have; theta = (have == L.kprime) ? L.cand[(size_t)q * L.kprime + L.kprime - 1] : 0ull; }
   __syncthreads();
   int ub = have;
-  auto compact = [&]() {
+  auto compact = [&]() {   // returns the number of keys kept (CTA-uniform)
     __syncthreads();
     int n = count;
     int m = next_pow2(n < 2 ? 2 : n);
     for (int i = n + tid; i < m; i += kKnnSelThreads) buf[i] = 0ull;
     __syncthreads();
     block_bitonic_sort_desc(buf, m);
-    if (tid == 0) { int keep = n < L.kprime ? n : L.kprime; count = keep; if (keep == L.kprime) theta = buf[L.kprime - 1]; }
+    const int keep = n < L.kprime ? n : L.kprime;
+    if (tid == 0) { count = keep; if (keep == L.kprime) theta = buf[L.kprime - 1]; }
     __syncthreads();
+    return keep;
   };
   for (int i0 = 0; i0 < L.n_chunk; i0 += kKnnSelThreads) {
     int i = i0 + tid;
@@ -132,7 +146,11 @@ __global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLau
     if (i < L.n_chunk) {
       int ord = L.chunk_base + i;
       bool ok = true;
-      if (L.filter) { int doc = L.vec_docs ? L.vec_docs[ord] : ord; ok = L.filter[doc] != 0; }
+      if (L.filter || L.live_bits) {
+        const int doc = L.vec_docs ? L.vec_docs[ord] : ord;
+        if (L.filter) ok = L.filter[doc] != 0;
+        if (ok && L.live_bits) ok = (L.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+      }
       if (ok) { key = make_key(L.S[(size_t)q * L.ldS + i], ord); is_cand = key > theta; }
     }
     unsigned bal = __ballot_sync(0xffffffffu, is_cand);
@@ -145,12 +163,12 @@ __global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLau
     ub += kKnnSelThreads;
     if (ub > kKnnCandCap - kKnnSelThreads) {
       __syncthreads();
-      if (count > kKnnCandCap - kKnnSelThreads) compact();
-      ub = count;
+      const int seen = count;
+      __syncthreads();   // every thread has read the count before anybody appends again
+      ub = (seen > kKnnCandCap - kKnnSelThreads) ? compact() : seen;
     }
   }
-  compact();
-  int keep = count;
+  const int keep = compact();
   for (int i = tid; i < keep; i += kKnnSelThreads) L.cand[(size_t)q * L.kprime + i] = buf[i];
   if (tid == 0) L.cand_cnt[q] = keep;
 }
@@ -161,7 +179,32 @@ struct KnnRescoreLaunch {
   const uint64_t* cand; const int32_t* cand_cnt; int kprime;
   const int32_t* vec_docs; int doc_base; const float* boosts; int k;
   int32_t* out_docs; float* out_scores; int32_t* out_counts;
+  // rank-safety certificate of the candidate stage: unsafe[q] = 1 unless every vector OUTSIDE the candidate list is
+  // proven to score below the k-th exact score. eps_rel bounds the relative error of the candidate stage's dot product
+  // in units of |q||d| (bf16 operands: 2^-7; fp32 SIMT: dims * 2^-23), dmax = largest |d| in the corpus.
+  int32_t* unsafe; float eps_rel; float dmax;
 };
+
+// largest final score a vector whose APPROXIMATE score is <= th can have (monotone score mapping applied to th + error bound)
+__device__ __forceinline__ float knn_score_upper_bound(int sim, double th, double qn, double dmax, double eps_rel, float boost) {
+  const double slack = 1.0 + 1e-3;   // rsqrt / float norm / accumulation rounding on top of the operand rounding
+  double s;
+  if (sim == NRTGPU_SIM_COSINE) {            // approx = dot / |d|  (|q| cos)
+    const double c = (th + eps_rel * slack * qn) / fmax(qn, 1e-300);
+    s = (1.0 + fmin(c, 1.0)) / 2.0;
+  } else if (sim == NRTGPU_SIM_L2) {         // approx = 2 dot - |d|^2 = |q|^2 - dist^2
+    const double d2 = qn * qn - (th + 2.0 * eps_rel * slack * qn * dmax);
+    s = 1.0 / (1.0 + fmax(d2, 0.0));
+  } else {                                   // approx = dot
+    const double d = th + eps_rel * slack * qn * dmax;
+    if (sim == NRTGPU_SIM_DOT) s = (1.0 + d) / 2.0;
+    else s = d < 0.0 ? 1.0 / (1.0 - d) : d + 1.0;
+  }
+  if (s < 0.0) s = 0.0;
+  float f = (float)(s * (1.0 + 1e-6));
+  f = __fmul_ru(f, boost);
+  return f;
+}
 
 __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
   __shared__ uint64_t keys[kKnnCandCap];
@@ -169,6 +212,13 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
   const int n = L.cand_cnt[q];
   const float* qv = L.Q + (size_t)q * L.dims;
   const float boost = L.boosts ? L.boosts[q] : 1.0f;
+  __shared__ double q_norm2;
+  if (warp == 0) {
+    double s = 0.0;
+    for (int i = lane; i < L.dims; i += 32) { const double x = qv[i]; s += x * x; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) q_norm2 = s;
+  }
   for (int c = warp; c < n; c += 8) {
     int ord = key_doc(L.cand[(size_t)q * L.kprime + c]);
     const float* dv = L.D + (size_t)ord * L.dims;
@@ -203,7 +253,83 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
     L.out_docs[(size_t)q * L.k + i] = key_doc(keys[i]) + L.doc_base;
     L.out_scores[(size_t)q * L.k + i] = key_score(keys[i]);
   }
-  if (tid == 0) L.out_counts[q] = keep;
+  if (tid == 0) {
+    L.out_counts[q] = keep;
+    if (L.unsafe) {
+      int bad = 0;
+      if (n == L.kprime) {   // the list is full: vectors outside it exist, all with approximate scores <= the weakest candidate's
+        const double th = (double)key_score(L.cand[(size_t)q * L.kprime + n - 1]);
+        const float ub = knn_score_upper_bound(L.sim, th, sqrt(q_norm2), (double)L.dmax, (double)L.eps_rel, boost);
+        bad = !(n >= L.k && ub < key_score(keys[L.k - 1]));
+      }
+      L.unsafe[q] = bad;
+    }
+  }
+}
+
+// Exact fallback of the queries the certificate rejected: every vector of a 4096-vector chunk is scored with the oracle's
+// arithmetic (fp64 accumulation, Lucene score mapping in float, x boost), the chunk's best k keys go to a slice list and
+// merge_slices_kernel merges the chunks -- ExactVectorQuery.java:137-173 literally.
+constexpr int kKnnExactChunk = 4096;
+struct KnnExactLaunch {
+  const float* Q; const float* D; int n, dims, sim;
+  const int32_t* qsel;         // [n_sel] query ordinals
+  const float* boosts; const uint8_t* filter; const uint32_t* live_bits; const int32_t* vec_docs;
+  int k, n_chunks;
+  uint64_t* keys;              // [n_sel][n_chunks][k]
+  int32_t* cnt;                // [n_sel][n_chunks]
+};
+
+__global__ void __launch_bounds__(256) knn_exact_chunk_kernel(KnnExactLaunch L) {
+  __shared__ uint64_t keys[kKnnExactChunk];
+  const int chunk = blockIdx.x, sel = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = L.qsel[sel];
+  const float* qv = L.Q + (size_t)q * L.dims;
+  const float boost = L.boosts ? L.boosts[q] : 1.0f;
+  const int base = chunk * kKnnExactChunk;
+  const int m = min(kKnnExactChunk, L.n - base);
+  for (int c = warp; c < kKnnExactChunk; c += 8) {
+    uint64_t key = 0ull;
+    if (c < m) {
+      const int ord = base + c;
+      const int doc = L.vec_docs ? L.vec_docs[ord] : ord;
+      bool ok = true;
+      if (L.filter) ok = L.filter[doc] != 0;
+      if (ok && L.live_bits) ok = (L.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+      if (ok) {
+        const float* dv = L.D + (size_t)ord * L.dims;
+        double dot = 0, na = 0, nb = 0, d2 = 0;
+        for (int i = lane; i < L.dims; i += 32) {
+          const double x = qv[i], y = dv[i];
+          dot += x * y; na += x * x; nb += y * y; d2 += (x - y) * (x - y);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+          nb += __shfl_xor_sync(0xffffffffu, nb, o);  d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        float s;
+        if (L.sim == NRTGPU_SIM_L2) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, (float)d2));
+        else if (L.sim == NRTGPU_SIM_DOT) { s = __fdiv_rn(__fadd_rn(1.0f, (float)dot), 2.0f); s = s > 0.f ? s : 0.f; }
+        else if (L.sim == NRTGPU_SIM_COSINE) { const float cs = (float)(dot / sqrt(na * nb)); s = __fdiv_rn(__fadd_rn(1.0f, cs), 2.0f); s = s > 0.f ? s : 0.f; }
+        else { const float t = (float)dot; s = t < 0.f ? __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(-1.0f, t))) : __fadd_rn(t, 1.0f); }
+        key = make_key(__fmul_rn(s, boost), doc);
+      }
+    }
+    if (lane == 0) keys[c] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort_desc(keys, kKnnExactChunk);
+  int have = 0;   // keys are > 0 for real hits, 0 for filtered / padding
+  for (int i = tid; i < L.k; i += 256) {
+    const uint64_t kk = keys[i];
+    L.keys[((size_t)sel * L.n_chunks + chunk) * L.k + i] = kk;
+    if (kk) have = i + 1;
+  }
+  have = __reduce_max_sync(0xffffffffu, have);
+  __shared__ int wmax[8];
+  if (lane == 0) wmax[warp] = have;
+  __syncthreads();
+  if (tid == 0) { int h = 0; for (int w = 0; w < 8; ++w) h = max(h, wmax[w]); L.cnt[(size_t)sel * L.n_chunks + chunk] = h; }
 }
 
 // fused path: fold the survivors of one chunk into the running best-k' list and refresh the query's threshold
@@ -266,7 +392,8 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
                            const uint8_t* h_filter, cudaStream_t st, int32_t* out_docs, float* out_scores,
                            int32_t* out_counts, const __nv_bfloat16* d_vec_bf16 = nullptr,
                            const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr, const float2* d_ab = nullptr,
-                           KnnScratch* sc = nullptr) {
+                           KnnScratch* sc = nullptr, const uint32_t* d_live_bits = nullptr, float dmax = 0.0f,
+                           int32_t* n_uncertified = nullptr) {
   KnnScratch local_scratch;   // only when the caller brings none (freed on return)
   if (!sc) sc = &local_scratch;
   const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr && d_ab != nullptr;
@@ -323,7 +450,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     if (use_tc) {
       tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
-      G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs;
+      G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs; G.live_bits = d_live_bits;
       // default: one tile per CTA, 2 CTAs/SM (measured 4.9 ms at C4); the persistent double-buffered variant measured
       // 7.5 ms -- both are bound by L2 -> SM operand traffic (48 KB per 128x256x64 k-block), see DESIGN.md 4.3
       static const bool simple_gemm = getenv("NRTGPU_KNN_GEMM_PERSISTENT") == nullptr;
@@ -347,7 +474,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       Mg.theta = dTheta; Mg.overflow = dOvf;
       knn_merge_chunk_kernel<<<nq, kKnnSelThreads, 0, st>>>(Mg);
     } else {
-      KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.vec_docs = d_vec_docs;
+      KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.live_bits = d_live_bits; S.vec_docs = d_vec_docs;
       S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
       knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
     }
@@ -367,12 +494,16 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     if (ovf) {
       if (stage_ms) for (auto& e : ev) cudaEventDestroy(e);
       return knn_search_host(d_vec, d_norm2, d_vec_docs, n, dims, sim, doc_base, n_docs, h_queries, nq, k, h_boosts, h_filter, st,
-                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms, nullptr, sc);
+                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms, nullptr, sc, d_live_bits, dmax, n_uncertified);
     }
   }
   if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
   KnnRescoreLaunch R; R.Q = dQ; R.D = d_vec; R.dims = dims; R.sim = sim; R.cand = dC; R.cand_cnt = dCn; R.kprime = kprime;
   R.vec_docs = d_vec_docs; R.doc_base = doc_base; R.boosts = dB; R.k = k; R.out_docs = dOD; R.out_scores = dOS; R.out_counts = dOC;
+  int32_t* dUnsafe = nullptr;
+  NRT_KNN_GET(14, dUnsafe, (size_t)nq * sizeof(int32_t));
+  R.unsafe = dUnsafe; R.dmax = dmax;
+  R.eps_rel = use_tc ? 0.0078125f /* bf16 operands: 2^-7 |q||d| */ : (float)dims * 1.1920929e-7f /* fp32 FMA chain: dims * 2^-23 */;
   knn_rescore_kernel<<<nq, 256, 0, st>>>(R);
   NRT_CUDA_TRY(cudaGetLastError());
   if (stage_ms) {
@@ -385,7 +516,48 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, dOD, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, dOS, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, dOC, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> unsafe((size_t)nq);
+  NRT_CUDA_TRY(cudaMemcpyAsync(unsafe.data(), dUnsafe, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaStreamSynchronize(st));
+  // ---- queries whose candidate list is not certified rank-safe (score clusters tighter than the candidate stage's
+  //      error bound, e.g. near-duplicate vectors): exact evaluation of every vector, as ExactVectorQuery does
+  std::vector<int32_t> sel;
+  for (int q = 0; q < nq; ++q) if (unsafe[(size_t)q]) sel.push_back(q);
+  if (n_uncertified) *n_uncertified = (int32_t)sel.size();
+  if (!sel.empty()) {
+    const int n_sel = (int)sel.size(), n_chunks = (n + kKnnExactChunk - 1) / kKnnExactChunk;
+    int32_t *dSel = nullptr, *dCnt = nullptr, *dXD = nullptr, *dXC = nullptr; uint64_t* dKeys = nullptr; float* dXS = nullptr;
+    NRT_KNN_GET(15, dSel, (size_t)n_sel * sizeof(int32_t));
+    NRT_CUDA_TRY(cudaMemcpyAsync(dSel, sel.data(), (size_t)n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // the slice lists can be large (n_sel * n_chunks * k keys): process the selected queries in groups that fit 256 MB
+    const size_t per_q = (size_t)n_chunks * k * sizeof(uint64_t);
+    const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_sel, ((size_t)256 << 20) / per_q));
+    NRT_KNN_GET(5, dKeys, (size_t)group * per_q);   // slot 5 (the unfused score matrix) is free by now
+    NRT_KNN_GET(1, dCnt, (size_t)group * n_chunks * sizeof(int32_t) + (size_t)group * k * 8 + (size_t)group * 4);
+    dXD = dCnt + (size_t)group * n_chunks; dXS = (float*)(dXD + (size_t)group * k); dXC = (int32_t*)(dXS + (size_t)group * k);
+    std::vector<int32_t> hd((size_t)group * k), hc((size_t)group); std::vector<float> hs((size_t)group * k);
+    for (int g0 = 0; g0 < n_sel; g0 += group) {
+      const int gn = std::min(group, n_sel - g0);
+      KnnExactLaunch X; X.Q = dQ; X.D = d_vec; X.n = n; X.dims = dims; X.sim = sim; X.qsel = dSel + g0; X.boosts = dB; X.filter = dF;
+      X.live_bits = d_live_bits; X.vec_docs = d_vec_docs; X.k = k; X.n_chunks = n_chunks; X.keys = dKeys; X.cnt = dCnt;
+      knn_exact_chunk_kernel<<<dim3((unsigned)n_chunks, (unsigned)gn), 256, 0, st>>>(X);
+      NRT_CUDA_TRY(cudaGetLastError());
+      MergeLaunch M; M.slice_keys = dKeys; M.slice_cnt = dCnt; M.n_lists = n_chunks; M.top_k = k; M.nq = gn; M.doc_base = doc_base;
+      M.out_docs = dXD; M.out_scores = dXS; M.out_counts = dXC;
+      merge_slices_kernel<<<gn, kMergeThreads, 0, st>>>(M);
+      NRT_CUDA_TRY(cudaGetLastError());
+      NRT_CUDA_TRY(cudaMemcpyAsync(hd.data(), dXD, (size_t)gn * k * 4, cudaMemcpyDeviceToHost, st));
+      NRT_CUDA_TRY(cudaMemcpyAsync(hs.data(), dXS, (size_t)gn * k * 4, cudaMemcpyDeviceToHost, st));
+      NRT_CUDA_TRY(cudaMemcpyAsync(hc.data(), dXC, (size_t)gn * 4, cudaMemcpyDeviceToHost, st));
+      NRT_CUDA_TRY(cudaStreamSynchronize(st));
+      for (int i = 0; i < gn; ++i) {
+        const int q = sel[(size_t)(g0 + i)];
+        std::memcpy(out_docs + (size_t)q * k, hd.data() + (size_t)i * k, (size_t)k * 4);
+        std::memcpy(out_scores + (size_t)q * k, hs.data() + (size_t)i * k, (size_t)k * 4);
+        out_counts[q] = hc[(size_t)i];
+      }
+    }
+  }
   return NRTGPU_OK;
 }
 

@@ -27,6 +27,7 @@ struct nrtgpu_ctx {
   int device = 0;
   int sm_count = 0;
   bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
+  bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
   bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
 };
 
@@ -51,6 +52,14 @@ __global__ void term_max_x_kernel(const int64_t* __restrict__ term_off, int n_te
   const uint8_t* nrm = norms[f];
   const float x = __fmul_rn(freq, caches[f * 256 + (nrm ? nrm[docs[p]] : 1)]);
   atomicMax(out_bits + t, __float_as_uint(x));   // x > 0: float order == unsigned order
+}
+
+// 2-bit planes: four docs per byte, min(tf, 3) each
+__global__ void plane_pack2_kernel(const uint8_t* __restrict__ planes, int64_t n_bytes_out, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bytes_out) return;
+  const uchar4 b = reinterpret_cast<const uchar4*>(planes)[i];
+  out[i] = (uint8_t)(min((int)b.x, 3) | (min((int)b.y, 3) << 2) | (min((int)b.z, 3) << 4) | (min((int)b.w, 3) << 6));
 }
 
 // dense tf plane of one term: plane[doc] = min(freq, 255) for every posting of the term (the plane is zeroed first)
@@ -139,6 +148,7 @@ struct nrtgpu_index {
   DevBuf<uint32_t> gran_tab;        // [n_rows][n_gran + 1] index-time granule offsets (skip data) of the long lists
   int32_t gran_n = 0;
   DevBuf<uint8_t> dense_tf;         // [n_planes][dense_stride]: direct-address tf bytes of the densest terms
+  DevBuf<uint8_t> dense_tf2;        // [n_planes][dense_stride / 4]: the same planes at 2 bits per doc (min(tf, 3))
   int64_t dense_stride = 0;
   int32_t n_planes = 0;
   DevBuf<uint8_t> field_min_norm;   // smallest non-zero norm byte per field (0 byte = doc lacks the field)
@@ -156,6 +166,8 @@ struct nrtgpu_index {
   CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16
   DevBuf<float2> vec_ab;            // per-vector (a, b) of the approximate score a * dot + b
   bool vec_tc = false;
+  float vec_dmax = 0.0f;    // largest vector magnitude (error bound of the kNN candidate-stage certificate)
+  int32_t knn_last_uncertified = 0;   // queries of the last kNN call that took the exact fallback
   DevBuf<float> vec_norm2;  // per-vector squared magnitude (double-accumulated, stored float) for cosine
   DevBuf<int32_t> vec_docs;
   int64_t device_bytes = 0;
@@ -174,7 +186,7 @@ struct nrtgpu_index {
     v.norms = norms_ptrs.p; v.caches = caches.p;
     v.col64 = col64_ptrs.p; v.col32 = col32_ptrs.p; v.col_has = col_has_ptrs.p;
     v.live_bits = live_bits.p;
-    v.dense_tf = dense_tf.p; v.dense_stride = dense_stride;
+    v.dense_tf = dense_tf.p; v.dense_stride = dense_stride; v.dense_tf2 = dense_tf2.p;
     v.gran_tab = gran_tab.p; v.n_gran = gran_n;
     return v;
   }
@@ -254,6 +266,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
+  { const char* e = getenv("NRTGPU_ORDER"); c->order_by_cost = e && std::strcmp(e, "cost") == 0; }
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint32_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -343,6 +356,10 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
         plane_fill_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ix->post_docs.p + off, ix->post_f8.p + off, n,
                                                                  ix->dense_tf.p + (size_t)k * stride);
       }
+      NRT_CUDA_TRY(cudaGetLastError());
+      const int64_t n2 = (int64_t)(stride / 4) * (int64_t)dense_terms.size();
+      if ((rc = ix->dense_tf2.alloc((size_t)n2))) return rc;
+      plane_pack2_kernel<<<(unsigned)((n2 + 255) / 256), 256>>>(ix->dense_tf.p, n2, ix->dense_tf2.p);
       NRT_CUDA_TRY(cudaGetLastError());
     }
   }
@@ -455,6 +472,16 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if (d->vec_docs) { if ((rc = ix->vec_docs.upload(d->vec_docs, (size_t)d->vec_count))) return rc; }
     if ((rc = ix->vec_norm2.alloc((size_t)d->vec_count))) return rc;
     if ((rc = knn_prepare_norms(ix->vectors.p, ix->vec_count, ix->vec_dims, ix->vec_norm2.p))) return rc;
+    {
+      DevBuf<unsigned int> d_mx;
+      if ((rc = d_mx.alloc(1))) return rc;
+      NRT_CUDA_TRY(cudaMemset(d_mx.p, 0, sizeof(unsigned int)));
+      knn_max_norm2_kernel<<<256, 256>>>(ix->vec_norm2.p, ix->vec_count, d_mx.p);
+      NRT_CUDA_TRY(cudaGetLastError());
+      float mx = 0.0f;
+      NRT_CUDA_TRY(cudaMemcpy(&mx, d_mx.p, sizeof(float), cudaMemcpyDeviceToHost));
+      ix->vec_dmax = std::sqrt(mx) * 1.0001f;
+    }
     if (d->vec_dims % 8 == 0) {   // TMA needs 16-byte row pitch
       if ((rc = ix->vec_bf16.alloc((size_t)d->vec_count * d->vec_dims))) return rc;
       tc::f32_to_bf16_kernel<<<1024, 256>>>(ix->vectors.p, ix->vec_bf16.p, (size_t)d->vec_count * d->vec_dims);
@@ -466,7 +493,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       ix->vec_tc = true;
     }
   }
-  ix->device_bytes = (int64_t)(ix->gran_tab.bytes() + ix->dense_tf.bytes() + ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
+  ix->device_bytes = (int64_t)(ix->gran_tab.bytes() + ix->dense_tf.bytes() + ix->dense_tf2.bytes() + ix->post_docs.bytes() + ix->post_f8.bytes() + ix->exc_pos.bytes() + ix->exc_freq.bytes() +
                                ix->caches.bytes() + ix->live_bits.bytes() + ix->vectors.bytes() + ix->vec_norm2.bytes() +
                                ix->vec_docs.bytes() + ix->vec_bf16.bytes());
   for (auto& b : ix->norms) ix->device_bytes += (int64_t)b->bytes();
@@ -616,6 +643,20 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     if (dq[qi].dense_driver) cost[qi] += ix->n_docs;
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost[a] > cost[c]; });
+  if (b->use_probe && !ix->ctx->order_by_cost) {
+    // probe kernel: inside a slice, queries that share their densest tf plane are adjacent in the queue, so the plane's
+    // bytes of the slice are gathered by CTAs that run together and stay in L2 between them (longer queries first inside
+    // a cluster, clusters of the densest -- most shared -- planes first)
+    std::vector<int64_t> ckey((size_t)nq, INT64_MAX);
+    for (int qi : order) {
+      int64_t best_n = -1;
+      for (int c = 0; c < dq[qi].n_clauses; ++c) {
+        const DevClause& x = dc[(size_t)dq[qi].clause_begin + c];
+        if (x.kind == NRTGPU_TERM && x.plane >= 0 && x.n_post > best_n) { best_n = x.n_post; ckey[(size_t)qi] = ((int64_t)(INT32_MAX - x.n_post) << 32) | (uint32_t)x.plane; }
+      }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return ckey[(size_t)a] < ckey[(size_t)c]; });
+  }
   // pure disjunctions of scoring term clauses over one text field (no deletes) run in their own kernel instantiation
   // (tf-pattern bound, deferred scoring, MAXSCORE): their work items come first
   auto is_simple = [&](int qi) {
@@ -961,7 +1002,7 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
                          ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr, ix->vec_ab.p,
-                         &ix->knn_scratch);
+                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
 }
 
 int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream, int32_t* out_docs,
@@ -975,8 +1016,10 @@ int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, 
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
                          ix->doc_base, ix->n_docs, queries, nq, k, nullptr, nullptr, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms, ix->vec_ab.p,
-                         &ix->knn_scratch);
+                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
 }
+
+int32_t nrtgpu_knn_last_uncertified(const nrtgpu_index* ix) { return ix ? ix->knn_last_uncertified : 0; }
 
 namespace {
 struct DevTmp {   // scoped device scratch for the O(k) hybrid stages

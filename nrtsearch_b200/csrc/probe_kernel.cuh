@@ -60,11 +60,12 @@ static_assert(kShortMax >= 1024, "stage too small");
 #endif
 constexpr int kR = NRT_PROBE_R;              // driver postings per thread per round (their gathers are in flight together)
 constexpr int kCand = 1024;                  // candidate buffer entries
-static_assert(kCand >= 2 * kR * kThreads, "a round must fit the candidate buffer twice");
 constexpr int kMaxTopK = kCand / 2;
 constexpr int kUbt = 6 * 6 * 6 * 6;
 constexpr int kWarmGran = v2::kWarmGran;
 constexpr uint32_t kPiece = 8192;            // bytes per bulk copy
+constexpr uint32_t kTfInexact = 0xFEu;       // tf byte of a plane probe whose 2-bit code saturated (tf >= 3): the exact byte is
+                                             // fetched from the byte plane when the doc is scored (rare); >= 5 for the bound table
 
 enum { kAbsent = 0, kLong = 1, kShort = 2, kPlane = 3, kGlobal = 4 };
 
@@ -105,7 +106,8 @@ struct alignas(128) ProbeSmem {
   // per slot (CTA-uniform, written by thread 0 / threads < kT between barriers)
   const int32_t* s_gdocs[kT];      // global postings of the list
   const uint8_t* s_gf8[kT];
-  const uint8_t* s_plane[kT];
+  const uint8_t* s_plane[kT];      // byte plane (exact min(tf, 255) per doc) of the list, or NULL
+  const uint8_t* s_plane2[kT];     // 2-bit plane (min(tf, 3), four docs per byte): what the probes gather
   float s_weight[kT];
   float s_ub[kT];
   int32_t s_kind[kT];
@@ -159,9 +161,10 @@ __device__ __noinline__ bool evaluate_doc(const ProbeLaunch& L, const ProbeSmem&
     bool present;
     float s = 0.0f;
     if (c.kind == NRTGPU_TERM) {
-      const uint32_t b = (word >> (8 * c.slot)) & 0xffu;
+      uint32_t b = (word >> (8 * c.slot)) & 0xffu;
       present = b != 0;
       if (present && c.scoring) {
+        if (b == kTfInexact && sm.s_plane[c.slot]) b = (uint32_t)__ldg(sm.s_plane[c.slot] + doc);   // saturated 2-bit code
         if (c.field != cur_field) {
           cur_field = c.field;
           const uint8_t* nrm = L.ix.norms[c.field];
@@ -217,8 +220,9 @@ __device__ __forceinline__ float score_disjunction(const ProbeLaunch& L, const P
 #pragma unroll
   for (int s = 0; s < kT; ++s) {
     if (s >= n_term) break;
-    const uint32_t b = (word >> (8 * s)) & 0xffu;
+    uint32_t b = (word >> (8 * s)) & 0xffu;
     if (b == 0) continue;
+    if (b == kTfInexact && sm.s_plane[s]) b = (uint32_t)__ldg(sm.s_plane[s] + doc);   // saturated 2-bit code: the exact byte
     const float f = (b == 255u) ? exact_freq_slow<uint32_t>(L.ix, sm.cl[sm.s_clause[s]], doc) : (float)b;
     sum += (double)bm25_score(sm.s_weight[s], f, __ldg(&L.ix.caches[sm.s_field[s] * 256 + nb]));
   }
@@ -229,7 +233,7 @@ __device__ __forceinline__ float score_disjunction(const ProbeLaunch& L, const P
 // (generic) or unscored (tf word << 32 | doc) pairs (pure disjunctions) which are scored here, one per thread, so the norm
 // loads of the whole buffer overlap. Keeps the best top_k, publishes the k-th key as the query's threshold.
 template <bool kSimple>
-__device__ __forceinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& sm, const uint8_t* norms0, int n_term,
+__device__ __noinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& sm, const uint8_t* norms0, int n_term,
                                                  bool has_after, uint64_t after_key, int top_k, uint64_t* g_theta) {
   __syncthreads();
   int n = sm.cand_count;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     }
     if (tid < ncl) sm.cl[tid] = L.clauses[cbeg + tid];
     if (tid >= 32 && tid < 32 + kT) { const int s = tid - 32; sm.s_kind[s] = kAbsent; sm.s_ia[s] = 0; sm.s_ib[s] = 0; sm.s_ra[s] = 0; sm.s_rb[s] = 0;
-                                      sm.s_plane[s] = nullptr; sm.s_gdocs[s] = nullptr; sm.s_gf8[s] = nullptr; sm.s_weight[s] = 0.f; sm.s_ub[s] = 0.f;
+                                      sm.s_plane[s] = nullptr; sm.s_plane2[s] = nullptr; sm.s_gdocs[s] = nullptr; sm.s_gf8[s] = nullptr; sm.s_weight[s] = 0.f; sm.s_ub[s] = 0.f;
                                       sm.s_clause[s] = 0; sm.s_field[s] = 0; sm.s_sdelta[s] = 0; sm.s_pbm[s] = 0; sm.s_row[s] = -1; }
     const int g_first = slice * gran_per_slice;
     const int g_count = min(gran_per_slice, L.n_gran - g_first);
@@ -374,8 +378,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       sm.s_ia[s] = a; sm.s_ib[s] = b;
       sm.s_gdocs[s] = L.ix.post_docs + c.post_base;
       sm.s_gf8[s] = L.ix.post_f8 + c.post_base;
-      const bool has_plane = c.plane >= 0 && L.ix.dense_tf != nullptr;
+      const bool has_plane = c.plane >= 0 && L.ix.dense_tf != nullptr && L.ix.dense_tf2 != nullptr;
       sm.s_plane[s] = has_plane ? L.ix.dense_tf + (size_t)c.plane * (size_t)L.ix.dense_stride : nullptr;
+      sm.s_plane2[s] = has_plane ? L.ix.dense_tf2 + (size_t)c.plane * (size_t)(L.ix.dense_stride >> 2) : nullptr;
       sm.s_kind[s] = has_plane ? kPlane : (c.gran_row >= 0 ? kLong : kShort);   // kShort may become kGlobal below
       sm.s_weight[s] = c.weight; sm.s_ub[s] = c.ub; sm.s_clause[s] = tid; sm.s_field[s] = c.field;
       sm.s_pbm[s] = (uint32_t)(c.post_base & (int64_t)(kAlign - 1)); sm.s_row[s] = c.gran_row;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     const uint8_t* norms0 = (kSimple && sm.q.single_field >= 0) ? L.ix.norms[sm.q.single_field] : nullptr;
     const uint32_t drv_mask = sm.drv_mask, ess_mask = sm.ess_mask;
     const uint32_t plane_mask = sm.plane_mask, long_mask = sm.long_mask, short_mask = sm.short_mask, global_mask = sm.global_mask;
-    const uint8_t* pl0 = sm.s_plane[0]; const uint8_t* pl1 = sm.s_plane[1]; const uint8_t* pl2 = sm.s_plane[2]; const uint8_t* pl3 = sm.s_plane[3];
+    const uint8_t* pl0 = sm.s_plane2[0]; const uint8_t* pl1 = sm.s_plane2[1]; const uint8_t* pl2 = sm.s_plane2[2]; const uint8_t* pl3 = sm.s_plane2[3];
     unsigned int my_hits = 0;
     unsigned long long dbg_post = 0; unsigned int dbg_runs = 0, dbg_rounds = 0, dbg_flush = 0, dbg_staged = 0;
     const long long t_setup = L.stats ? clock64() : 0ll;
@@ -623,84 +628,136 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       ++dbg_runs;
       // ---------------- rounds over the driver postings of the run
       const uint32_t n_total = sm.s_pre[kT];
-      const uint32_t pre1 = sm.s_pre[1], pre2 = sm.s_pre[2], pre3 = sm.s_pre[3];
       if (L.stats && tid == 0) { dbg_post += n_total; dbg_staged += sm.staged ? 1u : 0u; }
-      for (uint32_t base = 0; base < n_total; base += kR * kThreads) {
-        const unsigned long long theta = sm.theta;
-        const float theta_s = theta ? key_score(theta) : -INFINITY;
-        int32_t doc[kR]; uint32_t word[kR]; int slot[kR];
-        uint32_t pbyte[kR][kT];
-        // phase 1: fetch the driver postings (staged lists from shared memory, plane / global lists straight from HBM)
+      // No barrier between rounds: every warp streams through its postings on its own. A thread whose candidate does
+      // not fit the buffer parks it and stops; the CTA meets at the barrier below, flushes once, and the loop resumes.
+      // Driver lists are swept one after the other, so everything that depends on the leading list (what to probe,
+      // where its postings live, who owns a doc) is loop invariant.
+      int ct = 0;           // driver slot this thread is working on
+      uint32_t cb = 0;      // first posting (of the slot's run segment) of the thread's next round
+      uint64_t park[kR];
+      uint32_t pmask = 0;   // parked candidates of this thread
+      for (;;) {
+        bool full = false;
 #pragma unroll
-        for (int j = 0; j < kR; ++j) {
-          const uint32_t p = base + (uint32_t)(j * kThreads + tid);
-          slot[j] = -1; doc[j] = 0; word[j] = 0;
-          if (p < n_total) {
-            const int t = (p >= pre3) ? 3 : (p >= pre2) ? 2 : (p >= pre1) ? 1 : 0;
-            const uint32_t x = sm.s_ra[t] + (p - sm.s_pre[t]);
-            slot[j] = t;
-            uint32_t tf;
-            if (((long_mask | short_mask) >> t) & 1u) { const int i = (int)x + sm.s_sdelta[t]; doc[j] = sm.sdocs[i]; tf = sm.sf8[i]; }
-            else { doc[j] = __ldg(sm.s_gdocs[t] + x); tf = __ldg(sm.s_gf8[t] + x); }
-            word[j] = tf << (8 * t);
+        for (int j = 0; j < kR; ++j)
+          if ((pmask >> j) & 1u) {
+            const int p = atomicAdd(&sm.cand_count, 1);
+            if (p < kCand) { sm.cand[p] = park[j]; pmask &= ~(1u << j); } else full = true;
           }
-        }
-        // phase 2: plane gathers of every posting of the round (all in flight together)
+        while (!full && ct < n_term) {
+          const uint32_t n_t = ((drv_mask >> ct) & 1u) ? sm.s_rb[ct] - sm.s_ra[ct] : 0u;
+          if (cb >= n_t) { ++ct; cb = 0; continue; }
+          const int t = ct;
+          const uint32_t need = sm.s_need[t];
+          const uint32_t need_plane = need & plane_mask, need_long = need & long_mask, need_short = need & short_mask,
+                         need_glob = need & global_mask;
+          const bool t_staged = ((long_mask | short_mask) >> t) & 1u;
+          const bool t_ess = (ess_mask >> t) & 1u;
+          const uint32_t candbelow = sm.s_candbelow[t], cntbefore = sm.s_cntbefore[t];
+          const int32_t* sdoc_t = sm.sdocs + ((int)sm.s_ra[t] + sm.s_sdelta[t]);   // posting x of the run segment: sdoc_t[x]
+          const uint8_t* sf8_t = sm.sf8 + ((int)sm.s_ra[t] + sm.s_sdelta[t]);
+          const int32_t* gdoc_t = sm.s_gdocs[t] + sm.s_ra[t];
+          const uint8_t* gf8_t = sm.s_gf8[t] + sm.s_ra[t];
+          const uint32_t tshift = 8u * (uint32_t)t;
+          // software pipeline: the postings of the NEXT round are fetched before the current round is processed
+          int32_t nd[kR]; uint32_t nf[kR];
 #pragma unroll
-        for (int j = 0; j < kR; ++j) {
-          const uint32_t need = slot[j] >= 0 ? (sm.s_need[slot[j]] & plane_mask) : 0u;
-          pbyte[j][0] = (need & 1u) ? (uint32_t)__ldg(pl0 + doc[j]) : 0u;
-          pbyte[j][1] = (need & 2u) ? (uint32_t)__ldg(pl1 + doc[j]) : 0u;
-          pbyte[j][2] = (need & 4u) ? (uint32_t)__ldg(pl2 + doc[j]) : 0u;
-          pbyte[j][3] = (need & 8u) ? (uint32_t)__ldg(pl3 + doc[j]) : 0u;
-        }
-        // phase 3: searches of the staged lists (shared memory; overlaps the gathers)
-#pragma unroll
-        for (int j = 0; j < kR; ++j) {
-          if (slot[j] < 0) continue;
-          const uint32_t need = sm.s_need[slot[j]];
-          const int g = (doc[j] - slice_base) >> kLogGran;
-#pragma unroll
-          for (int u = 0; u < kT; ++u) {
-            if (!((need >> u) & 1u)) continue;
-            uint32_t b = 0;
-            if ((long_mask >> u) & 1u) {
-              const uint32_t lo = max(sm.gb[u][g], sm.s_ra[u]), hi = min(sm.gb[u][g + 1], sm.s_rb[u]);
-              if (hi > lo) b = probe_smem(sm, (int)lo + sm.s_sdelta[u], (int)hi + sm.s_sdelta[u], doc[j]);
-            } else if ((short_mask >> u) & 1u) {
-              if (sm.s_rb[u] > sm.s_ra[u]) b = probe_smem(sm, (int)sm.s_ra[u] + sm.s_sdelta[u], (int)sm.s_rb[u] + sm.s_sdelta[u], doc[j]);
-            } else if ((global_mask >> u) & 1u) {
-              if (sm.s_rb[u] > sm.s_ra[u]) b = probe_global(sm.s_gdocs[u], sm.s_gf8[u], sm.s_ra[u], sm.s_rb[u], doc[j]);
+          for (int j = 0; j < kR; ++j) {
+            const uint32_t x = cb + (uint32_t)(j * kThreads + tid);
+            nd[j] = 0; nf[j] = 0;
+            if (x < n_t) {
+              if (t_staged) { nd[j] = sdoc_t[x]; nf[j] = sf8_t[x]; } else { nd[j] = __ldg(gdoc_t + x); nf[j] = __ldg(gf8_t + x); }
             }
-            word[j] |= b << (8 * u);
           }
-        }
-        // phase 4: ownership, hit count, bound test / clause evaluation, append
+          while (!full && cb < n_t) {
+            const unsigned long long theta = sm.theta;
+            const float theta_s = theta ? key_score(theta) : -INFINITY;
+            int32_t doc[kR]; uint32_t word[kR];
+            uint32_t pbyte[kR][kT];
 #pragma unroll
-        for (int j = 0; j < kR; ++j) {
-          if (slot[j] < 0) continue;
-          const int t = slot[j];
-          const uint32_t v = word[j] | pbyte[j][0] | (pbyte[j][1] << 8) | (pbyte[j][2] << 16) | (pbyte[j][3] << 24);
-          if (kSimple) {
-            if ((v & sm.s_cntbefore[t]) == 0u) ++my_hits;
-            if (!((ess_mask >> t) & 1u) || (v & sm.s_candbelow[t]) != 0u) continue;   // counted only / emitted by a lower list
-            if (sm.ubt[__dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u)] < theta_s) continue;   // cannot reach the top-k
-            sm.cand[atomicAdd(&sm.cand_count, 1)] = ((uint64_t)v << 32) | (uint32_t)doc[j];
-          } else {
-            if ((v & sm.s_candbelow[t]) != 0u) continue;   // a lower driver list owns this doc
-            float score;
-            if (!evaluate_doc(L, sm, doc[j], v, &score)) continue;
-            ++my_hits;
-            const uint64_t key = make_key(score, doc[j]);
-            if (key > theta && (!has_after || key < after_key)) sm.cand[atomicAdd(&sm.cand_count, 1)] = key;
+            for (int j = 0; j < kR; ++j) { doc[j] = nd[j]; word[j] = nf[j] << tshift; }   // word == 0: no posting (tf >= 1)
+            // plane gathers of every posting of the round (2-bit tf codes, all in flight together)
+#pragma unroll
+            for (int j = 0; j < kR; ++j) {
+              const uint32_t d4 = (uint32_t)doc[j] >> 2;
+              pbyte[j][0] = ((need_plane & 1u) && word[j]) ? (uint32_t)__ldg(pl0 + d4) : 0u;
+              pbyte[j][1] = ((need_plane & 2u) && word[j]) ? (uint32_t)__ldg(pl1 + d4) : 0u;
+              pbyte[j][2] = ((need_plane & 4u) && word[j]) ? (uint32_t)__ldg(pl2 + d4) : 0u;
+              pbyte[j][3] = ((need_plane & 8u) && word[j]) ? (uint32_t)__ldg(pl3 + d4) : 0u;
+            }
+            // next round's postings
+            {
+              const uint32_t nb = cb + (uint32_t)(kR * kThreads);
+#pragma unroll
+              for (int j = 0; j < kR; ++j) {
+                const uint32_t x = nb + (uint32_t)(j * kThreads + tid);
+                nd[j] = 0; nf[j] = 0;
+                if (x < n_t) {
+                  if (t_staged) { nd[j] = sdoc_t[x]; nf[j] = sf8_t[x]; } else { nd[j] = __ldg(gdoc_t + x); nf[j] = __ldg(gf8_t + x); }
+                }
+              }
+            }
+            // searches of the staged lists (shared memory; overlaps the gathers)
+            if (need_long | need_short | need_glob) {
+#pragma unroll
+              for (int j = 0; j < kR; ++j) {
+                if (!word[j]) continue;
+                const int g = (doc[j] - slice_base) >> kLogGran;
+#pragma unroll
+                for (int u = 0; u < kT; ++u) {
+                  uint32_t b = 0;
+                  if ((need_long >> u) & 1u) {
+                    const uint32_t lo = max(sm.gb[u][g], sm.s_ra[u]), hi = min(sm.gb[u][g + 1], sm.s_rb[u]);
+                    if (hi > lo) b = probe_smem(sm, (int)lo + sm.s_sdelta[u], (int)hi + sm.s_sdelta[u], doc[j]);
+                  } else if ((need_short >> u) & 1u) {
+                    if (sm.s_rb[u] > sm.s_ra[u]) b = probe_smem(sm, (int)sm.s_ra[u] + sm.s_sdelta[u], (int)sm.s_rb[u] + sm.s_sdelta[u], doc[j]);
+                  } else if ((need_glob >> u) & 1u) {
+                    if (sm.s_rb[u] > sm.s_ra[u]) b = probe_global(sm.s_gdocs[u], sm.s_gf8[u], sm.s_ra[u], sm.s_rb[u], doc[j]);
+                  }
+                  word[j] |= b << (8 * u);
+                }
+              }
+            }
+            // ownership, hit count, bound test / clause evaluation, append
+#pragma unroll
+            for (int j = 0; j < kR; ++j) {
+              if (!word[j]) continue;
+              uint32_t v = word[j];
+              if (need_plane) {
+                const uint32_t sh = ((uint32_t)doc[j] & 3u) * 2u;
+#pragma unroll
+                for (int u = 0; u < kT; ++u) {
+                  const uint32_t c = (pbyte[j][u] >> sh) & 3u;   // min(tf, 3); 3 = "three or more" -> kTfInexact (resolved at scoring)
+                  v |= (c == 3u ? kTfInexact : c) << (8 * u);
+                }
+              }
+              uint64_t entry;
+              if (kSimple) {
+                if ((v & cntbefore) == 0u) ++my_hits;
+                if (!t_ess || (v & candbelow) != 0u) continue;   // counted only / emitted by a lower list
+                if (sm.ubt[__dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u)] < theta_s) continue;   // cannot reach the top-k
+                entry = ((uint64_t)v << 32) | (uint32_t)doc[j];   // scored at the next flush
+              } else {
+                if ((v & candbelow) != 0u) continue;   // a lower driver list owns this doc
+                float score;
+                if (!evaluate_doc(L, sm, doc[j], v, &score)) continue;
+                ++my_hits;
+                entry = make_key(score, doc[j]);
+                if (!(entry > theta) || (has_after && !(entry < after_key))) continue;
+              }
+              const int p = atomicAdd(&sm.cand_count, 1);
+              if (p < kCand) sm.cand[p] = entry;
+              else { park[j] = entry; pmask |= 1u << j; full = true; }
+            }
+            cb += kR * kThreads;
+            if (tid == 0) ++dbg_rounds;
           }
         }
-        ++dbg_rounds;
-        // every thread reads the count after its own appends; the last reader sees them all
-        if (__syncthreads_or(sm.cand_count > kCand - kR * kThreads)) {
-          flush_candidates<kSimple>(L, sm, norms0, n_term, has_after, after_key, L.top_k, &L.theta[qi]);
-          ++dbg_flush;
-        }
+        __syncthreads();
+        if (sm.cand_count <= kCand) break;   // nobody is parked (the count passes kCand only through a failed append)
+        flush_candidates<kSimple>(L, sm, norms0, n_term, has_after, after_key, L.top_k, &L.theta[qi]);
+        ++dbg_flush;
       }
       g0 = g1;
       first_run = false;

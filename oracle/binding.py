@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
         L.orc_vector_score_f32.restype = C.c_float
         L.orc_vector_score_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.orc_knn_exact.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                    C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+                                    C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_blend_rrf.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.orc_rescore_combine.restype = None
@@ -220,17 +220,19 @@ def vector_score(a, b, sim: int) -> np.float32:
     return np.float32(lib().orc_vector_score_f32(a.ctypes.data, b.ctypes.data, len(a), sim))
 
 
-def knn_exact(corpus, sim: int, queries, k: int, doc_base: int = 0, filter_docs=None, boosts=None, n_threads: int = 0):
+def knn_exact(corpus, sim: int, queries, k: int, doc_base: int = 0, filter_docs=None, boosts=None, n_threads: int = 0,
+              live_docs=None):
     corpus = np.ascontiguousarray(corpus, np.float32)
     queries = np.ascontiguousarray(queries, np.float32)
     n, dims = corpus.shape
     nq = queries.shape[0]
     f = None if filter_docs is None else np.ascontiguousarray(filter_docs, np.uint8)
     b = None if boosts is None else np.ascontiguousarray(boosts, np.float32)
+    lv = None if live_docs is None else np.ascontiguousarray(live_docs, np.uint8)
     docs, scores, counts = np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
     rc = lib().orc_knn_exact(corpus.ctypes.data, n, dims, sim, doc_base, None if f is None else f.ctypes.data,
                              queries.ctypes.data, nq, None if b is None else b.ctypes.data, k, n_threads,
-                             docs.ctypes.data, scores.ctypes.data, counts.ctypes.data)
+                             docs.ctypes.data, scores.ctypes.data, counts.ctypes.data, None if lv is None else lv.ctypes.data)
     if rc != 0:
         raise ValueError("orc_knn_exact failed")
     return docs, scores, counts

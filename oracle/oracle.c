@@ -446,7 +446,8 @@ float orc_vector_score_f32(const float* a, const float* b, int32_t dims, int32_t
  * every doc with a vector is scored, score = vectorScorer.score() * boost, collected top-k. */
 int orc_knn_exact(const float* corpus, int32_t n, int32_t dims, int32_t sim, int32_t doc_base,
                   const uint8_t* filter, const float* queries, int32_t nq, const float* boosts, int32_t k,
-                  int32_t n_threads, int32_t* out_docs, float* out_scores, int32_t* out_counts) {
+                  int32_t n_threads, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                  const uint8_t* live_docs) {
   if (k <= 0) return -1;
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -459,6 +460,7 @@ int orc_knn_exact(const float* corpus, int32_t n, int32_t dims, int32_t sim, int
     const float* qv = queries + (size_t)q * dims;
     for (int32_t d = 0; d < n; ++d) {
       if (filter && !filter[d]) continue;
+      if (live_docs && !live_docs[d]) continue; /* IndexSearcher acceptDocs: deleted docs are never scored */
       float s = orc_vector_score_f32(qv, corpus + (size_t)d * dims, dims, sim) * boost;
       collect(&col, d, s);
     }

@@ -105,7 +105,8 @@ float orc_vector_score_f32(const float* a, const float* b, int32_t dims, int32_t
 int orc_knn_exact(const float* corpus, int32_t n, int32_t dims, int32_t sim, int32_t doc_base,
                   const uint8_t* filter /*[n] 0/1 or NULL*/, const float* queries, int32_t nq,
                   const float* boosts /*[nq] or NULL*/, int32_t k, int32_t n_threads,
-                  int32_t* out_docs, float* out_scores, int32_t* out_counts);
+                  int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                  const uint8_t* live_docs /*[n] 0/1 or NULL: deleted docs are never hits*/);
 
 /* ---- hybrid stages ---- */
 /* weighted RRF over R retrievers; lists [R][top_in] with counts [R]; result sorted (score desc, doc asc);
