@@ -2,14 +2,18 @@
 """bench.py -- BM25 queries/s of the batched posting-traversal path (BASELINE.json configs[1]):
 10M-doc synthetic Zipf corpus, 1024 three-term disjunctive queries, top-100, on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload bm25|conj|knn|hybrid]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over the 1024-query batch. `value` = whole-job queries/s with the
-compiled batch resident in HBM; `e2e` = the same through nrtgpu_search_bool with HOST buffers (query
-upload + result download inside the timed region). N > 1: the corpus is split into N contiguous doc-range
-shards (one per GPU, index-wide BM25 statistics all-reduced at build time); every step ends with one NCCL
-all-gather of the per-shard top-k and a device-side TopDocs.merge => strong scaling.
+One "step" = one pass of the hot path over the 1024-query batch. `value` = whole-job queries/s with the compiled batch
+resident in HBM; `e2e` = the same through the public one-shot call with HOST query buffers (query upload + result
+download inside the timed region). N > 1: the corpus is split into N contiguous doc-range shards (one per GPU, index-wide
+BM25 statistics all-reduced at build time); every step ends with ONE NCCL all-gather of the packed per-shard results
+(docs, scores, counts, relation flags, totalHits) and a device-side TopDocs.merge => strong scaling.
+
+Every number is gated: before timing, the results of the first `--cpu-sample` queries are compared bit for bit with the CPU
+oracle (at N > 1 the MERGED page against the oracle run on the whole corpus by rank 0). The default N = 1 line also carries
+`extra.conj` (configs[2]) and `extra.knn` (configs[3]), each with its own gate and roofline.
 """
 import argparse
 import ctypes
@@ -24,8 +28,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NRT_ORACLE_NATIVE", "1")   # the CPU baseline is the oracle compiled -O3 -march=native ON THE BOX THAT RUNS IT
 
 ALG_BYTES_PER_POSTING = 9  # int32 doc id + int32 freq + 1 B norm gather
+INT_MAX = 2**31 - 1
 
 
 def parse():
@@ -39,10 +45,11 @@ def parse():
     ap.add_argument("--nq", type=int, default=1024)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--threshold", type=int, default=1000, help="totalHitsThreshold (reference default 1000)")
-    ap.add_argument("--cpu-sample", type=int, default=512, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="queries in the bounded CPU-baseline / gate sample")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] legs of the default N=1 line")
     ap.add_argument("--workload", default="bm25", choices=["bm25", "conj", "knn", "hybrid"],
-                    help="bm25 = configs[1] (the headline line); conj = configs[2]; knn = configs[3] (extra lines, N=1 only)")
+                    help="bm25 = configs[1] (the headline line); conj = configs[2]; knn = configs[3] (1..8 GPUs); hybrid = configs[4] shape")
     ap.add_argument("--vectors", type=int, default=1_000_000)
     ap.add_argument("--dims", type=int, default=768)
     return ap.parse_args()
@@ -52,9 +59,19 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return p, "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def static_traffic(name):
+    """Physical DRAM bytes per launch from the committed ncu --set full capture of this exact workload (a STATIC figure:
+    the bench cannot run under the profiler). Returns (bytes, source) or (None, None)."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[name]
+        return tr["dram_bytes_read"] + tr["dram_bytes_write"], "static: profiles/r2_traffic.json (%s)" % tr["source"]
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -110,78 +127,244 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_conj_queries(nq, vocab):
+# ---------------------------------------------------------------------------------------------- workloads
+
+def make_queries(nq, vocab):
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.search import BooleanQuery, Occur, TermQuery
+    terms = ix.synth_query_terms(nq, 3, vocab)   # rank log-uniform in [10, 10^4)
+    return [BooleanQuery().add(TermQuery(int(t[0])), Occur.SHOULD).add(TermQuery(int(t[1])), Occur.SHOULD)
+            .add(TermQuery(int(t[2])), Occur.SHOULD) for t in terms]
+
+
+def make_conj_queries(nq, vocab, with_filter=True):
     """configs[2]: 2 MUST terms + FILTER price in [lo, lo + 1e5] (10 % selective), SURVEY.md App. B."""
     from nrtsearch_b200 import index as ix
     from nrtsearch_b200.search import BooleanQuery, Occur, RangeQuery, TermQuery
     terms = ix.synth_query_terms(nq, 2, vocab)
     los = (ix.synth_uniform(nq, ix.SEED_RANGE) * 900_000).astype(np.int64)
-    return [BooleanQuery().add(TermQuery(int(t[0])), Occur.MUST).add(TermQuery(int(t[1])), Occur.MUST)
-            .add(RangeQuery(0, int(lo), int(lo) + 100_000), Occur.FILTER) for t, lo in zip(terms, los)]
+    qs = []
+    for t, lo in zip(terms, los):
+        q = BooleanQuery().add(TermQuery(int(t[0])), Occur.MUST).add(TermQuery(int(t[1])), Occur.MUST)
+        if with_filter:
+            q.add(RangeQuery(0, int(lo), int(lo) + 100_000), Occur.FILTER)
+        qs.append(q)
+    return qs
 
 
-def run_knn(args):
-    """configs[3]: 1M x 768 fp32 vectors, batch-1024 cosine top-100 (exact search; tensor-core candidate stage)."""
+def build_shard(args, rank, world, with_column=True):
+    """Rank r holds docs [r*N/G, (r+1)*N/G); df / docCount / sumTotalTermFreq become index-wide."""
+    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200.shards import install_global_stats, shard_range
+    lo, hi = shard_range(args.docs, rank, world)
+    sh = ix.synth_text_shard(hi - lo, args.vocab, doc_begin=lo)
+    if with_column:
+        sh.columns = [ix.synth_int_column(hi - lo, doc_begin=lo)]
+        sh.column_has = [None]
+    if world > 1:
+        import torch
+        install_global_stats(sh, device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))   # NCCL all-reduce, build time
+    else:
+        sh.term_df = np.diff(sh.term_off).astype(np.int64)
+    return sh
+
+
+def oracle_run(sh, queries, topk, threshold, mode, threads, repeat=1):
+    """The reference's CPU path restated (oracle/): mode 1 = MAXSCORE dynamic pruning for pure disjunctions, one query
+    per thread. Returns (queries/s of the last run, results, OracleIndex)."""
+    import oracle
+    from nrtsearch_b200.search import compile_queries
+    oix = oracle.OracleIndex(sh, with_impacts=True)
+    carr, ncl, qarr, nq = compile_queries(queries)
+    oracle.search_compiled(oix, carr, ncl, qarr, min(nq, 8), topk, threshold, mode, threads)  # warm
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        res = oracle.search_compiled(oix, carr, ncl, qarr, nq, topk, threshold, mode, threads)
+        dt = time.perf_counter() - t0
+    return nq / dt, res, oix
+
+
+def gate(what, got_docs, got_scores, got_counts, ref):
+    """Bit-exact doc ids + scores of the sampled queries vs the oracle; raises on any difference."""
+    n = len(ref[2])
+    assert np.array_equal(got_counts[:n], ref[2]), f"bench gate ({what}): hit counts differ from the CPU oracle"
+    for q in range(n):
+        c = int(ref[2][q])
+        assert np.array_equal(got_docs[q, :c], ref[0][q, :c]), f"bench gate ({what}): top-k doc ids of query {q} differ from the CPU oracle"
+        assert np.array_equal(got_scores[q, :c].view(np.uint32), ref[1][q, :c].view(np.uint32)), \
+            f"bench gate ({what}): scores of query {q} differ from the CPU oracle"
+    return {"queries": n, "bit_exact": True}
+
+
+def time_batch(batch, stream, steps, warmup=3):
+    """Kernel (stage 0) and merge (stage 1) time per run of a prepared batch, CUDA events on the launch stream."""
     import torch
-    import __graft_entry__ as g
-    g.build_if_needed()
+    for _ in range(warmup):
+        batch.run(stream)
+    torch.cuda.synchronize()
+    batch.reset_timing()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        batch.run(stream)
+    e1.record()
+    torch.cuda.synchronize()
+    return batch.stage_ms(0), batch.stage_ms(1), e0.elapsed_time(e1) / steps
+
+
+def workload_config(args, kind="bm25"):
+    if kind == "conj":
+        return {"workload": "configs[2]: 10M-doc synthetic, conjunctive AND (2 MUST terms) + int range FILTER, 1024-query batch top-100",
+                "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "top_k": args.topk, "sharding": f"doc-range x{args.gpus}"}
+    return {"workload": "configs[1]: 10M-doc synthetic Zipf postings, 1024-query disjunctive BM25 top-100",
+            "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "terms_per_query": 3, "top_k": args.topk,
+            "total_hits_threshold": args.threshold, "sharding": f"doc-range x{args.gpus}",
+            "l2": "posting image (GBs) >> 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------- conj leg (configs[2])
+
+def conj_leg(args, searcher, sh, stream, steps, threads, n_sample):
+    """configs[2] on the resident index: gate vs the exhaustive oracle, kernel time, SURVEY 8d byte formula
+    sum_q [ sum_t df(t) * 8 B + |intersection_q| * (T + 4) B ]."""
+    import torch
+    from nrtsearch_b200.search import RelevanceCollector
+    queries = make_conj_queries(args.nq, args.vocab)
+    coll = RelevanceCollector(args.topk, args.threshold)
+    qps_cpu, ref, _ = oracle_run(sh, queries[:n_sample], args.topk, args.threshold, 1, threads)
+    res = searcher.search_batch(queries, coll)
+    g = gate("conj", res.docs, res.scores, res.counts, ref)
+    # |intersection|: the same conjunctions without the range filter, exact counts
+    inter = searcher.search_batch(make_conj_queries(args.nq, args.vocab, with_filter=False), RelevanceCollector(1, INT_MAX)).total_hits
+    batch = searcher.prepare(queries, coll)
+    stats = batch.stats()
+    kernel_ms, merge_ms, step_ms = time_batch(batch, stream, steps)
+    batch.close()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        searcher.search_batch(queries, coll)
+    e2e = args.nq * steps / (time.perf_counter() - t0)
+    pk, src = peaks()
+    alg = float(stats["alg_postings"]) * 8.0 + float(inter.sum()) * (2 + 4) + args.nq * args.topk * 8
+    ach = alg / (kernel_ms * 1e-3) / 1e9
+    return {"metric": "conjunctive (2 MUST + range FILTER) queries/sec (batch 1024, 10M docs)", "value": args.nq / (step_ms * 1e-3),
+            "unit": "queries/s", "ms_per_step": step_ms, "config": workload_config(args, "conj"),
+            "e2e": {"value": e2e, "unit": "queries/s"}, "gate": g,
+            "roofline": {"bound": "hbm", "kernel": "posting_probe_kernel<generic> (leap-frog: the rarest MUST list leads, the other list is probed, norm / doc-value gathers only for the intersection)",
+                         "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "peak_source": src,
+                         "kernel_ms": kernel_ms, "merge_ms": merge_ms, "alg_bytes_per_launch": alg,
+                         "alg_formula": "sum_q [sum_t df(t) * 8 B + |intersection_q| * (2 + 4) B] + nq * k * 8 B (SURVEY.md 8d)",
+                         "intersection_docs": int(inter.sum())},
+            "cpu_baseline": {"value": qps_cpu, "unit": "queries/s", "cores": threads, "kind": "port",
+                             "sample": f"first {n_sample} queries, exhaustive DAAT (oracle/oracle.c), same corpus"}}
+
+
+# ---------------------------------------------------------------------------------------------- kNN (configs[3])
+
+def knn_leg(args, rank, world, local_rank, steps, warmup):
+    """configs[3]: 1M x 768 fp32 vectors, batch-1024 cosine top-100; exact search (tcgen05 bf16 candidate stage, fp64
+    re-score, rank-safety certificate). world > 1: the corpus is row-partitioned, every rank searches its shard, ONE
+    all-gather of the packed results, TopDocs.merge on the device."""
+    import torch
     import oracle
     from nrtsearch_b200 import _native, index as ix
     from nrtsearch_b200.index import HostShard
     from nrtsearch_b200.search import GpuContext, GpuIndex
+    from nrtsearch_b200.shards import PackedGather, shard_range
     n, dims, nq, k = args.vectors, args.dims, args.nq, args.topk
-    corpus = ix.synth_vectors(n, dims)
+    lo, hi = shard_range(n, rank, world)
+    corpus = ix.synth_vectors(hi - lo, dims, row_begin=lo)
     queries = ix.synth_vectors(nq, dims, seed=ix.SEED_VQUERIES)
-    sh = HostShard(n_docs=n, doc_base=0, term_off=np.zeros(1, np.int64), post_docs=np.zeros(0, np.int32),
+    sh = HostShard(n_docs=hi - lo, doc_base=lo, term_off=np.zeros(1, np.int64), post_docs=np.zeros(0, np.int32),
                    post_freqs=np.zeros(0, np.int32), fields=[], vectors=corpus, vec_similarity=ix.SIM_COSINE)
-    ctx = GpuContext(0)
+    ctx = GpuContext(local_rank)
     gix = GpuIndex(ctx, sh)
     lib = _native.gpu_lib()
+    dev = torch.device("cuda", local_rank)
     docs, scores, counts = np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
     stage = (ctypes.c_float * 3)()
     stream = torch.cuda.current_stream().cuda_stream
+    pg = PackedGather(nq, k, world, dev) if world > 1 else None
+    host_rec = torch.zeros(pg.words, dtype=torch.int32).pin_memory() if pg else None
 
     def call():
         _native.check(lib.nrtgpu_search_knn_timed(gix.handle, queries.ctypes.data, nq, k, ctypes.c_void_p(stream), docs.ctypes.data,
                                                   scores.ctypes.data, counts.ctypes.data, stage))
-    sampler = ClockSampler(0); sampler.start()
-    for _ in range(args.warmup):
-        call()
-    t_wait = time.time()
-    while not sampler.ready() and time.time() - t_wait < 1.5:
-        call()
-    gemm, sel, resc, wall = [], [], [], []
+        if pg:   # per-shard page -> packed record -> one all-gather -> device merge -> merged page on the host
+            r = host_rec.numpy()
+            r[:nq * k] = docs.reshape(-1); r[nq * k:2 * nq * k] = scores.reshape(-1).view(np.int32); r[2 * nq * k:2 * nq * k + nq] = counts
+            pg.local.copy_(host_rec, non_blocking=True)
+            pg.gather(); pg.merge_on_device(ctx, stream)
+            return pg.unpack()
+        return docs, scores, counts, None, None
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(warmup, 1)):
+        out = call()
+    uncert = int(lib.nrtgpu_knn_last_uncertified(gix.handle))
+    barrier()
+    gemm, sel, resc = [], [], []
     sampler.mark_begin()
-    for _ in range(args.steps):
-        t0 = time.perf_counter(); call(); wall.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = call()
         gemm.append(stage[0]); sel.append(stage[1]); resc.append(stage[2])
+    barrier()
+    wall = (time.perf_counter() - t0) / steps
     sampler.mark_end()
-    clocks = sampler.stop()
-    ns = min(32, nq)
-    wd, ws, wc = oracle.knn_exact(corpus, ix.SIM_COSINE, queries[:ns], k, n_threads=os.cpu_count() or 1)
-    recall = float(np.mean([len(set(docs[q]) & set(wd[q])) / k for q in range(ns)]))
-    t0 = time.perf_counter(); oracle.knn_exact(corpus, ix.SIM_COSINE, queries[:ns], k, n_threads=os.cpu_count() or 1)
-    cpu_qps = ns / (time.perf_counter() - t0)
-    gemm_ms, dev_ms, wall_ms = float(np.mean(gemm)), float(np.mean(gemm) + np.mean(sel) + np.mean(resc)), float(np.mean(wall)) * 1e3
-    try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); peak, src = float(pk["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
-    except Exception:
-        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
-    flops = 2.0 * nq * n * dims
-    print(json.dumps({
-        "metric": "kNN queries/sec (batch 1024, 1M x 768 cosine top-100, exact)", "value": nq / (dev_ms * 1e-3), "unit": "queries/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16 candidates + f64 exact re-score", "data": "synthetic",
-        "config": {"workload": "configs[3]: 1M x 768-d fp32 vectors, batch-1024 cosine top-100", "vectors": n, "dims": dims, "batch": nq, "top_k": k},
-        "e2e": {"value": nq / (wall_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * dims * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4},
-        "recall_at_k_vs_exact": recall,
-        "roofline": {"bound": "tensor", "kernel": "knn_gemm_bf16_kernel (tcgen05 UMMA 128x256x16, TMEM accumulators, TMA operands)",
-                     "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak,
-                     "traffic": None, "peak_source": src, "gemm_ms": gemm_ms, "select_ms": float(np.mean(sel)), "rescore_ms": float(np.mean(resc))},
-        "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
-                         "sample": f"{ns} queries, exact fp64 brute force (oracle/oracle.c), same corpus"},
-        "clocks": clocks}))
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = float(np.mean(gemm) + np.mean(sel) + np.mean(resc))
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([wall, dev_ms, float(np.mean(gemm))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, dev_ms, gemm_ms = float(t[0]), float(t[1]), float(t[2])
+    else:
+        gemm_ms = float(np.mean(gemm))
+    line = None
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        whole = corpus if world == 1 else ix.synth_vectors(n, dims)
+        ns = min(32, nq)
+        t0 = time.perf_counter()
+        wd, ws, wc = oracle.knn_exact(whole, ix.SIM_COSINE, queries[:ns], k, n_threads=threads)
+        cpu_qps = ns / (time.perf_counter() - t0)
+        gd, gs = out[0], out[1]
+        recall = float(np.mean([len(set(gd[q]) & set(wd[q])) / k for q in range(ns)]))
+        bad = [q for q in range(ns) if not np.array_equal(gd[q], wd[q])]
+        for q in bad:   # ids may differ only inside a score tie band (1e-5 relative), as in tests/test_gpu_knn.py
+            np.testing.assert_allclose(np.sort(gs[q])[::-1], ws[q], rtol=1e-5)
+            assert set(gd[q]) == set(wd[q]) or abs(gs[q, -1] - ws[q, -1]) <= 1e-5 * abs(ws[q, -1]), "bench gate (knn): ids differ from the exact oracle"
+        np.testing.assert_allclose(gs[:ns], ws, rtol=1e-5, err_msg="bench gate (knn): scores differ from the exact oracle")
+        pk, src = peaks()
+        flops = 2.0 * nq * n * dims
+        ach = flops / world / (gemm_ms * 1e-3) / 1e12   # per GPU: every rank multiplies the batch by its 1/world of the corpus
+        line = {"metric": "kNN queries/sec (batch 1024, 1M x 768 cosine top-100, exact)", "value": nq / (dev_ms * 1e-3) if world == 1 else nq / wall,
+                "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms if world == 1 else wall * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 candidates + f64 exact re-score",
+                "data": "synthetic",
+                "config": {"workload": "configs[3]: 1M x 768-d fp32 vectors, batch-1024 cosine top-100", "vectors": n, "dims": dims, "batch": nq,
+                           "top_k": k, "sharding": f"row-partition x{world}"},
+                "e2e": {"value": nq / wall, "unit": "queries/s", "h2d_bytes_per_step": nq * dims * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4},
+                "recall_at_k_vs_exact": recall,
+                "gate": {"queries": ns, "ids_equal_oracle": ns - len(bad), "tie_band_only": len(bad), "scores_rtol": 1e-5},
+                "certificate": {"uncertified_queries": uncert, "of": nq,
+                                "rule": "every vector outside the k' = 4k candidate list proven below the k-th exact score with the bf16 error bound 2^-7 |q||d|; rejected queries re-run exactly"},
+                "roofline": {"bound": "tensor", "kernel": "knn_gemm_bf16_kernel (tcgen05 UMMA 128x256x16, TMEM accumulators, TMA operands, fused top-k' epilogue)",
+                             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                             "peak_source": src + " burst", "gemm_ms": gemm_ms, "select_ms": float(np.mean(sel)), "rescore_ms": float(np.mean(resc))},
+                "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                 "sample": f"{ns} queries, exact fp64 brute force (oracle/oracle.c), same corpus"},
+                "clocks": clocks}
     gix.close(); ctx.close()
+    return line
 
 
 def run_hybrid(args):
@@ -228,56 +411,25 @@ def run_hybrid(args):
     gix.close(); ctx.close()
 
 
-def make_queries(nq, vocab):
-    from nrtsearch_b200 import index as ix
-    from nrtsearch_b200.search import BooleanQuery, Occur, TermQuery
-    terms = ix.synth_query_terms(nq, 3, vocab)   # rank log-uniform in [10, 10^4)
-    return [BooleanQuery().add(TermQuery(int(t[0])), Occur.SHOULD).add(TermQuery(int(t[1])), Occur.SHOULD)
-            .add(TermQuery(int(t[2])), Occur.SHOULD) for t in terms]
-
-
-def build_shard(args, rank, world):
-    """Rank r holds docs [r*N/G, (r+1)*N/G); df / docCount / sumTotalTermFreq become index-wide."""
-    from nrtsearch_b200 import index as ix
-    from nrtsearch_b200.shards import install_global_stats, shard_range
-    lo, hi = shard_range(args.docs, rank, world)
-    sh = ix.synth_text_shard(hi - lo, args.vocab, doc_begin=lo)
-    if world > 1:
-        import torch
-        install_global_stats(sh, device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))   # NCCL all-reduce, build time
-    else:
-        sh.term_df = np.diff(sh.term_off).astype(np.int64)
-    return sh
-
-
-def cpu_baseline(sh, queries, args, n_sample, threads):
-    """The reference's CPU path restated (oracle/, MAXSCORE dynamic pruning, one query per thread)."""
-    import oracle
-    from nrtsearch_b200.search import compile_queries
-    oix = oracle.OracleIndex(sh, with_impacts=True)
-    sample = queries[:n_sample]
-    carr, ncl, qarr, nq = compile_queries(sample)
-    oracle.search_compiled(oix, carr, ncl, qarr, min(nq, 8), args.topk, args.threshold, 1, threads)  # warm
-    t0 = time.perf_counter()
-    res = oracle.search_compiled(oix, carr, ncl, qarr, nq, args.topk, args.threshold, 1, threads)
-    dt = time.perf_counter() - t0
-    return nq / dt, res, oix
-
+# ---------------------------------------------------------------------------------------------- reference arm
 
 def run_reference(args, rank, world):
+    """The reference's CPU path (restated: oracle/oracle.c, NOT Lucene -- no JVM / lucene-core jar in this image) on all
+    host threads, same config / metric; each step = a bounded sample (the first --cpu-sample queries)."""
     if rank != 0:
         return
     import __graft_entry__ as g
     g.build_if_needed()
     threads = os.cpu_count() or 1
-    sh = build_shard(args, 0, 1)
-    queries = make_queries(args.nq, args.vocab)
+    sh = build_shard(args, 0, 1, with_column=args.workload == "conj")
+    conj = args.workload == "conj"
+    queries = make_conj_queries(args.nq, args.vocab) if conj else make_queries(args.nq, args.vocab)
     n_sample = min(args.cpu_sample, args.nq)
-    times = []
     import oracle
     from nrtsearch_b200.search import compile_queries
     oix = oracle.OracleIndex(sh, with_impacts=True)
     carr, ncl, qarr, nq = compile_queries(queries[:n_sample])
+    times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         oracle.search_compiled(oix, carr, ncl, qarr, nq, args.topk, args.threshold, 1, threads)
@@ -290,32 +442,24 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "BM25 queries/sec (batch 1024, 10M docs)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * args.nq / n_sample,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": workload_config(args, args.workload),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "restated CPU oracle (oracle/oracle.c), NOT Lucene: no JVM / lucene-core jar exists in this image",
+        "note": "restated CPU oracle (oracle/oracle.c, -O3 -march=native), NOT Lucene: no JVM / lucene-core jar exists in this image",
     }))
 
 
-def workload_config(args):
-    if getattr(args, "workload", "bm25") == "conj":
-        return {"workload": "configs[2]: 10M-doc synthetic, conjunctive AND (2 MUST terms) + int range FILTER, 1024-query batch top-100",
-                "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "top_k": args.topk, "sharding": f"doc-range x{args.gpus}"}
-    return {"workload": "configs[1]: 10M-doc synthetic Zipf postings, 1024-query disjunctive BM25 top-100",
-            "docs": args.docs, "vocab": args.vocab, "batch": args.nq, "terms_per_query": 3, "top_k": args.topk,
-            "total_hits_threshold": args.threshold, "sharding": f"doc-range x{args.gpus}",
-            "l2": "posting image (GBs) >> 126 MB L2; no flush needed"}
-
+# ---------------------------------------------------------------------------------------------- main line
 
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":   # torchrun pins 1 thread: the corpus generators are OpenMP
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     if args.impl == "reference":
         return run_reference(args, rank, world)
-    if args.workload == "knn":
-        return run_knn(args) if rank == 0 else None
     if args.workload == "hybrid":
         return run_hybrid(args) if rank == 0 else None
 
@@ -324,6 +468,7 @@ def main():
     g.build_if_needed()
     from nrtsearch_b200 import _native
     from nrtsearch_b200.search import GpuContext, GpuIndex, GpuIndexSearcher, RelevanceCollector, compile_queries
+    from nrtsearch_b200.shards import PackedGather, unpack_record
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; nrtsearch_b200 has no CPU fallback")
@@ -333,18 +478,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if args.workload == "knn":
+        line = knn_leg(args, rank, world, local_rank, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
+    threads = os.cpu_count() or 1
+    conj = args.workload == "conj"
     t_build = time.perf_counter()
     sh = build_shard(args, rank, world)
-    if args.workload == "conj":
-        from nrtsearch_b200 import index as ix
-        from nrtsearch_b200.shards import shard_range
-        lo_, hi_ = shard_range(args.docs, rank, world)
-        sh.columns = [ix.synth_int_column(hi_ - lo_, doc_begin=lo_)]
-        sh.column_has = [None]
-        queries = make_conj_queries(args.nq, args.vocab)
-    else:
-        queries = make_queries(args.nq, args.vocab)
+    queries = make_conj_queries(args.nq, args.vocab) if conj else make_queries(args.nq, args.vocab)
     ctx = GpuContext(local_rank)
     gix = GpuIndex(ctx, sh)
     searcher = GpuIndexSearcher(gix)
@@ -352,40 +498,43 @@ def main():
     batch = searcher.prepare(queries, coll)
     build_s = time.perf_counter() - t_build
     stats = batch.stats()
+    n_postings, dev_bytes = int(sh.term_off[-1]), gix.device_bytes
     nq, k = args.nq, args.topk
     lib = _native.gpu_lib()
 
-    # device buffers (torch = memory + streams plumbing only)
-    from nrtsearch_b200.shards import TopKGather
-    tg = TopKGather(nq, k, world, dev)
-    loc_docs, loc_scores, loc_counts = tg.loc_docs, tg.loc_scores, tg.loc_counts
-    batch.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
+    # device buffers (torch = memory + streams + the collective: plumbing only)
+    pg = PackedGather(nq, k, world, dev)
+    batch.bind_packed(pg.local.data_ptr())
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         batch.run(stream)
         if world > 1:
-            tg.gather()                        # ONE exchange step: NCCL all-gather of the per-shard top-k
-            tg.merge_on_device(ctx, stream)    # TopDocs.merge on every rank
+            pg.gather()                        # ONE exchange step: NCCL all-gather of the packed per-shard results
+            pg.merge_on_device(ctx, stream)    # TopDocs.merge on every rank
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness gate before any number is reported (rank 0, N == 1: vs the oracle on a sample)
-    cpu = None
-    if rank == 0 and world == 1:
-        n_sample = min(args.cpu_sample, nq)
-        qps_cpu, ref, _ = cpu_baseline(sh, queries, args, n_sample, os.cpu_count() or 1)
-        cpu = {"value": qps_cpu, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"first {n_sample} of the {nq} queries, MAXSCORE-pruned DAAT (oracle/oracle.c mode 1), same corpus"}
+    # ---- correctness gate before any number is reported: the (merged) page of the first queries vs the CPU oracle
+    #      run on the WHOLE corpus (rank 0; bit-exact ids + scores), at every N
+    cpu, gate_info = None, None
+    n_sample = min(args.cpu_sample, nq)
+    step(); barrier()
+    if rank == 0:
+        whole = sh if world == 1 else build_shard(args, 0, 1)
+        qps_cpu, ref, _ = oracle_run(whole, queries[:n_sample], k, args.threshold, 1, threads, repeat=3 if world == 1 else 1)
+        if world == 1:
+            cpu = {"value": qps_cpu, "unit": "queries/s", "cores": threads, "kind": "port",
+                   "sample": f"first {n_sample} of the {nq} queries, %s (oracle/oracle.c, -O3 -march=native), same corpus"
+                             % ("exhaustive DAAT" if conj else "MAXSCORE-pruned DAAT, mode 1")}
         if not args.no_check:
-            step(); torch.cuda.synchronize()
-            got_docs = loc_docs.cpu().numpy().reshape(nq, k)[:n_sample]
-            got_scores = loc_scores.cpu().numpy().reshape(nq, k)[:n_sample]
-            assert np.array_equal(got_docs, ref[0]), "bench: GPU top-k doc ids differ from the CPU oracle"
-            assert np.array_equal(got_scores.view(np.uint32), ref[1].view(np.uint32)), "bench: GPU scores differ from the oracle"
+            gd, gs, gc, gf, gt = pg.unpack(pg.merged if world > 1 else pg.local)
+            gate_info = gate(f"{args.workload} N={world}", gd, gs, gc, ref)
+            gate_info["against"] = "oracle on the whole corpus" + (" (merged page after the all-gather)" if world > 1 else "")
+        del whole
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -424,46 +573,34 @@ def main():
     ms_per_step = ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
 
-    # ---- the same batch with exact counts (ScoreMode.COMPLETE: every posting swept, no MAXSCORE): the exhaustive
-    #      kernel's roofline, reported beside the default TOP_SCORES run
+    # ---- the same batch with exact counts (ScoreMode.COMPLETE): the exhaustive figure SURVEY.md 8d asks for
     exh_ms = None
-    if args.threshold != 2**31 - 1:
-        bex = searcher.prepare(queries, RelevanceCollector(args.topk, 2**31 - 1))
-        bex.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
-        for _ in range(2):
-            bex.run(stream)
-        torch.cuda.synchronize()
-        bex.reset_timing()
-        for _ in range(5):
-            bex.run(stream)
-        torch.cuda.synchronize()
-        exh_ms = bex.stage_ms(0)
+    if args.threshold != INT_MAX and not conj:
+        bex = searcher.prepare(queries, RelevanceCollector(args.topk, INT_MAX))
+        exh_ms, _, _ = time_batch(bex, stream, 5, warmup=2)
         bex.close()
-        batch.bind_output(loc_docs.data_ptr(), loc_scores.data_ptr(), loc_counts.data_ptr())
         if world > 1:
             t = torch.tensor([exh_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             exh_ms = float(t[0])
 
-    # ---- e2e: the public one-shot call with HOST buffers, every step: H2D plan + D2H results
+    # ---- e2e: the public one-shot call with HOST query buffers every step: H2D plan, kernels, (all-gather + merge on
+    #      the device at N > 1 -- results stay on the device until the merged page), D2H of the final page
     carr, ncl, qarr, _ = compile_queries(queries)
     h2d = ctypes.sizeof(carr) + ctypes.sizeof(qarr)
-    d2h = nq * k * 8 + nq * (4 + 8)
-    from nrtsearch_b200.search import BatchResult
-    out = BatchResult(np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32),
-                      np.zeros(nq, np.int64), np.zeros(nq, np.uint8))
+    d2h = int(pg.words) * 4
+    host_rec = torch.zeros(pg.words, dtype=torch.int32).pin_memory()
 
     def e2e_step():
-        _native.check(lib.nrtgpu_search_bool(gix.handle, carr, ncl, qarr, nq, k, args.threshold, 0, ctypes.c_void_p(stream),
-                                             out.docs.ctypes.data, out.scores.ctypes.data, out.counts.ctypes.data,
-                                             out.total_hits.ctypes.data, out.relation.ctypes.data))
-        if world > 1:   # per-shard host results -> the merged page needs the gather too
-            loc_docs.copy_(torch.from_numpy(out.docs.reshape(-1)), non_blocking=True)
-            loc_scores.copy_(torch.from_numpy(out.scores.reshape(-1)), non_blocking=True)
-            loc_counts.copy_(torch.from_numpy(out.counts), non_blocking=True)
-            tg.gather()
-            tg.merge_on_device(ctx, stream)
-            tg.fin_docs.cpu(); tg.fin_scores.cpu()
+        _native.check(lib.nrtgpu_search_bool_packed(gix.handle, carr, ncl, qarr, nq, k, args.threshold, 0, None, ctypes.c_void_p(stream),
+                                                    pg.local.data_ptr()))
+        if world > 1:
+            pg.gather()
+            pg.merge_on_device(ctx, stream)
+            host_rec.copy_(pg.merged, non_blocking=True)
+        else:
+            host_rec.copy_(pg.local, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     e2e_step()
     barrier()
@@ -477,44 +614,67 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_qps = nq * args.steps / e2e_s
+    e2e_gate = None
+    if rank == 0 and not args.no_check:   # the e2e path returns the same page
+        ed, es, ec, _, _ = unpack_record(host_rec.numpy(), nq, k)
+        e2e_gate = gate(f"{args.workload} e2e N={world}", ed, es, ec, ref)["bit_exact"]
+
+    extra = None
+    if rank == 0 and world == 1 and not conj and not args.no_extra:
+        extra = {"conj": conj_leg(args, searcher, sh, stream, max(5, args.steps // 2), threads, min(256, n_sample))}
+    batch.close()
+    gix.close()
+    if rank == 0 and world == 1 and not conj and not args.no_extra:
+        del sh
+        ctx.close()
+        ctx = None
+        extra["knn"] = knn_leg(args, 0, 1, local_rank, max(5, args.steps // 4), 2)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        alg_bytes = alg_postings_total / world * ALG_BYTES_PER_POSTING + nq * k * 8   # per launch (per GPU)
-        traffic = None   # physical DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["posting_stream_kernel"]
-            if (world == 1 and args.workload == "bm25" and args.docs == 10_000_000 and args.vocab == 1_000_000 and nq == 1024
-                    and k == 100 and args.threshold == 1000):
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except Exception:
-            pass
+        pk, peak_src = peaks()
+        peak = pk["hbm_gbs"]
+        per_gpu_postings = alg_postings_total / world
+        if conj:
+            alg_bytes = per_gpu_postings * 8 + nq * k * 8   # + the intersection gathers, reported by the default line's extra.conj
+        else:
+            alg_bytes = per_gpu_postings * ALG_BYTES_PER_POSTING + nq * k * 8   # per launch (per GPU)
+        traffic, traffic_src = (None, None)
+        exh_traffic = None
+        if world == 1 and not conj and args.docs == 10_000_000 and args.vocab == 1_000_000 and nq == 1024 and k == 100 and args.threshold == 1000:
+            traffic, traffic_src = static_traffic("posting_probe_kernel<simple> TOP_SCORES")
+            exh_traffic, _ = static_traffic("posting_probe_kernel<simple> COMPLETE")
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        kernel_name = ("posting_probe_kernel<generic>" if conj else "posting_probe_kernel<simple>") + \
+            " (persistent, data-parallel over the driver postings: 2-bit tf-plane gathers / granule-narrowed searches of TMA-staged lists, MAXSCORE roles, BM25 + exact top-k)"
         line = {
             "metric": "BM25 queries/sec (batch 1024, 10M docs)", "value": qps, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": workload_config(args, args.workload),
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "gate_bit_exact": e2e_gate},
             "gpu_launches": stats["launches_per_run"] * args.steps + (args.steps if world > 1 else 0),
-            "roofline": {"bound": "hbm", "kernel": "posting_stream_kernel<simple> (TMA-streamed posting traversal: window scatter / tf-plane / sparse merge modes + BM25 + exact top-k)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "gate": gate_info,
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_kind": "effective: ALGORITHMIC bytes of every posting of the batch (9 B each, SURVEY.md 8d) / kernel time; MAXSCORE lets the kernel skip most of them, as the reference does",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "physical_frac": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src, "kernel_ms": kernel_ms, "merge_ms": merge_ms,
-                         "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": alg_postings_total / world,
-                         "mode": "TOP_SCORES (totalHitsThreshold %d, the reference default: once a query has that many hits, lists whose score bounds sum below theta stop driving and are only looked up -- MAXSCORE, as Lucene does; achieved/frac here divide the ALGORITHMIC bytes of every posting of the batch by the kernel time, the every-posting-swept figure is under exhaustive)" % args.threshold
-                                 if args.threshold != 2**31 - 1 else "COMPLETE (every posting swept)",
+                         "alg_bytes_per_launch": alg_bytes, "alg_postings_per_launch": per_gpu_postings,
+                         "mode": ("TOP_SCORES (totalHitsThreshold %d, the reference default)" % args.threshold) if args.threshold != INT_MAX else "COMPLETE (exact counts)",
                          "exhaustive": None if exh_ms is None else
-                                       {"kernel_ms": exh_ms, "achieved": alg_bytes / (exh_ms * 1e-3) / 1e9,
-                                        "frac": alg_bytes / (exh_ms * 1e-3) / 1e9 / peak}},
+                                       {"mode": "ScoreMode.COMPLETE: exact totalHits for every query (inclusion by ownership; a dense non-essential list contributes its posting count unread)",
+                                        "kernel_ms": exh_ms, "achieved": alg_bytes / (exh_ms * 1e-3) / 1e9,
+                                        "frac": alg_bytes / (exh_ms * 1e-3) / 1e9 / peak, "traffic": exh_traffic,
+                                        "physical_frac": None if exh_traffic is None else exh_traffic / (exh_ms * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "index": {"postings": int(sh.term_off[-1]), "device_bytes": gix.device_bytes, "build_s": build_s,
-                      "work_items": stats["work_items"]},
+            "index": {"postings": n_postings, "device_bytes": dev_bytes, "build_s": build_s, "work_items": stats["work_items"]},
+            "extra": extra,
         }
         print(json.dumps(line))
-    batch.close()
-    gix.close()
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

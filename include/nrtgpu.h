@@ -42,7 +42,8 @@ typedef enum {
   NRTGPU_ERR_INVALID = 1,      /* IllegalArgumentException on the Java side */
   NRTGPU_ERR_CUDA = 2,         /* -> Status.INTERNAL (SearchHandler.java:136-145) */
   NRTGPU_ERR_UNSUPPORTED = 3,  /* query shape outside the GPU path: caller falls through to Lucene */
-  NRTGPU_ERR_OOM = 4
+  NRTGPU_ERR_OOM = 4,
+  NRTGPU_ERR_TIMEOUT = 5       /* CollectionTimeoutException (SearchCutoffWrapper.java:164-174, noPartialResults) */
 } nrtgpu_status;
 
 typedef struct nrtgpu_ctx nrtgpu_ctx;     /* one per (process, device) */
@@ -134,6 +135,41 @@ int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n
                        float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
                        uint8_t* out_relation);
 
+/* Deadline and terminateAfter of a search (DocCollector config: timeoutSec, terminateAfter, terminateAfterMaxRecallCount,
+ * disallowPartialResults -- reference src/main/java/com/yelp/nrtsearch/server/search/collectors/CollectorCreatorContext.java:36-53,
+ * wrappers SearchCutoffWrapper.java:164-202 and TerminateAfterWrapper.java:85-162).
+ *  - timeout_sec > 0: the timer starts when the first work item of the batch starts on the device (elapsed_sec = time the
+ *    request already spent before the call is subtracted); it is checked at every work-item boundary ((query, <= 512K-doc
+ *    slice): the reference checks per segment and, optionally, every timeoutCheckEvery docs). Work items claimed after the
+ *    deadline are skipped: the query returns the hits collected so far with out_hit_timeout = 1 and relation GTE, or, with
+ *    disallow_partial_results, the call fails with NRTGPU_ERR_TIMEOUT ("Search collection exceeded timeout of ...s").
+ *  - terminate_after > 0: a query that has collected that many hits takes no further work items; whenever more than
+ *    terminate_after docs match, out_terminated_early = 1, relation GTE and totalHits = hits counted, capped at
+ *    terminate_after_max_recall_count. (The reference's slices race on one AtomicInteger, so WHICH docs are collected
+ *    before the cut is timing dependent there too; here the cut falls on work-item boundaries.)
+ * Both apply to queries the posting-probe kernel runs (<= 4 term clauses led by a posting list); others ignore them. */
+typedef struct {
+  double timeout_sec;                       /* 0: none */
+  double elapsed_sec;                       /* already spent by the request before this call */
+  int32_t disallow_partial_results;
+  int32_t terminate_after;                  /* 0: none */
+  int32_t terminate_after_max_recall_count; /* 0: = terminate_after */
+} nrtgpu_search_limits;
+
+/* nrtgpu_search_bool + limits; out_hit_timeout / out_terminated_early [nq] may be NULL */
+int nrtgpu_search_bool_ex(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                          const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                          int32_t total_hits_threshold, int32_t flags, const nrtgpu_search_limits* limits,
+                          void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                          int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
+                          uint8_t* out_terminated_early);
+/* same search with HOST query buffers, results left on the DEVICE in one packed record (see nrtgpu_packed_words): the
+ * multi-GPU request path (the caller all-gathers the record on `stream`, then nrtgpu_merge_topk_packed). Synchronises. */
+int nrtgpu_search_bool_packed(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                              const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                              int32_t total_hits_threshold, int32_t flags, const nrtgpu_search_limits* limits,
+                              void* stream, int32_t* d_record);
+
 /* Split form: compile+upload once, launch many times with everything resident in HBM. */
 int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
                          const nrtgpu_query* queries, int32_t nq, int32_t top_k,
@@ -141,11 +177,27 @@ int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
 int nrtgpu_batch_run(nrtgpu_batch* b, void* stream);   /* asynchronous: kernels only */
 int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream, int32_t* out_docs, float* out_scores,
                        int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation);
+int nrtgpu_batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* limits);   /* NULL clears; applies to later runs */
+int nrtgpu_batch_fetch_ex(nrtgpu_batch* b, void* stream, int32_t* out_docs, float* out_scores,
+                          int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation,
+                          uint8_t* out_hit_timeout, uint8_t* out_terminated_early);
 /* device pointers of the last run's results: uint64 keys are not exposed; these are the final arrays */
 int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts);
 /* redirect the final (docs, scores, counts) of subsequent runs into caller-owned DEVICE buffers
  * ([nq*top_k], [nq*top_k], [nq]); NULLs restore the internal buffers */
 int nrtgpu_batch_bind_output(nrtgpu_batch* b, int32_t* d_docs, float* d_scores, int32_t* d_counts);
+/* Packed per-shard result record: the ONE buffer a multi-GPU step all-gathers (docs, scores, counts, relation /
+ * terminated flags and totalHits of every query). int32 words:
+ *   docs [nq*top_k] | scores [nq*top_k] (float bits) | counts [nq] | flags [nq] (bit 0: relation GTE, bit 1: terminated
+ *   early) | pad to 8 bytes | totalHits [nq] int64.      nrtgpu_packed_words = record size in words.
+ * nrtgpu_batch_bind_packed redirects the results of subsequent runs into a caller-owned DEVICE record (NULL restores
+ * the internal buffers); nrtgpu_merge_topk_packed is TopDocs.merge over n_lists gathered records (totalHits summed,
+ * relation GTE if any shard's is: LazyQueueTopScoreDocCollectorManager.java:137-144) into one record, on the device. */
+int64_t nrtgpu_packed_words(int32_t nq, int32_t top_k);
+int nrtgpu_batch_bind_packed(nrtgpu_batch* b, int32_t* d_record);
+int nrtgpu_merge_topk_packed(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k, const int32_t* d_records,
+                             int32_t* d_out_record, void* stream);
+
 /* stats of the compiled batch: algorithmic postings (sum of df over all term clauses), kernel launches per run */
 int nrtgpu_batch_stats(const nrtgpu_batch* b, int64_t* alg_postings, int32_t* launches_per_run,
                        int64_t* work_items);

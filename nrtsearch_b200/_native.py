@@ -23,6 +23,10 @@ class NrtGpuUnsupported(NrtGpuError):
     """Query shape outside the GPU path (the Java adaptor would fall through to Lucene)."""
 
 
+class CollectionTimeoutException(NrtGpuError):
+    """SearchCutoffWrapper.CollectionTimeoutException: the deadline passed and partial results are disallowed."""
+
+
 def _load(name: str) -> C.CDLL:
     path = os.path.join(_HERE, name)
     if name == "libnrtgpu.so" and os.environ.get("NRTGPU_LIB_PATH"):   # kernel-variant experiments only
@@ -57,6 +61,11 @@ class Clause(C.Structure):
                 ("lo", C.c_int64), ("hi", C.c_int64)]
 
 
+class SearchLimits(C.Structure):
+    _fields_ = [("timeout_sec", C.c_double), ("elapsed_sec", C.c_double), ("disallow_partial_results", C.c_int32),
+                ("terminate_after", C.c_int32), ("terminate_after_max_recall_count", C.c_int32)]
+
+
 class Query(C.Structure):
     _fields_ = [("clause_begin", C.c_int32), ("clause_end", C.c_int32), ("min_should_match", C.c_int32),
                 ("has_after", C.c_int32), ("after_doc", C.c_int32), ("after_score", C.c_float)]
@@ -68,7 +77,7 @@ NRTGPU_SYMBOLS = [
     "nrtgpu_index_close", "nrtgpu_index_device_bytes", "nrtgpu_search_bool", "nrtgpu_batch_prepare",
     "nrtgpu_batch_run", "nrtgpu_batch_fetch", "nrtgpu_batch_device_results", "nrtgpu_batch_stats",
     "nrtgpu_batch_stage_ms", "nrtgpu_batch_reset_timing", "nrtgpu_batch_bind_output", "nrtgpu_batch_free", "nrtgpu_search_knn", "nrtgpu_search_knn_timed", "nrtgpu_merge_topk_device",
-    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified",
+    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified", "nrtgpu_packed_words", "nrtgpu_search_bool_ex", "nrtgpu_search_bool_packed", "nrtgpu_batch_set_limits", "nrtgpu_batch_fetch_ex", "nrtgpu_batch_bind_packed", "nrtgpu_merge_topk_packed",
 ]
 
 _gpu = None
@@ -107,6 +116,16 @@ def gpu_lib() -> C.CDLL:
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nrtgpu_search_knn_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]
+        lib.nrtgpu_search_bool_ex.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_int32, C.POINTER(SearchLimits), C.c_void_p] + [C.c_void_p] * 7
+        lib.nrtgpu_search_bool_packed.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32,
+                                                  C.c_int32, C.c_int32, C.POINTER(SearchLimits), C.c_void_p, C.c_void_p]
+        lib.nrtgpu_batch_set_limits.argtypes = [C.c_void_p, C.POINTER(SearchLimits)]
+        lib.nrtgpu_batch_fetch_ex.argtypes = [C.c_void_p] * 9
+        lib.nrtgpu_packed_words.argtypes = [C.c_int32, C.c_int32]
+        lib.nrtgpu_packed_words.restype = C.c_int64
+        lib.nrtgpu_batch_bind_packed.argtypes = [C.c_void_p, C.c_void_p]
+        lib.nrtgpu_merge_topk_packed.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nrtgpu_knn_last_uncertified.argtypes = [C.c_void_p]
         lib.nrtgpu_knn_last_uncertified.restype = C.c_int32
         lib.nrtgpu_merge_topk_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
@@ -122,7 +141,7 @@ def gpu_lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         msg = gpu_lib().nrtgpu_last_error().decode("utf-8", "replace")
-        raise (NrtGpuUnsupported if rc == 3 else NrtGpuError)(rc, msg)
+        raise (NrtGpuUnsupported if rc == 3 else CollectionTimeoutException if rc == 5 else NrtGpuError)(rc, msg)
 
 
 def synth_lib() -> C.CDLL:

@@ -405,6 +405,11 @@ struct MergeLaunch {
   int32_t n_lists, top_k, nq;
   int32_t doc_base;
   int32_t* out_docs; float* out_scores; int32_t* out_counts;
+  // optional: per-query totalHits / relation of the shard written next to the hits (the packed record of the one
+  // all-gather of a multi-GPU step, nrtgpu_batch_bind_packed)
+  const unsigned long long* total_hits; const int32_t* pruned; int32_t* terminated;
+  long long terminate_after;                  // > 0: a query with more hits than this terminated early (TerminateAfterWrapper.java:150-158)
+  long long* out_total; int32_t* out_flags;   // flags: bit 0 relation GREATER_THAN_OR_EQUAL_TO, bit 1 terminated early
 };
 
 constexpr int kMergeThreads = 256;
@@ -441,14 +446,24 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
     M.out_docs[(size_t)q * M.top_k + i] = key_doc(k) + M.doc_base;
     M.out_scores[(size_t)q * M.top_k + i] = key_score(k);
   }
-  if (tid == 0) M.out_counts[q] = have;
+  if (tid == 0) {
+    M.out_counts[q] = have;
+    if (M.terminate_after > 0 && M.terminated && M.total_hits && (long long)M.total_hits[q] > M.terminate_after) M.terminated[q] = 1;
+    const bool term = M.terminated && M.terminated[q];
+    if (M.out_total) M.out_total[q] = M.total_hits ? (long long)M.total_hits[q] : 0ll;
+    if (M.out_flags) M.out_flags[q] = ((M.pruned && M.pruned[q]) || term ? 1 : 0) | (term ? 2 : 0);
+  }
 }
 
 // TopDocs.merge over lists of (doc, score) pairs (cross-shard merge after the NCCL all-gather).
 struct MergePairsLaunch {
-  const int32_t* docs; const float* scores; const int32_t* counts;  // [n_lists][nq][top_k], [n_lists][nq]
+  const int32_t* docs; const float* scores; const int32_t* counts;  // list l: docs + l * stride_hits [nq][top_k], counts + l * stride_counts [nq]
+  int64_t stride_hits, stride_counts;   // elements between consecutive lists
   int32_t n_lists, top_k, nq;
   int32_t* out_docs; float* out_scores; int32_t* out_counts;
+  // optional (packed records): totalHits summed, flags ORed over the shards (TopDocs.merge: relation GTE if any input is)
+  const long long* totals; const int32_t* flags; int64_t stride_totals, stride_flags;
+  long long* out_total; int32_t* out_flags;
 };
 
 __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(MergePairsLaunch M) {
@@ -462,9 +477,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(MergePairsLa
     int l_end = l;
     __syncthreads();
     while (l_end < M.n_lists) {
-      int c = M.counts[(size_t)l_end * M.nq + q];
+      int c = M.counts[(size_t)l_end * M.stride_counts + q];
       if (fill + c > kMergeCap) break;
-      size_t base = ((size_t)l_end * M.nq + q) * M.top_k;
+      size_t base = (size_t)l_end * M.stride_hits + (size_t)q * M.top_k;
       for (int i = tid; i < c; i += kMergeThreads) keys[fill + i] = make_key(M.scores[base + i], M.docs[base + i]);
       fill += c; ++l_end;
     }
@@ -481,7 +496,14 @@ __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(MergePairsLa
     M.out_docs[(size_t)q * M.top_k + i] = key_doc(k);
     M.out_scores[(size_t)q * M.top_k + i] = key_score(k);
   }
-  if (tid == 0) M.out_counts[q] = have;
+  if (tid == 0) {
+    M.out_counts[q] = have;
+    if (M.out_total) {
+      long long t = 0; int32_t f = 0;
+      for (int l2 = 0; l2 < M.n_lists; ++l2) { t += M.totals[(size_t)l2 * M.stride_totals + q]; f |= M.flags[(size_t)l2 * M.stride_flags + q]; }
+      M.out_total[q] = t; M.out_flags[q] = f;
+    }
+  }
 }
 
 }  // namespace nrtgpu

@@ -544,6 +544,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       NRT_CUDA_TRY(cudaGetLastError());
       MergeLaunch M; M.slice_keys = dKeys; M.slice_cnt = dCnt; M.n_lists = n_chunks; M.top_k = k; M.nq = gn; M.doc_base = doc_base;
       M.out_docs = dXD; M.out_scores = dXS; M.out_counts = dXC;
+      M.total_hits = nullptr; M.pruned = nullptr; M.terminated = nullptr; M.terminate_after = 0; M.out_total = nullptr; M.out_flags = nullptr;
       merge_slices_kernel<<<gn, kMergeThreads, 0, st>>>(M);
       NRT_CUDA_TRY(cudaGetLastError());
       NRT_CUDA_TRY(cudaMemcpyAsync(hd.data(), dXD, (size_t)gn * k * 4, cudaMemcpyDeviceToHost, st));

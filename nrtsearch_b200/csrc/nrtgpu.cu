@@ -216,8 +216,14 @@ struct nrtgpu_batch {
   DevBuf<unsigned long long> mode_stats;   // NRTGPU_DEBUG_MODES=1: cycles / work items per kernel mode
   DevBuf<int32_t> pruned;    // [nq] relation GTE flags
   DevBuf<int32_t> terminated; // [nq] terminateAfter cut the query short
-  DevBuf<int32_t> abort_flag; // [1] device abort word polled at work-item boundaries (deadline / cancellation), or NULL
-  DevBuf<int64_t> terminate_after;   // [nq] or NULL
+  DevBuf<int32_t> timed_out;  // [nq] a work item of the query was skipped because the deadline had passed
+  DevBuf<unsigned long long> clock0;  // [1] %globaltimer when the first work item of the run started
+  std::vector<int32_t> h_flags;
+  bool limits_active = false, disallow_partial = false;
+  double timeout_sec = 0.0;
+  long long deadline_ns = 0;       // budget from the first work item on (0: none)
+  int64_t ta_scalar = 0;           // terminateAfter (0: none)
+  int64_t terminate_after_max_recall = 0;
   std::vector<DevClause> h_dc; std::vector<DevQuery> h_dq; std::vector<int32_t> h_wq, h_ws;   // host copies the async uploads read
   int32_t slice_docs = 0;
   int64_t threshold = INT32_MAX;
@@ -235,6 +241,7 @@ struct nrtgpu_batch {
   bool ran = false;
   // optional caller-provided device output buffers (e.g. torch tensors feeding the NCCL all-gather)
   int32_t* bound_docs = nullptr; float* bound_scores = nullptr; int32_t* bound_counts = nullptr;
+  long long* bound_total = nullptr; int32_t* bound_flags = nullptr;   // packed record (nrtgpu_batch_bind_packed)
   int32_t* o_docs() { return bound_docs ? bound_docs : out_docs.p; }
   float* o_scores() { return bound_scores ? bound_scores : out_scores.p; }
   int32_t* o_counts() { return bound_counts ? bound_counts : out_counts.p; }
@@ -242,6 +249,11 @@ struct nrtgpu_batch {
 };
 
 static void free_batch(nrtgpu_batch* b) { delete b; }
+extern "C" {
+static int batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* lim, cudaStream_t st);
+static int batch_fetch_impl(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                            int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout, uint8_t* out_terminated_early);
+}
 nrtgpu_index::~nrtgpu_index() { for (auto* b : ws_free) free_batch(b); }
 
 extern "C" {
@@ -798,7 +810,12 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
         P.n_lists = b->n_lists; P.n_slices = b->n_slices; P.top_k = b->top_k; P.slice_docs = b->slice_docs; P.n_gran = b->n_gran;
         P.threshold = b->threshold; P.pruned = b->pruned.p; P.theta = L.theta; P.total_hits = L.total_hits;
         P.slice_keys = L.slice_keys; P.slice_cnt = L.slice_cnt;
-        P.abort_flag = b->abort_flag.p; P.terminate_after = b->terminate_after.p; P.terminated = b->terminated.p;
+        P.deadline_ns = b->limits_active ? b->deadline_ns : 0; P.clock0 = b->clock0.p; P.timed_out = b->timed_out.p;
+        P.terminate_after = b->ta_scalar; P.terminated = b->terminated.p;
+        if (P.deadline_ns) {
+          NRT_CUDA_TRY(cudaMemsetAsync(b->clock0.p, 0, sizeof(unsigned long long), st));
+          NRT_CUDA_TRY(cudaMemsetAsync(b->timed_out.p, 0, b->timed_out.bytes(), st));
+        }
         if (debug) {
           if (!b->probe_stats.p && (rc_dbg = b->probe_stats.alloc(16))) return rc_dbg;
           NRT_CUDA_TRY(cudaMemsetAsync(b->probe_stats.p, 0, 16 * sizeof(unsigned long long), st));
@@ -871,6 +888,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   M.slice_keys = b->slice_keys.p; M.slice_cnt = b->slice_cnt.p;
   M.n_lists = b->n_lists; M.top_k = b->top_k; M.nq = b->nq; M.doc_base = b->ix->doc_base;
   M.out_docs = b->o_docs(); M.out_scores = b->o_scores(); M.out_counts = b->o_counts();
+  M.total_hits = b->total_hits.p; M.pruned = b->pruned.p; M.terminated = b->terminated.p; M.terminate_after = b->ta_scalar;
+  M.out_total = b->bound_total; M.out_flags = b->bound_flags;
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
   NRT_CUDA_TRY(cudaEventRecord(ev[2], st));
@@ -879,8 +898,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   return NRTGPU_OK;
 }
 
-int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores,
-                       int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation) {
+static int batch_fetch_impl(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                            int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout, uint8_t* out_terminated_early) {
   if (!b || !b->ran) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_fetch: batch has not run");
   cudaStream_t st = (cudaStream_t)stream_;
   size_t n = (size_t)b->nq * b->top_k;
@@ -888,14 +907,66 @@ int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float*
   if (out_scores) NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, b->o_scores(), n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (out_counts) NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, b->o_counts(), (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (out_total_hits) NRT_CUDA_TRY(cudaMemcpyAsync(out_total_hits, b->total_hits.p, (size_t)b->nq * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  std::vector<int32_t> pr;
-  if (out_relation) {
-    pr.resize((size_t)b->nq);
-    NRT_CUDA_TRY(cudaMemcpyAsync(pr.data(), b->pruned.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  }
+  std::vector<int32_t>& pr = b->h_flags;
+  pr.resize(3 * (size_t)b->nq);
+  NRT_CUDA_TRY(cudaMemcpyAsync(pr.data(), b->pruned.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(pr.data() + b->nq, b->terminated.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  const bool has_to = b->timed_out.p != nullptr && b->limits_active;
+  if (has_to) NRT_CUDA_TRY(cudaMemcpyAsync(pr.data() + 2 * (size_t)b->nq, b->timed_out.p, (size_t)b->nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   NRT_CUDA_TRY(cudaStreamSynchronize(st));
-  if (out_relation) for (int i = 0; i < b->nq; ++i) out_relation[i] = pr[(size_t)i] ? 1 : 0;   // 1 = GREATER_THAN_OR_EQUAL_TO
+  bool any_timeout = false;
+  for (int i = 0; i < b->nq; ++i) {
+    const bool term = pr[(size_t)b->nq + i] != 0;
+    const bool to = has_to && pr[2 * (size_t)b->nq + i] != 0;
+    any_timeout |= to;
+    // TerminateAfterWrapper.java:85-90: an early-terminated search reports (hits counted, GREATER_THAN_OR_EQUAL_TO)
+    if (out_relation) out_relation[i] = (pr[(size_t)i] || term || to) ? 1 : 0;
+    if (out_terminated_early) out_terminated_early[i] = term ? 1 : 0;
+    if (out_hit_timeout) out_hit_timeout[i] = to ? 1 : 0;
+    if (term && out_total_hits && b->terminate_after_max_recall > 0 && out_total_hits[i] > b->terminate_after_max_recall)
+      out_total_hits[i] = b->terminate_after_max_recall;
+  }
+  // SearchCutoffWrapper.java:164-174: with noPartialResults a timeout is an error (CollectionTimeoutException), else the
+  // partial results are returned and hitTimeout is set
+  if (any_timeout && b->disallow_partial) NRT_FAIL(NRTGPU_ERR_TIMEOUT, "Search collection exceeded timeout of " + std::to_string(b->timeout_sec) + "s");
   return NRTGPU_OK;
+}
+
+int nrtgpu_batch_fetch(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores,
+                       int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation) {
+  return batch_fetch_impl(b, stream_, out_docs, out_scores, out_counts, out_total_hits, out_relation, nullptr, nullptr);
+}
+
+int nrtgpu_batch_fetch_ex(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                          int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout, uint8_t* out_terminated_early) {
+  return batch_fetch_impl(b, stream_, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+}
+
+// deadline / terminateAfter of the batch (SearchCutoffWrapper / TerminateAfterWrapper semantics, see include/nrtgpu.h)
+static int batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* lim, cudaStream_t st) {
+  b->limits_active = false; b->disallow_partial = false; b->timeout_sec = 0.0; b->terminate_after_max_recall = 0;
+  b->deadline_ns = 0; b->ta_scalar = 0;
+  if (!lim) return NRTGPU_OK;
+  if (lim->timeout_sec < 0.0 || lim->terminate_after < 0) NRT_FAIL(NRTGPU_ERR_INVALID, "timeout_sec / terminate_after must be >= 0");
+  int rc;
+  if (lim->timeout_sec > 0.0) {
+    b->limits_active = true; b->timeout_sec = lim->timeout_sec; b->disallow_partial = lim->disallow_partial_results != 0;
+    const double left = lim->timeout_sec - lim->elapsed_sec;   // the timer started when the request's first collector was created
+    b->deadline_ns = left <= 0.0 ? -1 : std::max<long long>(1, (long long)(left * 1e9));
+    if ((rc = b->timed_out.alloc((size_t)b->nq))) return rc;
+    if ((rc = b->clock0.alloc(1))) return rc;
+  }
+  if (lim->terminate_after > 0) {
+    b->ta_scalar = lim->terminate_after;
+    b->terminate_after_max_recall = lim->terminate_after_max_recall_count > lim->terminate_after ? lim->terminate_after_max_recall_count : lim->terminate_after;
+  }
+  (void)st;
+  return NRTGPU_OK;
+}
+
+int nrtgpu_batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* limits) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  return batch_set_limits(b, limits, (cudaStream_t)0);
 }
 
 int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_scores, int32_t** d_counts) {
@@ -909,6 +980,46 @@ int nrtgpu_batch_device_results(nrtgpu_batch* b, int32_t** d_docs, float** d_sco
 int nrtgpu_batch_bind_output(nrtgpu_batch* b, int32_t* d_docs, float* d_scores, int32_t* d_counts) {
   if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
   b->bound_docs = d_docs; b->bound_scores = d_scores; b->bound_counts = d_counts;
+  b->bound_total = nullptr; b->bound_flags = nullptr;
+  return NRTGPU_OK;
+}
+
+// Packed per-shard result record (one all-gather carries everything TopDocs.merge needs), int32 words:
+//   docs [nq*top_k] | scores [nq*top_k] (float bits) | counts [nq] | flags [nq] | (pad to 8 bytes) | totalHits [nq] int64
+int64_t nrtgpu_packed_words(int32_t nq, int32_t top_k) {
+  int64_t w = (int64_t)nq * top_k * 2 + 2ll * nq;
+  w = (w + 1) & ~1ll;
+  return w + 2ll * nq;
+}
+
+int nrtgpu_batch_bind_packed(nrtgpu_batch* b, int32_t* d_record) {
+  if (!b) NRT_FAIL(NRTGPU_ERR_INVALID, "NULL batch");
+  if (!d_record) { b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr; return NRTGPU_OK; }
+  if (((uintptr_t)d_record & 7u) != 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_bind_packed: record must be 8-byte aligned");
+  const int64_t n = (int64_t)b->nq * b->top_k;
+  b->bound_docs = d_record; b->bound_scores = (float*)(d_record + n); b->bound_counts = d_record + 2 * n;
+  b->bound_flags = d_record + 2 * n + b->nq;
+  int64_t w = 2 * n + 2ll * b->nq; w = (w + 1) & ~1ll;
+  b->bound_total = (long long*)(d_record + w);
+  return NRTGPU_OK;
+}
+
+int nrtgpu_merge_topk_packed(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k, const int32_t* d_records,
+                             int32_t* d_out_record, void* stream) {
+  if (!ctx || !d_records || !d_out_record || n_lists <= 0 || nq <= 0 || top_k <= 0 || top_k > kMaxTopK)
+    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_merge_topk_packed: bad argument");
+  NRT_CUDA_TRY(cudaSetDevice(ctx->device));
+  const int64_t n = (int64_t)nq * top_k, words = nrtgpu_packed_words(nq, top_k);
+  int64_t w = 2 * n + 2ll * nq; w = (w + 1) & ~1ll;
+  MergePairsLaunch M;
+  M.docs = d_records; M.scores = (const float*)(d_records + n); M.counts = d_records + 2 * n;
+  M.stride_hits = words; M.stride_counts = words;
+  M.n_lists = n_lists; M.top_k = top_k; M.nq = nq;
+  M.out_docs = d_out_record; M.out_scores = (float*)(d_out_record + n); M.out_counts = d_out_record + 2 * n;
+  M.flags = d_records + 2 * n + nq; M.totals = (const long long*)(d_records + w); M.stride_flags = words; M.stride_totals = words / 2;
+  M.out_flags = d_out_record + 2 * n + nq; M.out_total = (long long*)(d_out_record + w);
+  merge_pairs_kernel<<<nq, kMergeThreads, 0, (cudaStream_t)stream>>>(M);
+  NRT_CUDA_TRY(cudaGetLastError());
   return NRTGPU_OK;
 }
 
@@ -953,11 +1064,13 @@ int nrtgpu_batch_free(nrtgpu_batch* b) {
   return NRTGPU_OK;
 }
 
-int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
-                       const nrtgpu_query* queries, int32_t nq, int32_t top_k,
-                       int32_t total_hits_threshold, int32_t flags, void* stream, int32_t* out_docs,
-                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
-                       uint8_t* out_relation) {
+// one-shot search: compile + upload the batch into a pooled workspace, run; results either copied to HOST buffers
+// (d_record == NULL) or left in a packed DEVICE record (the multi-GPU path: the caller all-gathers it on `stream`)
+static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                            const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold, int32_t flags,
+                            const nrtgpu_search_limits* limits, void* stream, int32_t* d_record, int32_t* out_docs, float* out_scores,
+                            int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
+                            uint8_t* out_terminated_early) {
   if (!ix) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool: NULL index");
   // take a cached workspace (device buffers survive between calls: no cudaMalloc on the request path)
   nrtgpu_batch* b = nullptr;
@@ -966,15 +1079,47 @@ int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n
     if (!ix->ws_free.empty()) { b = ix->ws_free.back(); ix->ws_free.pop_back(); }
   }
   if (!b) b = new nrtgpu_batch;
-  b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr;
+  b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
   int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream);
+  if (!rc) rc = batch_set_limits(b, limits, (cudaStream_t)stream);
+  if (!rc && d_record) rc = nrtgpu_batch_bind_packed(b, d_record);
   if (!rc) rc = nrtgpu_batch_run(b, stream);
-  if (!rc) rc = nrtgpu_batch_fetch(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation);
+  if (!rc) {
+    if (d_record) { cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; } }
+    else rc = batch_fetch_impl(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+  }
+  b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
   {
     std::lock_guard<std::mutex> g(ix->ws_mu);
     ix->ws_free.push_back(b);
   }
   return rc;
+}
+
+int nrtgpu_search_bool(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                       const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                       int32_t total_hits_threshold, int32_t flags, void* stream, int32_t* out_docs,
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
+                       uint8_t* out_relation) {
+  return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, nullptr, stream, nullptr,
+                          out_docs, out_scores, out_counts, out_total_hits, out_relation, nullptr, nullptr);
+}
+
+int nrtgpu_search_bool_ex(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                          const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold, int32_t flags,
+                          const nrtgpu_search_limits* limits, void* stream, int32_t* out_docs, float* out_scores,
+                          int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
+                          uint8_t* out_terminated_early) {
+  return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, limits, stream, nullptr,
+                          out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+}
+
+int nrtgpu_search_bool_packed(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                              const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold, int32_t flags,
+                              const nrtgpu_search_limits* limits, void* stream, int32_t* d_record) {
+  if (!d_record) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool_packed: NULL record");
+  return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, limits, stream, d_record,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int nrtgpu_merge_topk_device(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32_t top_k,
@@ -984,7 +1129,9 @@ int nrtgpu_merge_topk_device(nrtgpu_ctx* ctx, int32_t n_lists, int32_t nq, int32
   NRT_CUDA_TRY(cudaSetDevice(ctx->device));
   MergePairsLaunch M;
   M.docs = d_docs; M.scores = d_scores; M.counts = d_counts; M.n_lists = n_lists; M.top_k = top_k; M.nq = nq;
+  M.stride_hits = (int64_t)nq * top_k; M.stride_counts = nq;
   M.out_docs = d_out_docs; M.out_scores = d_out_scores; M.out_counts = d_out_counts;
+  M.totals = nullptr; M.flags = nullptr; M.stride_totals = 0; M.stride_flags = 0; M.out_total = nullptr; M.out_flags = nullptr;
   merge_pairs_kernel<<<nq, kMergeThreads, 0, (cudaStream_t)stream>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
   return NRTGPU_OK;

@@ -88,9 +88,15 @@ struct ProbeLaunch {
   unsigned long long* total_hits;
   uint64_t* slice_keys;
   int32_t* slice_cnt;
-  const int32_t* abort_flag;     // optional: non-zero => remaining items are skipped (deadline / cancellation)
-  const int64_t* terminate_after; // optional [nq] (0: none): a query that has collected this many hits stops collecting
-  int32_t* terminated;           // [nq] set when terminate_after cut a query short
+  // deadline (SearchCutoffWrapper.java:164-174, checked at work-item boundaries = the reference's per-segment check):
+  // the first work item of the run stamps clock0 with %globaltimer; an item claimed more than deadline_ns later is
+  // skipped and its query flagged. terminateAfter (TerminateAfterWrapper.java:150-162): a query that has already
+  // collected that many hits takes no further work items.
+  long long deadline_ns;         // 0: no deadline; < 0: already expired
+  unsigned long long* clock0;
+  int32_t* timed_out;            // [nq]
+  long long terminate_after;     // 0: none
+  int32_t* terminated;           // [nq]
 };
 
 struct alignas(128) ProbeSmem {
@@ -331,8 +337,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
   for (;;) {
     __syncthreads();   // the previous item is retired (also orders the mbarrier init before its first use)
     if (tid == 0) {
-      sm.wi = (int)atomicAdd(L.work_counter, 1u);
-      sm.skip = (L.abort_flag && *(volatile const int32_t*)L.abort_flag) ? 1 : 0;   // deadline passed / cancelled: drain the queue
+      const int w = (int)atomicAdd(L.work_counter, 1u);
+      sm.wi = w;
+      sm.skip = 0;
+      if (L.deadline_ns && w < L.n_work) {
+        bool late = L.deadline_ns < 0;   // the request's budget was spent before the launch
+        if (!late) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          unsigned long long t0 = atomicCAS(L.clock0, 0ull, now);
+          if (t0 == 0ull) t0 = now;
+          late = now - t0 > (unsigned long long)L.deadline_ns;
+        }
+        if (late) { sm.skip = 1; L.timed_out[L.work_query[w]] = 1; }   // drain the queue
+      }
     }
     __syncthreads();
     const int wi = sm.wi;
@@ -361,12 +379,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     const int g_hi = (wflags & 1) ? min(g_count, kWarmGran) : g_count;
     __syncthreads();   // B1: query + clauses resident
     // terminateAfter (TerminateAfterWrapper.java:150-162): a query that has collected enough hits stops collecting
-    if (L.terminate_after) {
-      const int64_t ta = L.terminate_after[qi];
-      if (ta > 0 && (int64_t)sm.hits0 >= ta) {
-        if (tid == 0) { L.terminated[qi] = 1; const int ol = (wflags & 1) ? L.n_lists - 1 : slice; L.slice_cnt[(size_t)qi * L.n_lists + ol] = 0; }
-        continue;
-      }
+    if (L.terminate_after > 0 && (long long)sm.hits0 >= L.terminate_after) {
+      if (tid == 0) L.terminated[qi] = 1;
+      continue;
     }
     // ---- per-slot descriptors (one thread per clause), granule offsets of the lists with skip data (all threads)
     if (tid < ncl && sm.cl[tid].kind == NRTGPU_TERM) {
@@ -661,14 +676,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
           const uint8_t* gf8_t = sm.s_gf8[t] + sm.s_ra[t];
           const uint32_t tshift = 8u * (uint32_t)t;
           // software pipeline: the postings of the NEXT round are fetched before the current round is processed
+          // (generic pointers: one load path for staged -- shared memory -- and plane / global -- HBM -- driver lists)
+          const int32_t* dptr = t_staged ? sdoc_t : gdoc_t;
+          const uint8_t* fptr = t_staged ? sf8_t : gf8_t;
           int32_t nd[kR]; uint32_t nf[kR];
 #pragma unroll
           for (int j = 0; j < kR; ++j) {
             const uint32_t x = cb + (uint32_t)(j * kThreads + tid);
             nd[j] = 0; nf[j] = 0;
-            if (x < n_t) {
-              if (t_staged) { nd[j] = sdoc_t[x]; nf[j] = sf8_t[x]; } else { nd[j] = __ldg(gdoc_t + x); nf[j] = __ldg(gf8_t + x); }
-            }
+            if (x < n_t) { nd[j] = dptr[x]; nf[j] = fptr[x]; }
           }
           while (!full && cb < n_t) {
             const unsigned long long theta = sm.theta;
@@ -678,13 +694,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
 #pragma unroll
             for (int j = 0; j < kR; ++j) { doc[j] = nd[j]; word[j] = nf[j] << tshift; }   // word == 0: no posting (tf >= 1)
             // plane gathers of every posting of the round (2-bit tf codes, all in flight together)
+            // (lanes without a posting gather byte 0 of the plane: harmless, and the branches stay CTA-uniform)
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
               const uint32_t d4 = (uint32_t)doc[j] >> 2;
-              pbyte[j][0] = ((need_plane & 1u) && word[j]) ? (uint32_t)__ldg(pl0 + d4) : 0u;
-              pbyte[j][1] = ((need_plane & 2u) && word[j]) ? (uint32_t)__ldg(pl1 + d4) : 0u;
-              pbyte[j][2] = ((need_plane & 4u) && word[j]) ? (uint32_t)__ldg(pl2 + d4) : 0u;
-              pbyte[j][3] = ((need_plane & 8u) && word[j]) ? (uint32_t)__ldg(pl3 + d4) : 0u;
+              pbyte[j][0] = 0u; pbyte[j][1] = 0u; pbyte[j][2] = 0u; pbyte[j][3] = 0u;
+              if (need_plane & 1u) pbyte[j][0] = (uint32_t)__ldg(pl0 + d4);
+              if (need_plane & 2u) pbyte[j][1] = (uint32_t)__ldg(pl1 + d4);
+              if (need_plane & 4u) pbyte[j][2] = (uint32_t)__ldg(pl2 + d4);
+              if (need_plane & 8u) pbyte[j][3] = (uint32_t)__ldg(pl3 + d4);
             }
             // next round's postings
             {
@@ -693,9 +711,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
               for (int j = 0; j < kR; ++j) {
                 const uint32_t x = nb + (uint32_t)(j * kThreads + tid);
                 nd[j] = 0; nf[j] = 0;
-                if (x < n_t) {
-                  if (t_staged) { nd[j] = sdoc_t[x]; nf[j] = sf8_t[x]; } else { nd[j] = __ldg(gdoc_t + x); nf[j] = __ldg(gf8_t + x); }
-                }
+                if (x < n_t) { nd[j] = dptr[x]; nf[j] = fptr[x]; }
               }
             }
             // searches of the staged lists (shared memory; overlaps the gathers)
@@ -725,12 +741,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
               if (!word[j]) continue;
               uint32_t v = word[j];
               if (need_plane) {
-                const uint32_t sh = ((uint32_t)doc[j] & 3u) * 2u;
-#pragma unroll
-                for (int u = 0; u < kT; ++u) {
-                  const uint32_t c = (pbyte[j][u] >> sh) & 3u;   // min(tf, 3); 3 = "three or more" -> kTfInexact (resolved at scoring)
-                  v |= (c == 3u ? kTfInexact : c) << (8 * u);
-                }
+                // the four gathered bytes side by side; the doc's 2-bit code of every plane with one shift and one mask
+                // (bits shifted in from the neighbouring byte fall outside the mask); code 3 = "three or more" becomes
+                // kTfInexact (resolved when the doc is scored)
+                const uint32_t raw = pbyte[j][0] | (pbyte[j][1] << 8) | (pbyte[j][2] << 16) | (pbyte[j][3] << 24);
+                const uint32_t codes = (raw >> (((uint32_t)doc[j] & 3u) * 2u)) & 0x03030303u;
+                const uint32_t sat = __vcmpeq4(codes, 0x03030303u);   // 0xff where the code saturated
+                v |= (codes & ~sat) | (sat & (kTfInexact * 0x01010101u));
               }
               uint64_t entry;
               if (kSimple) {

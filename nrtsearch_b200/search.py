@@ -22,7 +22,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native
-from ._native import Clause, NrtGpuError, NrtGpuUnsupported, Query as CQuery, check
+from ._native import (Clause, CollectionTimeoutException, NrtGpuError, NrtGpuUnsupported, Query as CQuery, SearchLimits,
+                      check)
 from .index import HostShard, PinnedDesc
 
 TOTAL_HITS_THRESHOLD = 1000  # SearchRequestProcessor.TOTAL_HITS_THRESHOLD (:102)
@@ -117,10 +118,23 @@ class TopDocs:
 
 @dataclass
 class RelevanceCollector:
-    """DocCollector config (CollectorCreatorContext.java:36-53): numHitsToCollect, totalHitsThreshold, searchAfter."""
+    """DocCollector config (CollectorCreatorContext.java:36-53, DocCollector.java wrappers): numHitsToCollect,
+    totalHitsThreshold, searchAfter; timeoutSec / disallowPartialResults (SearchCutoffWrapper.java:164-202);
+    terminateAfter / terminateAfterMaxRecallCount (TerminateAfterWrapper.java:85-162)."""
     num_hits_to_collect: int
     total_hits_threshold: int = TOTAL_HITS_THRESHOLD
     search_after: Optional[ScoreDoc] = None
+    timeout_sec: float = 0.0
+    elapsed_sec: float = 0.0
+    disallow_partial_results: bool = False
+    terminate_after: int = 0
+    terminate_after_max_recall_count: int = 0
+
+    def limits(self) -> Optional[SearchLimits]:
+        if self.timeout_sec <= 0 and self.terminate_after <= 0:
+            return None
+        return SearchLimits(self.timeout_sec, self.elapsed_sec, 1 if self.disallow_partial_results else 0,
+                            self.terminate_after, self.terminate_after_max_recall_count)
 
 
 def _f32(x: float) -> np.float32:
@@ -221,6 +235,8 @@ class BatchResult:
     counts: np.ndarray    # int32 [nq]
     total_hits: np.ndarray  # int64 [nq]
     relation: np.ndarray  # uint8 [nq]
+    hit_timeout: Optional[np.ndarray] = None        # uint8 [nq] (SearchResponse.hitTimeout, per query of the batch)
+    terminated_early: Optional[np.ndarray] = None   # uint8 [nq] (SearchResponse.terminatedEarly)
 
     def top_docs(self, i: int) -> TopDocs:
         n = int(self.counts[i])
@@ -265,6 +281,11 @@ class PreparedBatch:
     def bind_output(self, d_docs: int, d_scores: int, d_counts: int):
         check(self._lib.nrtgpu_batch_bind_output(self.handle, C.c_void_p(d_docs), C.c_void_p(d_scores), C.c_void_p(d_counts)))
 
+    def bind_packed(self, d_record: int):
+        """Results of subsequent runs go into one packed DEVICE record (nrtgpu_batch_bind_packed): the buffer a multi-GPU
+        step all-gathers."""
+        check(self._lib.nrtgpu_batch_bind_packed(self.handle, C.c_void_p(d_record)))
+
     def device_results(self):
         d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(self._lib.nrtgpu_batch_device_results(self.handle, C.byref(d), C.byref(s), C.byref(c)))
@@ -299,10 +320,14 @@ class GpuIndexSearcher:
         carr, ncl, qarr, nq = compile_queries(queries, search_after)
         k = collector.num_hits_to_collect
         out = BatchResult(np.zeros((nq, max(k, 1)), np.int32), np.zeros((nq, max(k, 1)), np.float32),
-                          np.zeros(nq, np.int32), np.zeros(nq, np.int64), np.zeros(nq, np.uint8))
-        check(self._lib.nrtgpu_search_bool(self.index.handle, carr, ncl, qarr, nq, k, collector.total_hits_threshold, 0,
-                                           C.c_void_p(stream), out.docs.ctypes.data, out.scores.ctypes.data,
-                                           out.counts.ctypes.data, out.total_hits.ctypes.data, out.relation.ctypes.data))
+                          np.zeros(nq, np.int32), np.zeros(nq, np.int64), np.zeros(nq, np.uint8),
+                          np.zeros(nq, np.uint8), np.zeros(nq, np.uint8))
+        lim = collector.limits()
+        check(self._lib.nrtgpu_search_bool_ex(self.index.handle, carr, ncl, qarr, nq, k, collector.total_hits_threshold, 0,
+                                              None if lim is None else C.byref(lim), C.c_void_p(stream), out.docs.ctypes.data,
+                                              out.scores.ctypes.data, out.counts.ctypes.data, out.total_hits.ctypes.data,
+                                              out.relation.ctypes.data, out.hit_timeout.ctypes.data,
+                                              out.terminated_early.ctypes.data))
         return out
 
     def search(self, query, collector: RelevanceCollector) -> TopDocs:

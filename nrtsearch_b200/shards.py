@@ -74,3 +74,54 @@ class TopKGather:
             ctx.handle, self.world, self.nq, self.k, self.all_docs.data_ptr(), self.all_scores.data_ptr(),
             self.all_counts.data_ptr(), self.fin_docs.data_ptr(), self.fin_scores.data_ptr(), self.fin_counts.data_ptr(),
             ctypes.c_void_p(stream)))
+
+
+class PackedGather:
+    """The ONE exchange step of a multi-GPU search: every rank's packed result record
+    (docs, scores, counts, relation flags, totalHits of all queries; include/nrtgpu.h nrtgpu_packed_words) is
+    all-gathered once, then nrtgpu_merge_topk_packed does TopDocs.merge on every rank. Results never leave the device
+    between the shard search and the merged page."""
+
+    def __init__(self, nq: int, k: int, world: int, device):
+        import torch
+        from . import _native
+        self.nq, self.k, self.world = nq, k, world
+        self.words = int(_native.gpu_lib().nrtgpu_packed_words(nq, k)) if device.type == "cuda" else packed_words(nq, k)
+        self.local = torch.zeros(self.words, dtype=torch.int32, device=device)
+        self.all = torch.zeros(world * self.words, dtype=torch.int32, device=device)
+        self.merged = torch.zeros(self.words, dtype=torch.int32, device=device)
+
+    def gather(self, group=None):
+        import torch.distributed as dist
+        if self.world == 1:
+            self.all.copy_(self.local)
+        else:
+            dist.all_gather_into_tensor(self.all, self.local, group=group)
+
+    def merge_on_device(self, ctx, stream: int):
+        import ctypes
+        from . import _native
+        _native.check(_native.gpu_lib().nrtgpu_merge_topk_packed(
+            ctx.handle, self.world, self.nq, self.k, self.all.data_ptr(), self.merged.data_ptr(), ctypes.c_void_p(stream)))
+
+    def unpack(self, record=None):
+        """Host view of a record: docs [nq,k], scores [nq,k], counts [nq], flags [nq], total_hits [nq]."""
+        r = (self.merged if record is None else record).cpu().numpy()
+        return unpack_record(r, self.nq, self.k)
+
+
+def packed_words(nq: int, k: int) -> int:
+    w = nq * k * 2 + 2 * nq
+    w = (w + 1) & ~1
+    return w + 2 * nq
+
+
+def unpack_record(r: np.ndarray, nq: int, k: int):
+    n = nq * k
+    w = (2 * n + 2 * nq + 1) & ~1
+    docs = r[:n].reshape(nq, k)
+    scores = r[n:2 * n].view(np.float32).reshape(nq, k)
+    counts = r[2 * n:2 * n + nq]
+    flags = r[2 * n + nq:2 * n + 2 * nq]
+    total = r[w:w + 2 * nq].view(np.int64)
+    return docs, scores, counts, flags, total

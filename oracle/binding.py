@@ -42,12 +42,31 @@ def build(force: bool = False) -> str:
     return so
 
 
+def _native_so() -> str:
+    """liboracle.so rebuilt with -O3 -march=native for the host it runs on (bench.py's cpu_baseline / reference arm: the
+    portable build that travels to the GPU box is -march=x86-64-v2). Same sources, same results (-ffp-contract=off, no
+    fast-math); falls back to the portable build when no compiler is present."""
+    so = os.path.join(_HERE, "liboracle_native.so")
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h")]
+    try:
+        if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in src):
+            tmp = so + f".{os.getpid()}.tmp"
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fopenmp", "-std=c11",
+                                   "-shared", "-o", tmp, src[0], "-lm"], stderr=subprocess.DEVNULL)
+            os.replace(tmp, so)
+        return so
+    except Exception:
+        return ""
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         so = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(so):
             build()
+        if os.environ.get("NRT_ORACLE_NATIVE") == "1":
+            so = _native_so() or so
         L = C.CDLL(so)
         L.orc_int_to_byte4.restype = C.c_uint8
         L.orc_int_to_byte4.argtypes = [C.c_int32]
@@ -66,6 +85,9 @@ def lib() -> C.CDLL:
         L.orc_search.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]
+        L.orc_search_limits.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_merge_topk.restype = None
         L.orc_merge_topk.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
         L.orc_vector_score_f32.restype = C.c_float
@@ -200,6 +222,23 @@ def search_compiled(oix: OracleIndex, carr, ncl: int, qarr, nq: int, top_k: int,
     if rc != 0:
         raise ValueError(f"orc_search failed ({rc})")
     return docs, scores, counts, total, rel
+
+
+def search_terminate_after(oix: OracleIndex, carr, ncl: int, qarr, nq: int, top_k: int, terminate_after: int,
+                           max_recall: int = 0, n_threads: int = 0):
+    """TerminateAfterWrapper semantics, sequential (doc order). Returns docs, scores, counts, total, relation, terminated."""
+    docs = np.zeros((nq, top_k), np.int32)
+    scores = np.zeros((nq, top_k), np.float32)
+    counts = np.zeros(nq, np.int32)
+    total = np.zeros(nq, np.int64)
+    rel = np.zeros(nq, np.uint8)
+    term = np.zeros(nq, np.uint8)
+    rc = lib().orc_search_limits(C.byref(oix.ix), C.cast(carr, C.POINTER(OrcClause)), C.cast(qarr, C.POINTER(OrcQuery)), nq,
+                                 top_k, 2**31 - 1, 0, n_threads, terminate_after, max_recall, docs.ctypes.data,
+                                 scores.ctypes.data, counts.ctypes.data, total.ctypes.data, rel.ctypes.data, term.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"orc_search_limits failed ({rc})")
+    return docs, scores, counts, total, rel, term
 
 
 def merge_topk(docs, scores, counts, top_k):

@@ -106,8 +106,21 @@ static int hit_cmp_best_first(const void* a, const void* b) {
 typedef struct {
   heap_t pq; int top_k; int64_t total_hits;
   int has_after; float after_score; int32_t after_doc;
+  /* TerminateAfterWrapper (reference src/main/java/com/yelp/nrtsearch/server/search/TerminateAfterWrapper.java:150-162),
+   * single-threaded: docs arrive in doc order, the first terminate_after are collected, later ones are only counted,
+   * up to terminate_after_max_recall_count, and set terminatedEarly */
+  int64_t terminate_after, max_recall, seen; int terminated_early;
 } collector_t;
 static inline void collect(collector_t* c, int32_t doc, float score) {
+  if (c->terminate_after > 0) {
+    int64_t cur = ++c->seen;
+    if (cur > c->terminate_after) {
+      c->terminated_early = 1;
+      if (cur > c->max_recall) return;   /* CollectionTerminatedException */
+      c->total_hits++;                  /* docCount++ without collecting */
+      return;
+    }
+  }
   c->total_hits++;
   if (c->has_after && (score > c->after_score || (score == c->after_score && doc <= c->after_doc))) return;
   if (c->pq.n < c->top_k) { hit_t h = {score, doc}; heap_push(&c->pq, h); return; }
@@ -322,7 +335,8 @@ static void search_one_pruned_disjunction(const orc_index* ix, cl_t* cl, int ncl
 
 static void run_query(const orc_index* ix, const orc_clause* cls, const orc_query* q, int top_k,
                       int64_t threshold, int mode, window_t* w, float (*field_cache)[256], uint8_t* cache_ready,
-                      int32_t* out_docs, float* out_scores, int32_t* out_count, int64_t* out_total, uint8_t* out_rel) {
+                      int32_t* out_docs, float* out_scores, int32_t* out_count, int64_t* out_total, uint8_t* out_rel,
+                      int64_t terminate_after, int64_t max_recall, uint8_t* out_terminated) {
   cl_t cl[64];
   int ncl = q->clause_end - q->clause_begin;
   *out_count = 0; *out_total = 0; *out_rel = 0;
@@ -332,6 +346,8 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
   collector_t col; memset(&col, 0, sizeof(col));
   col.pq.h = (hit_t*)malloc(sizeof(hit_t) * (size_t)(top_k > 0 ? top_k : 1)); col.pq.cap = top_k; col.top_k = top_k;
   col.has_after = q->has_after; col.after_score = q->after_score; col.after_doc = q->after_doc - ix->doc_base;
+  col.terminate_after = terminate_after; col.max_recall = max_recall > terminate_after ? max_recall : terminate_after;
+  if (terminate_after > 0) mode = 0;   /* the wrapper sees every matching doc: exhaustive evaluation */
   int pruned = 0;
   int pure_term_disj = 1;
   for (int i = 0; i < ncl; ++i) if (cl[i].kind != ORC_TERM || cl[i].occur != ORC_SHOULD) pure_term_disj = 0;
@@ -343,7 +359,8 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
   int n = col.pq.n;
   qsort(col.pq.h, (size_t)n, sizeof(hit_t), hit_cmp_best_first);
   for (int i = 0; i < n; ++i) { out_docs[i] = col.pq.h[i].doc + ix->doc_base; out_scores[i] = col.pq.h[i].score; }
-  *out_count = n; *out_total = col.total_hits; *out_rel = pruned ? 1 : 0;
+  *out_count = n; *out_total = col.total_hits; *out_rel = (pruned || col.terminated_early) ? 1 : 0;
+  if (out_terminated) *out_terminated = (uint8_t)col.terminated_early;
   free(col.pq.h);
 }
 
@@ -351,6 +368,15 @@ int orc_search(const orc_index* ix, const orc_clause* clauses, const orc_query* 
                int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
                int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
                uint8_t* out_rel) {
+  return orc_search_limits(ix, clauses, queries, nq, top_k, total_hits_threshold, mode, n_threads, 0, 0, out_docs, out_scores,
+                           out_counts, out_total, out_rel, NULL);
+}
+
+int orc_search_limits(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
+                      int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
+                      int32_t terminate_after, int32_t terminate_after_max_recall,
+                      int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
+                      uint8_t* out_rel, uint8_t* out_terminated) {
   if (top_k <= 0) return -1;
   /* manager rule: threshold = max(threshold, numHits)
    * (reference LazyQueueTopScoreDocCollectorManager.java:102) */
@@ -369,7 +395,8 @@ int orc_search(const orc_index* ix, const orc_clause* clauses, const orc_query* 
 #pragma omp for schedule(dynamic, 1)
     for (int qi = 0; qi < nq; ++qi) {
       run_query(ix, clauses, &queries[qi], top_k, thr, mode, w, fc, ready, out_docs + (size_t)qi * top_k,
-                out_scores + (size_t)qi * top_k, &out_counts[qi], &out_total[qi], &out_rel[qi]);
+                out_scores + (size_t)qi * top_k, &out_counts[qi], &out_total[qi], &out_rel[qi],
+                terminate_after, terminate_after_max_recall, out_terminated ? &out_terminated[qi] : NULL);
       if (out_counts[qi] < 0) {
 #pragma omp atomic write
         bad = 1;

@@ -92,6 +92,13 @@ int orc_search(const orc_index* ix, const orc_clause* clauses, const orc_query* 
                int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
                int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
                uint8_t* out_rel);
+/* the same search under TerminateAfterWrapper (sequential semantics: docs in doc order; reference
+ * src/main/java/com/yelp/nrtsearch/server/search/TerminateAfterWrapper.java:85-162): terminate_after 0 = none */
+int orc_search_limits(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
+                      int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
+                      int32_t terminate_after, int32_t terminate_after_max_recall,
+                      int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
+                      uint8_t* out_rel, uint8_t* out_terminated);
 
 /* TopDocs.merge(0, top_k, shards[]): inputs [n_lists][nq][top_k] sorted lists with counts [n_lists][nq]. */
 void orc_merge_topk(int32_t n_lists, int32_t nq, int32_t top_k, const int32_t* docs, const float* scores,
