@@ -170,6 +170,36 @@ int nrtgpu_search_bool_packed(nrtgpu_index* ix, const nrtgpu_clause* clauses, in
                               int32_t total_hits_threshold, int32_t flags, const nrtgpu_search_limits* limits,
                               void* stream, int32_t* d_record);
 
+/* Sort-by-field top-k (TopFieldCollector; reference src/main/java/com/yelp/nrtsearch/server/search/collectors/
+ * SortFieldCollector.java:44-105, sort construction .../search/sort/SortParser.java:54-131, numeric sort fields
+ * .../field/NumberFieldDef.java:266-278 = SortedNumericSortField(type, reverse) with missingValue from
+ * getSortMissingValue(missingLast)). One sort key + the implicit doc-id tie-break (lower doc first), i.e. the Sort
+ * [<numeric doc-value field>], [docid] or [docid reverse]; other sorts (several fields, score mixed in) return
+ * NRTGPU_ERR_UNSUPPORTED. Values live in the column's sortable-long domain (the adaptor maps int/long directly and
+ * float/double through NumericUtils.floatToSortableInt / doubleToSortableLong, exactly as the range query bounds).
+ *   missing_value: what a doc WITHOUT a value sorts as (Integer/Long.MIN|MAX_VALUE, -+Infinity in the sortable domain:
+ *                  the reference picks MAX when missingLast, irrespective of `reverse`);
+ *   after_values:  per query, the sort value of the last hit of the previous page (FieldDoc.fields[0]); used with
+ *                  nrtgpu_query.has_after / after_doc (LastHitInfo, SortParser.parseLastHitInfo :131-160).
+ * Results: docs in sort order, out_sort_values = the FieldDoc value of every hit (missing docs carry missing_value),
+ * scores are NaN (TopFieldCollector does not track scores), totalHits exact (relation EQUAL_TO). */
+enum { NRTGPU_SORT_RELEVANCE = 0, NRTGPU_SORT_COLUMN = 1, NRTGPU_SORT_DOCID = 2 };
+typedef struct {
+  int32_t kind;          /* NRTGPU_SORT_* */
+  int32_t column;        /* NRTGPU_SORT_COLUMN: doc-value column id */
+  int32_t reverse;       /* SortType.reverse */
+  int32_t reserved;
+  int64_t missing_value;
+  const int64_t* after_values; /* [nq] or NULL */
+} nrtgpu_sort;
+
+int nrtgpu_search_sorted(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t flags,
+                         const nrtgpu_sort* sort, const nrtgpu_search_limits* limits, void* stream,
+                         int32_t* out_docs, int64_t* out_sort_values, int32_t* out_counts,
+                         int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
+                         uint8_t* out_terminated_early);
+
 /* Split form: compile+upload once, launch many times with everything resident in HBM. */
 int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
                          const nrtgpu_query* queries, int32_t nq, int32_t top_k,

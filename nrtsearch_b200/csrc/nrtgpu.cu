@@ -4,6 +4,7 @@
 #include "bool_kernel.cuh"
 #include "stream_kernel.cuh"
 #include "probe_kernel.cuh"
+#include "sort_kernel.cuh"
 #include "knn_kernel.cuh"
 #include "hybrid_kernel.cuh"
 
@@ -155,6 +156,9 @@ struct nrtgpu_index {
   std::vector<std::unique_ptr<DevBuf<int64_t>>> col64;
   std::vector<std::unique_ptr<DevBuf<int32_t>>> col32;
   std::vector<std::unique_ptr<DevBuf<uint8_t>>> col_has;
+  std::vector<std::unique_ptr<DevBuf<uint32_t>>> col_code;      // per column: order-preserving sort code per doc (sort_kernel.cuh)
+  std::vector<std::unique_ptr<DevBuf<uint64_t>>> col_distinct;  // per column: sorted distinct values (sortable domain)
+  std::vector<int32_t> col_n_distinct;
   DevBuf<const int64_t*> col64_ptrs;
   DevBuf<const int32_t*> col32_ptrs;
   DevBuf<const uint8_t*> col_has_ptrs;
@@ -219,6 +223,12 @@ struct nrtgpu_batch {
   DevBuf<int32_t> timed_out;  // [nq] a work item of the query was skipped because the deadline had passed
   DevBuf<unsigned long long> clock0;  // [1] %globaltimer when the first work item of the run started
   std::vector<int32_t> h_flags;
+  // sort-by-field (TopFieldCollector)
+  int32_t sort_kind = 0, sort_column = 0, sort_reverse = 0;
+  int64_t sort_missing_value = 0;
+  DevBuf<int64_t> after_values; DevBuf<int32_t> after_docs; DevBuf<uint32_t> sort_missing_code;
+  DevBuf<int64_t> out_sort_values;
+  std::vector<int32_t> h_after_docs;
   bool limits_active = false, disallow_partial = false;
   double timeout_sec = 0.0;
   long long deadline_ns = 0;       // budget from the first work item on (0: none)
@@ -452,6 +462,22 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       const uint8_t* hh = d->column_has ? d->column_has[c] : nullptr;
       if (hh) { if ((rc = ix->col_has.back()->upload(hh, (size_t)d->n_docs))) return rc; ph[c] = ix->col_has.back()->p; }
     }
+    // sort codes of every column (TopFieldCollector path): one device sort per column at build time
+    if (d->n_columns > 0 && d->n_docs > 0) {
+      DevBuf<uint64_t> keys; DevBuf<int32_t> idx, rank;
+      if ((rc = keys.alloc((size_t)d->n_docs)) || (rc = idx.alloc((size_t)d->n_docs)) || (rc = rank.alloc((size_t)d->n_docs))) return rc;
+      for (int c = 0; c < d->n_columns; ++c) {
+        ix->col_code.emplace_back(new DevBuf<uint32_t>);
+        ix->col_distinct.emplace_back(new DevBuf<uint64_t>);
+        if ((rc = ix->col_code.back()->alloc((size_t)d->n_docs))) return rc;
+        if ((rc = ix->col_distinct.back()->alloc((size_t)d->n_docs))) return rc;
+        NRT_CUDA_TRY(cudaMemset(ix->col_code.back()->p, 0, ix->col_code.back()->bytes()));
+        int32_t nd = 0;
+        if ((rc = sort_codes_build(p64[c], p32[c], ph[c], d->n_docs, ix->col_code.back()->p, keys.p, idx.p, rank.p,
+                                   ix->col_distinct.back()->p, &nd))) return rc;
+        ix->col_n_distinct.push_back(nd);
+      }
+    }
     if ((rc = ix->col64_ptrs.upload(p64.data(), p64.size()))) return rc;
     if ((rc = ix->col32_ptrs.upload(p32.data(), p32.size()))) return rc;
     if ((rc = ix->col_has_ptrs.upload(ph.data(), ph.size()))) return rc;
@@ -512,6 +538,8 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
   for (auto& b : ix->col64) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col32) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col_has) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->col_code) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->col_distinct) ix->device_bytes += (int64_t)b->bytes();
   NRT_CUDA_TRY(cudaDeviceSynchronize());
   *out = ix.release();
   return NRTGPU_OK;
@@ -530,8 +558,18 @@ int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix) { return ix ? ix->devi
 // compile + upload a batch into `b` (buffers are reused when large enough); asynchronous on `st`
 static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
                        const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold,
-                       int32_t flags, cudaStream_t st) {
+                       int32_t flags, cudaStream_t st, const nrtgpu_sort* sort = nullptr) {
   if (!ix || !queries || (n_clauses > 0 && !clauses)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
+  const bool sorted = sort && sort->kind != NRTGPU_SORT_RELEVANCE;
+  b->sort_kind = sorted ? sort->kind : 0; b->sort_column = sorted ? sort->column : 0; b->sort_reverse = sorted ? (sort->reverse != 0) : 0;
+  b->sort_missing_value = sorted ? sort->missing_value : 0;
+  if (sorted) {
+    if (sort->kind != NRTGPU_SORT_COLUMN && sort->kind != NRTGPU_SORT_DOCID) NRT_FAIL(NRTGPU_ERR_INVALID, "bad sort kind");
+    if (sort->kind == NRTGPU_SORT_COLUMN && (sort->column < 0 || sort->column >= ix->n_columns))
+      NRT_FAIL(NRTGPU_ERR_INVALID, "sort column out of range (field does not support sorting: no doc values)");
+    if (ix->ctx->engine_stream) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sorted search needs the probe engine");
+    total_hits_threshold = INT32_MAX;   // every match is visited: exact totalHits
+  }
   if (nq <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: nq must be > 0");
   // LazyQueueTopScoreDocCollectorManager.java:93-96: numHits must be > 0
   if (top_k <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "numHits must be > 0; please use TotalHitCountCollectorManager if you just need the total hit count");
@@ -625,7 +663,8 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     else o.driver_mask = should_term_mask;                             // pure disjunction: every SHOULD list drives
     uint32_t all_terms = n_term >= 32 ? 0xffffffffu : ((1u << n_term) - 1u);
     o.has_non_driver = (!o.dense_driver && (all_terms & ~o.driver_mask)) ? 1 : 0;
-    if (q.has_after) {
+    if (q.has_after && sorted) o.has_after = 1;   // after_key is patched on the device (sort_after_kernel)
+    else if (q.has_after) {
       o.has_after = 1;
       int64_t local = (int64_t)q.after_doc - ix->doc_base;
       uint32_t ord = float_to_ordered(q.after_score);
@@ -636,6 +675,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   }
   b->wide_slots = max_terms > 4 || top_k > v2::kMaxTopKStream;
   b->use_probe = !b->wide_slots && !ix->ctx->engine_stream;
+  if (sorted && b->wide_slots) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sorted search: more than 4 term clauses or top_k > 512 is not on the GPU path");
   if (!b->wide_slots) {
     // slices of equal size, a multiple of the 1024-doc granule, at most 512K docs: a 1.25M-doc shard is 3 x 417K, not 2.38 -> 3 x 512K
     const int64_t n_sl = std::max<int64_t>(1, ((int64_t)ix->n_docs + v2::kSliceDocs - 1) / v2::kSliceDocs);
@@ -673,14 +713,14 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   // (tf-pattern bound, deferred scoring, MAXSCORE): their work items come first
   auto is_simple = [&](int qi) {
     const DevQuery& o = dq[(size_t)qi];
-    return o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
+    return !sorted && o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
            o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
   };
   // 0: probe kernel, simple; 1: probe kernel, generic (a posting list leads); 2: window/stream kernel (no list can lead)
   auto engine_class = [&](int qi) {
     if (is_simple(qi)) return 0;
     if (!b->use_probe) return 2;
-    return dq[(size_t)qi].dense_driver ? 2 : 1;
+    return 1;   // the probe kernel also sweeps whole doc ranges when no posting list can lead (match-all / range-led queries)
   };
   std::vector<int32_t>& wq = b->h_wq; std::vector<int32_t>& ws = b->h_ws;
   wq.clear(); ws.clear();
@@ -722,6 +762,26 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if ((rc = b->queries.upload_async(b->h_dq.data(), b->h_dq.size(), st))) return rc;
   if ((rc = b->work_query.upload_async(wq.data(), wq.size(), st))) return rc;
   if ((rc = b->work_slice.upload_async(ws.data(), ws.size(), st))) return rc;
+  if (sorted) {
+    bool any_after = false;
+    b->h_after_docs.assign((size_t)nq, 0);
+    for (int qi = 0; qi < nq; ++qi) if (queries[qi].has_after) { any_after = true; b->h_after_docs[(size_t)qi] = queries[qi].after_doc; }
+    if (any_after && sort->kind == NRTGPU_SORT_COLUMN && !sort->after_values) NRT_FAIL(NRTGPU_ERR_INVALID, "sorted searchAfter needs after_values");
+    if ((rc = b->sort_missing_code.alloc(1))) return rc;
+    if ((rc = b->after_docs.upload_async(b->h_after_docs.data(), (size_t)nq, st))) return rc;
+    if (sort->after_values) { if ((rc = b->after_values.upload_async(sort->after_values, (size_t)nq, st))) return rc; }
+    else if ((rc = b->after_values.alloc((size_t)nq))) return rc;
+    SortAfterLaunch A;
+    A.queries = b->queries.p; A.nq = nq; A.after_docs = b->after_docs.p; A.after_values = b->after_values.p;
+    A.kind = sort->kind; A.reverse = sort->reverse != 0; A.doc_base = ix->doc_base; A.n_docs = ix->n_docs;
+    const bool col = sort->kind == NRTGPU_SORT_COLUMN;
+    A.distinct = col ? ix->col_distinct[(size_t)sort->column]->p : nullptr;
+    A.n_distinct = col ? ix->col_n_distinct[(size_t)sort->column] : 0;
+    A.missing_value = sort->missing_value; A.missing_code = b->sort_missing_code.p;
+    sort_after_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(A);
+    NRT_CUDA_TRY(cudaGetLastError());
+    if ((rc = b->out_sort_values.alloc((size_t)nq * top_k))) return rc;
+  }
   if ((rc = b->theta.alloc((size_t)nq))) return rc;
   if ((rc = b->total_hits.alloc((size_t)nq))) return rc;
   if ((rc = b->slice_keys.alloc((size_t)nq * b->n_lists * top_k))) return rc;
@@ -812,6 +872,9 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
         P.slice_keys = L.slice_keys; P.slice_cnt = L.slice_cnt;
         P.deadline_ns = b->limits_active ? b->deadline_ns : 0; P.clock0 = b->clock0.p; P.timed_out = b->timed_out.p;
         P.terminate_after = b->ta_scalar; P.terminated = b->terminated.p;
+        P.sort_kind = b->sort_kind; P.sort_reverse = b->sort_reverse;
+        P.sort_codes = b->sort_kind == NRTGPU_SORT_COLUMN ? b->ix->col_code[(size_t)b->sort_column]->p : nullptr;
+        P.sort_missing_code = b->sort_missing_code.p;
         if (P.deadline_ns) {
           NRT_CUDA_TRY(cudaMemsetAsync(b->clock0.p, 0, sizeof(unsigned long long), st));
           NRT_CUDA_TRY(cudaMemsetAsync(b->timed_out.p, 0, b->timed_out.bytes(), st));
@@ -892,6 +955,17 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   M.out_total = b->bound_total; M.out_flags = b->bound_flags;
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
+  if (b->sort_kind != NRTGPU_SORT_RELEVANCE) {   // FieldDoc values of the final hits; scores become NaN
+    SortValuesLaunch V;
+    V.docs = b->o_docs(); V.counts = b->o_counts(); V.nq = b->nq; V.top_k = b->top_k; V.doc_base = b->ix->doc_base; V.kind = b->sort_kind;
+    const bool col = b->sort_kind == NRTGPU_SORT_COLUMN;
+    V.c64 = col ? b->ix->col64[(size_t)b->sort_column]->p : nullptr; V.c32 = col ? b->ix->col32[(size_t)b->sort_column]->p : nullptr;
+    V.has = col ? b->ix->col_has[(size_t)b->sort_column]->p : nullptr; V.missing_value = b->sort_missing_value;
+    V.out_values = b->out_sort_values.p; V.out_scores = b->o_scores();
+    const int n = b->nq * b->top_k;
+    sort_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V);
+    NRT_CUDA_TRY(cudaGetLastError());
+  }
   NRT_CUDA_TRY(cudaEventRecord(ev[2], st));
   b->runs_recorded++;
   b->ran = true;
@@ -1070,7 +1144,7 @@ static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int3
                             const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold, int32_t flags,
                             const nrtgpu_search_limits* limits, void* stream, int32_t* d_record, int32_t* out_docs, float* out_scores,
                             int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
-                            uint8_t* out_terminated_early) {
+                            uint8_t* out_terminated_early, const nrtgpu_sort* sort = nullptr, int64_t* out_sort_values = nullptr) {
   if (!ix) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool: NULL index");
   // take a cached workspace (device buffers survive between calls: no cudaMalloc on the request path)
   nrtgpu_batch* b = nullptr;
@@ -1080,13 +1154,19 @@ static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int3
   }
   if (!b) b = new nrtgpu_batch;
   b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
-  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream);
+  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream, sort);
   if (!rc) rc = batch_set_limits(b, limits, (cudaStream_t)stream);
   if (!rc && d_record) rc = nrtgpu_batch_bind_packed(b, d_record);
   if (!rc) rc = nrtgpu_batch_run(b, stream);
   if (!rc) {
     if (d_record) { cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; } }
-    else rc = batch_fetch_impl(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+    else {
+      if (out_sort_values && b->sort_kind != NRTGPU_SORT_RELEVANCE) {
+        cudaError_t e = cudaMemcpyAsync(out_sort_values, b->out_sort_values.p, (size_t)nq * top_k * sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; }
+      }
+      if (!rc) rc = batch_fetch_impl(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+    }
   }
   b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
   {
@@ -1112,6 +1192,18 @@ int nrtgpu_search_bool_ex(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_
                           uint8_t* out_terminated_early) {
   return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, limits, stream, nullptr,
                           out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+}
+
+int nrtgpu_search_sorted(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t flags,
+                         const nrtgpu_sort* sort, const nrtgpu_search_limits* limits, void* stream,
+                         int32_t* out_docs, int64_t* out_sort_values, int32_t* out_counts,
+                         int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
+                         uint8_t* out_terminated_early) {
+  if (!sort) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_sorted: NULL sort");
+  return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, INT32_MAX, flags, limits, stream, nullptr,
+                          out_docs, nullptr, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early,
+                          sort, out_sort_values);
 }
 
 int nrtgpu_search_bool_packed(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,

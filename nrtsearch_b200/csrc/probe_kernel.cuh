@@ -28,6 +28,7 @@
 // Results are bit-identical to the exhaustive oracle (tests/test_gpu_parity.py, tests/test_gpu_probe.py).
 #pragma once
 #include "stream_kernel.cuh"
+#include "sort_kernel.cuh"
 
 namespace nrtgpu {
 namespace v3 {
@@ -97,6 +98,11 @@ struct ProbeLaunch {
   int32_t* timed_out;            // [nq]
   long long terminate_after;     // 0: none
   int32_t* terminated;           // [nq]
+  // sort-by-field (generic instantiation): the key of a hit is (order-preserving code of its sort value, ~doc) instead
+  // of (score, ~doc); see sort_kernel.cuh
+  int32_t sort_kind, sort_reverse;
+  const uint32_t* sort_codes;    // [n_docs] codes of the sort column (0 = doc without a value)
+  const uint32_t* sort_missing_code;   // [1] code of the sort's missing value
 };
 
 struct alignas(128) ProbeSmem {
@@ -131,6 +137,7 @@ struct alignas(128) ProbeSmem {
   uint32_t drv_mask, ess_mask, plane_mask, long_mask, short_mask, global_mask;
   int32_t short_total;             // staged postings of the short lists (aligned)
   int32_t g1;                      // end of the current run (granule of the slice)
+  int32_t run_d0, run_d1;          // doc range of the current run
   int32_t staged;                  // the current run issued TMA copies
   int wi;
   int skip;                        // the claimed item is not processed (abort flag set)
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
         if (complete && cnt_first >= 0 && g_lo < g_hi)
           atomicAdd(&L.total_hits[qi], (unsigned long long)(sm.s_ib[cnt_first] - sm.s_ia[cnt_first]));
       } else {
-        ess = sm.q.driver_mask & all;
+        ess = sm.q.dense_driver ? 0u : (sm.q.driver_mask & all);   // dense: every doc of the slice is visited, all lists are probed
         drv = ess;
         for (int t = 0; t < n_term; ++t) {
           uint32_t below = 0;
@@ -520,8 +527,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     unsigned long long dbg_post = 0; unsigned int dbg_runs = 0, dbg_rounds = 0, dbg_flush = 0, dbg_staged = 0;
     const long long t_setup = L.stats ? clock64() : 0ll;
 
+    const bool dense = !kSimple && sm.q.dense_driver != 0;
+    const uint32_t sort_missing = (!kSimple && L.sort_kind == NRTGPU_SORT_COLUMN) ? *L.sort_missing_code : 0u;
     int g0 = g_lo;
-    if (drv_mask == 0u) g0 = g_hi;   // nothing leads (every list non-essential): the slice cannot contribute
+    if (drv_mask == 0u && !dense) g0 = g_hi;   // nothing leads (every list non-essential): the slice cannot contribute
     bool first_run = true;
     while (g0 < g_hi) {
       // ---------------- run = the longest granule range [g0, g1) whose long-list segments fit the stage
@@ -546,6 +555,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
         const int32_t d0 = slice_base + (g0 << kLogGran);
         const int64_t d1_64 = (int64_t)slice_base + ((int64_t)g1 << kLogGran);
         const int32_t d1 = d1_64 > (int64_t)L.ix.n_docs ? L.ix.n_docs : (int32_t)d1_64;
+        sm.run_d0 = d0; sm.run_d1 = d1;
         // run bounds of every list: skip data where the list has it, else a search by doc (staged short lists: in shared
         // memory once resident -- their first-run bounds are fixed up below; lists read from global memory: there)
         for (int s = 0; s < n_term; ++s) {
@@ -660,21 +670,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
             const int p = atomicAdd(&sm.cand_count, 1);
             if (p < kCand) { sm.cand[p] = park[j]; pmask &= ~(1u << j); } else full = true;
           }
-        while (!full && ct < n_term) {
-          const uint32_t n_t = ((drv_mask >> ct) & 1u) ? sm.s_rb[ct] - sm.s_ra[ct] : 0u;
+        const int ct_end = dense ? n_term + 1 : n_term;   // dense: one more "list" = every doc of the run
+        while (!full && ct < ct_end) {
+          const bool t_dense = ct == n_term;
+          const uint32_t n_t = t_dense ? (uint32_t)(sm.run_d1 - sm.run_d0) : (((drv_mask >> ct) & 1u) ? sm.s_rb[ct] - sm.s_ra[ct] : 0u);
           if (cb >= n_t) { ++ct; cb = 0; continue; }
-          const int t = ct;
-          const uint32_t need = sm.s_need[t];
+          const int t = t_dense ? 0 : ct;
+          const uint32_t need = t_dense ? ((n_term >= 32) ? 0xffffffffu : ((1u << n_term) - 1u)) : sm.s_need[t];
           const uint32_t need_plane = need & plane_mask, need_long = need & long_mask, need_short = need & short_mask,
                          need_glob = need & global_mask;
-          const bool t_staged = ((long_mask | short_mask) >> t) & 1u;
+          const bool t_staged = !t_dense && (((long_mask | short_mask) >> t) & 1u);
           const bool t_ess = (ess_mask >> t) & 1u;
-          const uint32_t candbelow = sm.s_candbelow[t], cntbefore = sm.s_cntbefore[t];
+          const uint32_t candbelow = t_dense ? 0u : sm.s_candbelow[t], cntbefore = t_dense ? 0u : sm.s_cntbefore[t];
+          const int32_t dense_d0 = sm.run_d0;
           const int32_t* sdoc_t = sm.sdocs + ((int)sm.s_ra[t] + sm.s_sdelta[t]);   // posting x of the run segment: sdoc_t[x]
           const uint8_t* sf8_t = sm.sf8 + ((int)sm.s_ra[t] + sm.s_sdelta[t]);
           const int32_t* gdoc_t = sm.s_gdocs[t] + sm.s_ra[t];
           const uint8_t* gf8_t = sm.s_gf8[t] + sm.s_ra[t];
-          const uint32_t tshift = 8u * (uint32_t)t;
+          const uint32_t tshift = t_dense ? 0u : 8u * (uint32_t)t;
           // software pipeline: the postings of the NEXT round are fetched before the current round is processed
           // (generic pointers: one load path for staged -- shared memory -- and plane / global -- HBM -- driver lists)
           const int32_t* dptr = t_staged ? sdoc_t : gdoc_t;
@@ -683,8 +696,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
 #pragma unroll
           for (int j = 0; j < kR; ++j) {
             const uint32_t x = cb + (uint32_t)(j * kThreads + tid);
-            nd[j] = 0; nf[j] = 0;
-            if (x < n_t) { nd[j] = dptr[x]; nf[j] = fptr[x]; }
+            nd[j] = -1; nf[j] = 0;   // doc -1: no posting
+            if (x < n_t) {
+              if (t_dense) nd[j] = dense_d0 + (int32_t)x; else { nd[j] = dptr[x]; nf[j] = fptr[x]; }
+            }
           }
           while (!full && cb < n_t) {
             const unsigned long long theta = sm.theta;
@@ -692,12 +707,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
             int32_t doc[kR]; uint32_t word[kR];
             uint32_t pbyte[kR][kT];
 #pragma unroll
-            for (int j = 0; j < kR; ++j) { doc[j] = nd[j]; word[j] = nf[j] << tshift; }   // word == 0: no posting (tf >= 1)
+            for (int j = 0; j < kR; ++j) { doc[j] = nd[j]; word[j] = nf[j] << tshift; }
             // plane gathers of every posting of the round (2-bit tf codes, all in flight together)
             // (lanes without a posting gather byte 0 of the plane: harmless, and the branches stay CTA-uniform)
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
-              const uint32_t d4 = (uint32_t)doc[j] >> 2;
+              const uint32_t d4 = (uint32_t)max(doc[j], 0) >> 2;
               pbyte[j][0] = 0u; pbyte[j][1] = 0u; pbyte[j][2] = 0u; pbyte[j][3] = 0u;
               if (need_plane & 1u) pbyte[j][0] = (uint32_t)__ldg(pl0 + d4);
               if (need_plane & 2u) pbyte[j][1] = (uint32_t)__ldg(pl1 + d4);
@@ -710,15 +725,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
 #pragma unroll
               for (int j = 0; j < kR; ++j) {
                 const uint32_t x = nb + (uint32_t)(j * kThreads + tid);
-                nd[j] = 0; nf[j] = 0;
-                if (x < n_t) { nd[j] = dptr[x]; nf[j] = fptr[x]; }
+                nd[j] = -1; nf[j] = 0;
+                if (x < n_t) {
+                  if (t_dense) nd[j] = dense_d0 + (int32_t)x; else { nd[j] = dptr[x]; nf[j] = fptr[x]; }
+                }
               }
             }
             // searches of the staged lists (shared memory; overlaps the gathers)
             if (need_long | need_short | need_glob) {
 #pragma unroll
               for (int j = 0; j < kR; ++j) {
-                if (!word[j]) continue;
+                if (doc[j] < 0) continue;
                 const int g = (doc[j] - slice_base) >> kLogGran;
 #pragma unroll
                 for (int u = 0; u < kT; ++u) {
@@ -738,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
             // ownership, hit count, bound test / clause evaluation, append
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
-              if (!word[j]) continue;
+              if (doc[j] < 0) continue;
               uint32_t v = word[j];
               if (need_plane) {
                 // the four gathered bytes side by side; the doc's 2-bit code of every plane with one shift and one mask
@@ -760,7 +777,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
                 float score;
                 if (!evaluate_doc(L, sm, doc[j], v, &score)) continue;
                 ++my_hits;
-                entry = make_key(score, doc[j]);
+                if (L.sort_kind == NRTGPU_SORT_RELEVANCE) entry = make_key(score, doc[j]);
+                else {   // TopFieldCollector: the key is the doc's sort value (order-preserving code), ties by doc id
+                  uint32_t code = 0;
+                  if (L.sort_kind == NRTGPU_SORT_COLUMN) { code = __ldg(L.sort_codes + doc[j]); if (code == 0u) code = sort_missing; }
+                  entry = ((uint64_t)sort_hi(L.sort_kind, L.sort_reverse, code, doc[j]) << 32) | (uint32_t)(~(uint32_t)doc[j]);
+                }
                 if (!(entry > theta) || (has_after && !(entry < after_key))) continue;
               }
               const int p = atomicAdd(&sm.cand_count, 1);

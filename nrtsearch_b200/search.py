@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _native
 from ._native import (Clause, CollectionTimeoutException, NrtGpuError, NrtGpuUnsupported, Query as CQuery, SearchLimits,
-                      check)
+                      Sort as CSort, check)
 from .index import HostShard, PinnedDesc
 
 TOTAL_HITS_THRESHOLD = 1000  # SearchRequestProcessor.TOTAL_HITS_THRESHOLD (:102)
@@ -135,6 +135,66 @@ class RelevanceCollector:
             return None
         return SearchLimits(self.timeout_sec, self.elapsed_sec, 1 if self.disallow_partial_results else 0,
                             self.terminate_after, self.terminate_after_max_recall_count)
+
+
+def float_to_sortable_int(f: float) -> int:
+    """NumericUtils.floatToSortableInt: the order-preserving int of a float (how FloatFieldDef stores doc values)."""
+    b = int(np.float32(f).view(np.int32))
+    return b ^ ((b >> 31) & 0x7fffffff)
+
+
+def double_to_sortable_long(d: float) -> int:
+    """NumericUtils.doubleToSortableLong."""
+    b = int(np.float64(d).view(np.int64))
+    return b ^ ((b >> 63) & 0x7fffffffffffffff)
+
+
+@dataclass(frozen=True)
+class SortType:
+    """SortType of the search request for ONE sort field (SortParser.parseSort :54-95): a numeric doc-value column, or
+    "docid". field_type picks the missing value exactly as the reference's FieldDefs do (IntFieldDef.java:103,
+    LongFieldDef.java:103, FloatFieldDef.java:105, DoubleFieldDef.java:105): MAX / +Infinity when missing_last, else
+    MIN / -Infinity -- irrespective of reverse."""
+    field: object            # column id, or "docid"
+    reverse: bool = False
+    missing_last: bool = False
+    field_type: str = "long"   # int | long | float | double
+
+    def missing_value(self) -> int:
+        hi = self.missing_last
+        if self.field_type == "int":
+            return 2**31 - 1 if hi else -(2**31)
+        if self.field_type == "long":
+            return 2**63 - 1 if hi else -(2**63)
+        if self.field_type == "float":
+            return float_to_sortable_int(float("inf") if hi else float("-inf"))
+        if self.field_type == "double":
+            return double_to_sortable_long(float("inf") if hi else float("-inf"))
+        raise ValueError(f"field type {self.field_type} does not support sorting")
+
+
+@dataclass
+class SortFieldCollector:
+    """SortFieldCollector.java:44-105: numHitsToCollect + the query's Sort; searchAfter is a FieldDoc (value, doc)."""
+    num_hits_to_collect: int
+    sort: SortType = None
+    timeout_sec: float = 0.0
+    terminate_after: int = 0
+
+
+@dataclass
+class FieldDoc:
+    doc: int
+    value: int   # fields[0], sortable-long domain
+
+
+@dataclass
+class SortedResult:
+    docs: np.ndarray          # int32 [nq, k]
+    sort_values: np.ndarray   # int64 [nq, k] FieldDoc.fields[0] of every hit
+    counts: np.ndarray
+    total_hits: np.ndarray
+    relation: np.ndarray
 
 
 def _f32(x: float) -> np.float32:
@@ -328,6 +388,29 @@ class GpuIndexSearcher:
                                               out.scores.ctypes.data, out.counts.ctypes.data, out.total_hits.ctypes.data,
                                               out.relation.ctypes.data, out.hit_timeout.ctypes.data,
                                               out.terminated_early.ctypes.data))
+        return out
+
+    def search_sorted(self, queries: Sequence[object], collector: SortFieldCollector,
+                      search_after: Optional[Sequence[Optional[FieldDoc]]] = None, stream: int = 0) -> SortedResult:
+        """IndexSearcher.search(query, TopFieldCollectorManager(sort, numHits, after, threshold)) for a batch."""
+        st = collector.sort
+        after_sd = None if search_after is None else [None if a is None else ScoreDoc(a.doc, 0.0) for a in search_after]
+        carr, ncl, qarr, nq = compile_queries(queries, after_sd)
+        k = collector.num_hits_to_collect
+        out = SortedResult(np.zeros((nq, k), np.int32), np.zeros((nq, k), np.int64), np.zeros(nq, np.int32), np.zeros(nq, np.int64),
+                           np.zeros(nq, np.uint8))
+        av = None
+        if search_after is not None:
+            av = np.array([0 if a is None else a.value for a in search_after], np.int64)
+        docid = st.field == "docid"
+        cs = CSort(2 if docid else 1, 0 if docid else int(st.field), 1 if st.reverse else 0, 0, 0 if docid else st.missing_value(),
+                   None if av is None else av.ctypes.data)
+        lim = None
+        if collector.timeout_sec > 0 or collector.terminate_after > 0:
+            lim = SearchLimits(collector.timeout_sec, 0.0, 0, collector.terminate_after, 0)
+        check(self._lib.nrtgpu_search_sorted(self.index.handle, carr, ncl, qarr, nq, k, 0, C.byref(cs), None if lim is None else C.byref(lim),
+                                             C.c_void_p(stream), out.docs.ctypes.data, out.sort_values.ctypes.data, out.counts.ctypes.data,
+                                             out.total_hits.ctypes.data, out.relation.ctypes.data, None, None))
         return out
 
     def search(self, query, collector: RelevanceCollector) -> TopDocs:

@@ -23,6 +23,11 @@ class OrcQuery(C.Structure):
                 ("has_after", C.c_int32), ("after_doc", C.c_int32), ("after_score", C.c_float)]
 
 
+class OrcSort(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("reverse", C.c_int32), ("reserved", C.c_int32),
+                ("missing_value", C.c_int64)]
+
+
 class OrcIndex(C.Structure):
     _fields_ = [
         ("n_docs", C.c_int32), ("doc_base", C.c_int32), ("n_terms", C.c_int32),
@@ -88,6 +93,8 @@ def lib() -> C.CDLL:
         L.orc_search_limits.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_search_sorted.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32,
+                                        C.c_int32, C.POINTER(OrcSort), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_merge_topk.restype = None
         L.orc_merge_topk.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
         L.orc_vector_score_f32.restype = C.c_float
@@ -239,6 +246,23 @@ def search_terminate_after(oix: OracleIndex, carr, ncl: int, qarr, nq: int, top_
     if rc != 0:
         raise ValueError(f"orc_search_limits failed ({rc})")
     return docs, scores, counts, total, rel, term
+
+
+def search_sorted(oix: OracleIndex, carr, ncl: int, qarr, nq: int, top_k: int, kind: int, column: int = 0, reverse: bool = False,
+                  missing_value: int = 0, after_values=None, n_threads: int = 0):
+    """TopFieldCollector semantics: returns docs [nq,k], sort values [nq,k] (int64), counts, total hits."""
+    docs = np.zeros((nq, top_k), np.int32)
+    vals = np.zeros((nq, top_k), np.int64)
+    counts = np.zeros(nq, np.int32)
+    total = np.zeros(nq, np.int64)
+    st = OrcSort(kind, column, 1 if reverse else 0, 0, missing_value)
+    av = None if after_values is None else np.ascontiguousarray(after_values, np.int64)
+    rc = lib().orc_search_sorted(C.byref(oix.ix), C.cast(carr, C.POINTER(OrcClause)), C.cast(qarr, C.POINTER(OrcQuery)), nq, top_k,
+                                 n_threads, C.byref(st), None if av is None else av.ctypes.data, docs.ctypes.data, vals.ctypes.data,
+                                 counts.ctypes.data, total.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"orc_search_sorted failed ({rc})")
+    return docs, vals, counts, total
 
 
 def merge_topk(docs, scores, counts, top_k):

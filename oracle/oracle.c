@@ -72,8 +72,11 @@ float orc_bm25_score(float weight, float freq, uint8_t norm, const float cache[2
 /* Order of reference src/main/java/org/apache/lucene/search/LazyQueueTopScoreDocCollector.java:129-143
  * (= Lucene HitQueue): higher score first; equal score => lower doc first. The heap root is the WORST
  * kept hit. */
-typedef struct { float score; int32_t doc; } hit_t;
+/* k: sort-by-field key (0 in relevance mode): larger k ranks first, then the relevance order (TopFieldCollector: sort value,
+ * then doc id -- scores are all 0 there) */
+typedef struct { float score; int32_t doc; uint64_t k; } hit_t;
 static inline int hit_worse(hit_t a, hit_t b) { /* a ranks after b */
+  if (a.k != b.k) return a.k < b.k;
   return a.score < b.score || (a.score == b.score && a.doc > b.doc);
 }
 typedef struct { hit_t* h; int n, cap; } heap_t;
@@ -97,6 +100,7 @@ static void heap_push(heap_t* q, hit_t x) {
 }
 static int hit_cmp_best_first(const void* a, const void* b) {
   const hit_t* x = (const hit_t*)a; const hit_t* y = (const hit_t*)b;
+  if (x->k != y->k) return x->k > y->k ? -1 : 1;
   if (x->score > y->score) return -1;
   if (x->score < y->score) return 1;
   return (x->doc > y->doc) - (x->doc < y->doc);
@@ -110,7 +114,14 @@ typedef struct {
    * single-threaded: docs arrive in doc order, the first terminate_after are collected, later ones are only counted,
    * up to terminate_after_max_recall_count, and set terminatedEarly */
   int64_t terminate_after, max_recall, seen; int terminated_early;
+  /* sort-by-field (reference SortFieldCollector.java:44-105 -> Lucene TopFieldCollector): sort_kind 1 = numeric doc-value
+   * column, 2 = doc id; a doc without a value sorts as missing_value (NumberFieldDef.java:275-276) */
+  int sort_kind, sort_reverse; const int64_t* sort_col; const uint8_t* sort_has; int64_t sort_missing; uint64_t after_k;
 } collector_t;
+static inline uint64_t sort_k(const collector_t* c, int64_t v) {
+  uint64_t u = (uint64_t)v ^ 0x8000000000000000ull;
+  return c->sort_reverse ? u : ~u;
+}
 static inline void collect(collector_t* c, int32_t doc, float score) {
   if (c->terminate_after > 0) {
     int64_t cur = ++c->seen;
@@ -122,9 +133,14 @@ static inline void collect(collector_t* c, int32_t doc, float score) {
     }
   }
   c->total_hits++;
-  if (c->has_after && (score > c->after_score || (score == c->after_score && doc <= c->after_doc))) return;
-  if (c->pq.n < c->top_k) { hit_t h = {score, doc}; heap_push(&c->pq, h); return; }
-  hit_t x = {score, doc};
+  uint64_t k = 0;
+  if (c->sort_kind) {
+    int64_t v = c->sort_kind == 2 ? (int64_t)doc : ((c->sort_has && !c->sort_has[doc]) ? c->sort_missing : c->sort_col[doc]);
+    k = sort_k(c, v); score = 0.0f;
+    if (c->has_after && (k > c->after_k || (k == c->after_k && doc <= c->after_doc))) return;   /* FieldDoc searchAfter */
+  } else if (c->has_after && (score > c->after_score || (score == c->after_score && doc <= c->after_doc))) return;
+  if (c->pq.n < c->top_k) { hit_t h = {score, doc, k}; heap_push(&c->pq, h); return; }
+  hit_t x = {score, doc, k};
   if (hit_worse(c->pq.h[0], x)) { c->pq.h[0] = x; heap_sift_down(&c->pq, 0); }
 }
 static inline float collector_min_competitive(const collector_t* c) { /* -inf until the queue is full */
@@ -336,7 +352,8 @@ static void search_one_pruned_disjunction(const orc_index* ix, cl_t* cl, int ncl
 static void run_query(const orc_index* ix, const orc_clause* cls, const orc_query* q, int top_k,
                       int64_t threshold, int mode, window_t* w, float (*field_cache)[256], uint8_t* cache_ready,
                       int32_t* out_docs, float* out_scores, int32_t* out_count, int64_t* out_total, uint8_t* out_rel,
-                      int64_t terminate_after, int64_t max_recall, uint8_t* out_terminated) {
+                      int64_t terminate_after, int64_t max_recall, uint8_t* out_terminated,
+                      const orc_sort* sort, int64_t after_value, int64_t* out_values) {
   cl_t cl[64];
   int ncl = q->clause_end - q->clause_begin;
   *out_count = 0; *out_total = 0; *out_rel = 0;
@@ -348,6 +365,15 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
   col.has_after = q->has_after; col.after_score = q->after_score; col.after_doc = q->after_doc - ix->doc_base;
   col.terminate_after = terminate_after; col.max_recall = max_recall > terminate_after ? max_recall : terminate_after;
   if (terminate_after > 0) mode = 0;   /* the wrapper sees every matching doc: exhaustive evaluation */
+  if (sort && sort->kind) {
+    mode = 0;
+    col.sort_kind = sort->kind; col.sort_reverse = sort->reverse; col.sort_missing = sort->missing_value;
+    if (sort->kind == 1) {
+      if (sort->column < 0 || sort->column >= ix->n_columns) { *out_count = -1; return; }
+      col.sort_col = ix->columns[sort->column]; col.sort_has = ix->column_has ? ix->column_has[sort->column] : NULL;
+    }
+    col.after_k = sort_k(&col, sort->kind == 2 ? (int64_t)(q->after_doc - ix->doc_base) : after_value);
+  }
   int pruned = 0;
   int pure_term_disj = 1;
   for (int i = 0; i < ncl; ++i) if (cl[i].kind != ORC_TERM || cl[i].occur != ORC_SHOULD) pure_term_disj = 0;
@@ -358,7 +384,13 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
   }
   int n = col.pq.n;
   qsort(col.pq.h, (size_t)n, sizeof(hit_t), hit_cmp_best_first);
-  for (int i = 0; i < n; ++i) { out_docs[i] = col.pq.h[i].doc + ix->doc_base; out_scores[i] = col.pq.h[i].score; }
+  for (int i = 0; i < n; ++i) {
+    out_docs[i] = col.pq.h[i].doc + ix->doc_base; out_scores[i] = col.pq.h[i].score;
+    if (out_values) {
+      uint64_t u = col.sort_reverse ? col.pq.h[i].k : ~col.pq.h[i].k;
+      out_values[i] = col.sort_kind == 2 ? (int64_t)out_docs[i] : (int64_t)(u ^ 0x8000000000000000ull);
+    }
+  }
   *out_count = n; *out_total = col.total_hits; *out_rel = (pruned || col.terminated_early) ? 1 : 0;
   if (out_terminated) *out_terminated = (uint8_t)col.terminated_early;
   free(col.pq.h);
@@ -372,10 +404,36 @@ int orc_search(const orc_index* ix, const orc_clause* clauses, const orc_query* 
                            out_counts, out_total, out_rel, NULL);
 }
 
+static int search_all(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
+                      int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
+                      int32_t terminate_after, int32_t terminate_after_max_recall, const orc_sort* sort, const int64_t* after_values,
+                      int32_t* out_docs, float* out_scores, int64_t* out_values, int32_t* out_counts, int64_t* out_total,
+                      uint8_t* out_rel, uint8_t* out_terminated);
+
+int orc_search_sorted(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq, int32_t top_k,
+                      int32_t n_threads, const orc_sort* sort, const int64_t* after_values, int32_t* out_docs,
+                      int64_t* out_values, int32_t* out_counts, int64_t* out_total) {
+  float* scores = (float*)malloc(sizeof(float) * (size_t)nq * (size_t)top_k);
+  uint8_t* rel = (uint8_t*)malloc((size_t)nq);
+  int rc = search_all(ix, clauses, queries, nq, top_k, INT32_MAX, 0, n_threads, 0, 0, sort, after_values, out_docs, scores, out_values,
+                      out_counts, out_total, rel, NULL);
+  free(scores); free(rel);
+  return rc;
+}
+
 int orc_search_limits(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
                       int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
                       int32_t terminate_after, int32_t terminate_after_max_recall,
                       int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
+                      uint8_t* out_rel, uint8_t* out_terminated) {
+  return search_all(ix, clauses, queries, nq, top_k, total_hits_threshold, mode, n_threads, terminate_after, terminate_after_max_recall,
+                    NULL, NULL, out_docs, out_scores, NULL, out_counts, out_total, out_rel, out_terminated);
+}
+
+static int search_all(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
+                      int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
+                      int32_t terminate_after, int32_t terminate_after_max_recall, const orc_sort* sort, const int64_t* after_values,
+                      int32_t* out_docs, float* out_scores, int64_t* out_values, int32_t* out_counts, int64_t* out_total,
                       uint8_t* out_rel, uint8_t* out_terminated) {
   if (top_k <= 0) return -1;
   /* manager rule: threshold = max(threshold, numHits)
@@ -396,7 +454,8 @@ int orc_search_limits(const orc_index* ix, const orc_clause* clauses, const orc_
     for (int qi = 0; qi < nq; ++qi) {
       run_query(ix, clauses, &queries[qi], top_k, thr, mode, w, fc, ready, out_docs + (size_t)qi * top_k,
                 out_scores + (size_t)qi * top_k, &out_counts[qi], &out_total[qi], &out_rel[qi],
-                terminate_after, terminate_after_max_recall, out_terminated ? &out_terminated[qi] : NULL);
+                terminate_after, terminate_after_max_recall, out_terminated ? &out_terminated[qi] : NULL,
+                sort, after_values ? after_values[qi] : 0, out_values ? out_values + (size_t)qi * top_k : NULL);
       if (out_counts[qi] < 0) {
 #pragma omp atomic write
         bad = 1;
@@ -440,7 +499,7 @@ void orc_merge_topk(int32_t n_lists, int32_t nq, int32_t top_k, const int32_t* d
     int n = 0;
     for (int l = 0; l < n_lists; ++l) {
       size_t base = ((size_t)l * nq + q) * top_k;
-      for (int i = 0; i < counts[(size_t)l * nq + q]; ++i) { buf[n].doc = docs[base + i]; buf[n].score = scores[base + i]; ++n; }
+      for (int i = 0; i < counts[(size_t)l * nq + q]; ++i) { buf[n].doc = docs[base + i]; buf[n].score = scores[base + i]; buf[n].k = 0; ++n; }
     }
     qsort(buf, (size_t)n, sizeof(hit_t), hit_cmp_best_first);
     if (n > top_k) n = top_k;
@@ -518,7 +577,7 @@ int orc_blend_rrf(int32_t n_retrievers, int32_t top_in, const int32_t* docs, con
       float add = boosts[r] / (float)(k + (i + 1));
       int j = 0;
       for (; j < n; ++j) if (m[j].doc == d) break;
-      if (j == n) { m[n].doc = d; m[n].score = add; ++n; } else m[j].score += add;
+      if (j == n) { m[n].doc = d; m[n].score = add; m[n].k = 0; ++n; } else m[j].score += add;
     }
   }
   *total = n;
@@ -540,7 +599,7 @@ void orc_rescore_combine(int32_t n_hits, int32_t window, int32_t* docs, float* s
   for (int i = 0; i < n_hits; ++i) {
     float s = second_matches[i] ? (float)(query_weight * (double)scores[i] + rescore_weight * (double)second_scores[i])
                                 : (float)(query_weight * (double)scores[i]);
-    h[i].doc = docs[i]; h[i].score = s;
+    h[i].doc = docs[i]; h[i].score = s; h[i].k = 0;
   }
   qsort(h, (size_t)n_hits, sizeof(hit_t), hit_cmp_best_first);
   for (int i = 0; i < n_hits; ++i) { docs[i] = h[i].doc; scores[i] = h[i].score; }

@@ -92,6 +92,14 @@ int orc_search(const orc_index* ix, const orc_clause* clauses, const orc_query* 
                int32_t top_k, int32_t total_hits_threshold, int32_t mode, int32_t n_threads,
                int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total,
                uint8_t* out_rel);
+/* sort-by-field top-k (TopFieldCollector semantics; reference SortFieldCollector.java:44-105, NumberFieldDef.java:266-278):
+ * kind 1 = numeric doc-value column (values in the sortable-long domain), 2 = doc id; ties by doc asc; a doc without a
+ * value sorts as missing_value; searchAfter = (after_values[q], queries[q].after_doc) when queries[q].has_after */
+typedef struct { int32_t kind, column, reverse, reserved; int64_t missing_value; } orc_sort;
+int orc_search_sorted(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq, int32_t top_k,
+                      int32_t n_threads, const orc_sort* sort, const int64_t* after_values, int32_t* out_docs,
+                      int64_t* out_values, int32_t* out_counts, int64_t* out_total);
+
 /* the same search under TerminateAfterWrapper (sequential semantics: docs in doc order; reference
  * src/main/java/com/yelp/nrtsearch/server/search/TerminateAfterWrapper.java:85-162): terminate_after 0 = none */
 int orc_search_limits(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq,
