@@ -200,6 +200,58 @@ int nrtgpu_search_sorted(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
                          int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
                          uint8_t* out_terminated_early);
 
+/* Aggregating "additional collectors" over ALL docs matching each query (ScoreMode.COMPLETE: RelevanceCollector.java:55-62
+ * forces totalHitsThreshold = MAX when additional collectors exist; fan-out SearchCollectorManager.java:192-198):
+ *   NRTGPU_AGG_TERMS  counts per distinct value of a numeric doc-value column, the `size` buckets with the largest
+ *                     (order_desc) or smallest counts, totalBuckets, totalOtherCounts
+ *                     ({Int,Long,Float,Double}TermsCollectorManager + TermsCollectorManager.fillBucketResultByCount);
+ *   NRTGPU_AGG_MIN / _MAX / _SUM   over the column's values as doubles (Min/Max/SumCollectorManager with the value
+ *                     source doc['field'].value; no matching doc => Double.MAX_VALUE / -Double.MAX_VALUE / 0.0).
+ * value_type says how the column's sortable long maps back to the number: 0 int / long, 1 float, 2 double.
+ * Docs without a value contribute nothing. Bucket ties at the cut are unordered in the reference (hash-map order); here
+ * the smaller value wins. Float / double sums are accumulated in a different order than the reference's single
+ * thread: equal within 1e-12 relative; int / long sums below 2^53, min, max and every count are exact. */
+enum { NRTGPU_AGG_TERMS = 1, NRTGPU_AGG_MIN = 2, NRTGPU_AGG_MAX = 3, NRTGPU_AGG_SUM = 4 };
+typedef struct {
+  int32_t kind, column, value_type;
+  int32_t size;        /* terms: buckets returned (<= 2048) */
+  int32_t order_desc;  /* terms: 1 = largest counts first (BucketOrder DESC by count, the default) */
+  int32_t reserved;
+} nrtgpu_aggregation;
+typedef struct {       /* caller-allocated outputs of one aggregation (unused pointers may be NULL) */
+  double* values;          /* [nq]        min / max / sum */
+  int64_t* bucket_keys;    /* [nq*size]   terms: column values (sortable-long domain) */
+  int32_t* bucket_counts;  /* [nq*size] */
+  int32_t* n_buckets;      /* [nq]        buckets filled */
+  int32_t* total_buckets;  /* [nq]        BucketResult.totalBuckets */
+  int64_t* other_counts;   /* [nq]        BucketResult.totalOtherCounts */
+} nrtgpu_aggregation_result;
+/* nrtgpu_search_bool with additional collectors: hits as usual (exact totalHits), plus the aggregations */
+int nrtgpu_search_bool_aggs(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                            const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t flags,
+                            const nrtgpu_aggregation* aggs, int32_t n_aggs, const nrtgpu_aggregation_result* results,
+                            void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                            int64_t* out_total_hits);
+
+/* QueryRescorer second pass (QueryRescore.java:39-57 -> Lucene QueryRescorer.rescore): query q of the batch evaluated on
+ * ITS OWN hit list docs[q][0..counts[q]) (global doc ids): out_matches / out_scores [nq*n_hits]. */
+int nrtgpu_score_docs(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                      const nrtgpu_query* queries, int32_t nq, int32_t n_hits, const int32_t* docs,
+                      const int32_t* counts /*[nq] or NULL*/, void* stream, uint8_t* out_matches, float* out_scores);
+/* The whole rescore on the device, Lucene QueryRescorer.rescore(searcher, hits, topN = windowSize) as QueryRescore.java:52-57
+ * calls it: second pass over EVERY first-pass hit + QueryRescore.combine (double math -> float) + re-sort
+ * (score desc, doc asc), in place; out_counts[q] = min(counts[q], window) hits are kept.
+ * docs / scores [nq*n_hits] HOST buffers (in/out), n_hits <= 4096. */
+int nrtgpu_rescore_query(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t n_hits, const int32_t* counts,
+                         int32_t window, double query_weight, double rescore_weight, void* stream,
+                         int32_t* docs, float* scores, int32_t* out_counts /*[nq] or NULL*/);
+
+/* Fetch phase on doc-value columns (SearchHandler.java:397-522, FillDocsTask.fetchFromDocVales / LoadedDocValues): the
+ * values of n_cols columns for n hits (global doc ids): out_values / out_has [n_cols*n]. */
+int nrtgpu_fetch_columns(nrtgpu_index* ix, const int32_t* col_ids, int32_t n_cols, const int32_t* docs, int32_t n,
+                         void* stream, int64_t* out_values, uint8_t* out_has);
+
 /* Split form: compile+upload once, launch many times with everything resident in HBM. */
 int nrtgpu_batch_prepare(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
                          const nrtgpu_query* queries, int32_t nq, int32_t top_k,

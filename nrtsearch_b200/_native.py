@@ -71,6 +71,16 @@ class Sort(C.Structure):
                 ("missing_value", C.c_int64), ("after_values", C.c_void_p)]
 
 
+class Aggregation(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("value_type", C.c_int32), ("size", C.c_int32),
+                ("order_desc", C.c_int32), ("reserved", C.c_int32)]
+
+
+class AggregationResult(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("bucket_keys", C.c_void_p), ("bucket_counts", C.c_void_p), ("n_buckets", C.c_void_p),
+                ("total_buckets", C.c_void_p), ("other_counts", C.c_void_p)]
+
+
 class Query(C.Structure):
     _fields_ = [("clause_begin", C.c_int32), ("clause_end", C.c_int32), ("min_should_match", C.c_int32),
                 ("has_after", C.c_int32), ("after_doc", C.c_int32), ("after_score", C.c_float)]
@@ -82,7 +92,7 @@ NRTGPU_SYMBOLS = [
     "nrtgpu_index_close", "nrtgpu_index_device_bytes", "nrtgpu_search_bool", "nrtgpu_batch_prepare",
     "nrtgpu_batch_run", "nrtgpu_batch_fetch", "nrtgpu_batch_device_results", "nrtgpu_batch_stats",
     "nrtgpu_batch_stage_ms", "nrtgpu_batch_reset_timing", "nrtgpu_batch_bind_output", "nrtgpu_batch_free", "nrtgpu_search_knn", "nrtgpu_search_knn_timed", "nrtgpu_merge_topk_device",
-    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified", "nrtgpu_packed_words", "nrtgpu_search_sorted", "nrtgpu_search_bool_ex", "nrtgpu_search_bool_packed", "nrtgpu_batch_set_limits", "nrtgpu_batch_fetch_ex", "nrtgpu_batch_bind_packed", "nrtgpu_merge_topk_packed",
+    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified", "nrtgpu_packed_words", "nrtgpu_search_sorted", "nrtgpu_search_bool_aggs", "nrtgpu_score_docs", "nrtgpu_rescore_query", "nrtgpu_fetch_columns", "nrtgpu_search_bool_ex", "nrtgpu_search_bool_packed", "nrtgpu_batch_set_limits", "nrtgpu_batch_fetch_ex", "nrtgpu_batch_bind_packed", "nrtgpu_merge_topk_packed",
 ]
 
 _gpu = None
@@ -127,6 +137,13 @@ def gpu_lib() -> C.CDLL:
                                                   C.c_int32, C.c_int32, C.POINTER(SearchLimits), C.c_void_p, C.c_void_p]
         lib.nrtgpu_search_sorted.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32,
                                              C.c_int32, C.POINTER(Sort), C.POINTER(SearchLimits), C.c_void_p] + [C.c_void_p] * 7
+        lib.nrtgpu_search_bool_aggs.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32, C.c_int32,
+                                                C.POINTER(Aggregation), C.c_int32, C.POINTER(AggregationResult), C.c_void_p] + [C.c_void_p] * 4
+        lib.nrtgpu_score_docs.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nrtgpu_rescore_query.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32, C.c_void_p,
+                                             C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nrtgpu_fetch_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nrtgpu_batch_set_limits.argtypes = [C.c_void_p, C.POINTER(SearchLimits)]
         lib.nrtgpu_batch_fetch_ex.argtypes = [C.c_void_p] * 9
         lib.nrtgpu_packed_words.argtypes = [C.c_int32, C.c_int32]

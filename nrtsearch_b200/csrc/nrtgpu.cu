@@ -5,10 +5,12 @@
 #include "stream_kernel.cuh"
 #include "probe_kernel.cuh"
 #include "sort_kernel.cuh"
+#include "collect_kernel.cuh"
 #include "knn_kernel.cuh"
 #include "hybrid_kernel.cuh"
 
 #include <algorithm>
+#include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -178,6 +180,8 @@ struct nrtgpu_index {
   // reusable batch workspaces of the one-shot entry point (nrtgpu_search_bool), one per concurrent caller
   std::mutex ws_mu;
   std::mutex knn_mu;          // one kNN call at a time per index: they share knn_scratch
+  std::mutex fetch_mu;        // fetch-phase scratch
+  DevBuf<int32_t> f_cols, f_docs; DevBuf<int64_t> f_vals; DevBuf<uint8_t> f_has;
   KnnScratch knn_scratch;
   std::vector<nrtgpu_batch*> ws_free;
   ~nrtgpu_index();
@@ -229,6 +233,14 @@ struct nrtgpu_batch {
   DevBuf<int64_t> after_values; DevBuf<int32_t> after_docs; DevBuf<uint32_t> sort_missing_code;
   DevBuf<int64_t> out_sort_values;
   std::vector<int32_t> h_after_docs;
+  // additional collectors (aggregations)
+  std::vector<nrtgpu_aggregation> aggs;
+  DevBuf<unsigned int> agg_counts[kMaxAggs];
+  DevBuf<unsigned long long> agg_dvals[kMaxAggs];
+  DevBuf<AggLaunch> agg_launch;
+  DevBuf<int64_t> agg_keys; DevBuf<int32_t> agg_cnts, agg_n, agg_tot; DevBuf<long long> agg_other;
+  // second pass of QueryRescorer (nrtgpu_score_docs / nrtgpu_rescore_query)
+  DevBuf<int32_t> sd_docs, sd_counts; DevBuf<uint8_t> sd_match; DevBuf<float> sd_scores, sd_first;
   bool limits_active = false, disallow_partial = false;
   double timeout_sec = 0.0;
   long long deadline_ns = 0;       // budget from the first work item on (0: none)
@@ -260,6 +272,7 @@ struct nrtgpu_batch {
 
 static void free_batch(nrtgpu_batch* b) { delete b; }
 extern "C" {
+static int batch_fetch_aggs(nrtgpu_batch* b, cudaStream_t st, const nrtgpu_aggregation_result* out);
 static int batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* lim, cudaStream_t st);
 static int batch_fetch_impl(nrtgpu_batch* b, void* stream_, int32_t* out_docs, float* out_scores, int32_t* out_counts,
                             int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout, uint8_t* out_terminated_early);
@@ -558,8 +571,27 @@ int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix) { return ix ? ix->devi
 // compile + upload a batch into `b` (buffers are reused when large enough); asynchronous on `st`
 static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
                        const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold,
-                       int32_t flags, cudaStream_t st, const nrtgpu_sort* sort = nullptr) {
+                       int32_t flags, cudaStream_t st, const nrtgpu_sort* sort = nullptr, const nrtgpu_aggregation* aggs = nullptr,
+                       int32_t n_aggs = 0) {
   if (!ix || !queries || (n_clauses > 0 && !clauses)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_batch_prepare: NULL argument");
+  b->aggs.clear();
+  if (n_aggs > 0) {
+    if (!aggs || n_aggs > kMaxAggs) NRT_FAIL(NRTGPU_ERR_INVALID, "at most 8 aggregations per search");
+    if (ix && ix->ctx->engine_stream) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "aggregations need the probe engine");
+    for (int i = 0; i < n_aggs; ++i) {
+      const nrtgpu_aggregation& a = aggs[i];
+      if (a.kind < NRTGPU_AGG_TERMS || a.kind > NRTGPU_AGG_SUM) NRT_FAIL(NRTGPU_ERR_INVALID, "bad aggregation kind");
+      if (!ix || a.column < 0 || a.column >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "aggregation column out of range");
+      if (a.value_type < 0 || a.value_type > 2) NRT_FAIL(NRTGPU_ERR_INVALID, "bad aggregation value_type");
+      if (a.kind == NRTGPU_AGG_TERMS) {
+        if (a.size <= 0 || a.size > kAggChunk) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "terms aggregation: size must be in [1, 2048]");
+        const int64_t cells = (int64_t)nq * ix->col_n_distinct[(size_t)a.column];
+        if (cells * 4 > (2ll << 30)) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "terms aggregation: batch x distinct values exceeds the 2 GB count table");
+      }
+      b->aggs.push_back(a);
+    }
+    total_hits_threshold = INT32_MAX;   // RelevanceCollector.java:55-62: additional collectors force exact collection
+  }
   const bool sorted = sort && sort->kind != NRTGPU_SORT_RELEVANCE;
   b->sort_kind = sorted ? sort->kind : 0; b->sort_column = sorted ? sort->column : 0; b->sort_reverse = sorted ? (sort->reverse != 0) : 0;
   b->sort_missing_value = sorted ? sort->missing_value : 0;
@@ -675,6 +707,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   }
   b->wide_slots = max_terms > 4 || top_k > v2::kMaxTopKStream;
   b->use_probe = !b->wide_slots && !ix->ctx->engine_stream;
+  if (n_aggs > 0 && b->wide_slots) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "aggregations: more than 4 term clauses or top_k > 512 is not on the GPU path");
   if (sorted && b->wide_slots) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sorted search: more than 4 term clauses or top_k > 512 is not on the GPU path");
   if (!b->wide_slots) {
     // slices of equal size, a multiple of the 1024-doc granule, at most 512K docs: a 1.25M-doc shard is 3 x 417K, not 2.38 -> 3 x 512K
@@ -713,7 +746,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   // (tf-pattern bound, deferred scoring, MAXSCORE): their work items come first
   auto is_simple = [&](int qi) {
     const DevQuery& o = dq[(size_t)qi];
-    return !sorted && o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
+    return !sorted && n_aggs == 0 && o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
            o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
   };
   // 0: probe kernel, simple; 1: probe kernel, generic (a posting list leads); 2: window/stream kernel (no list can lead)
@@ -875,6 +908,31 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
         P.sort_kind = b->sort_kind; P.sort_reverse = b->sort_reverse;
         P.sort_codes = b->sort_kind == NRTGPU_SORT_COLUMN ? b->ix->col_code[(size_t)b->sort_column]->p : nullptr;
         P.sort_missing_code = b->sort_missing_code.p;
+        P.aggs = nullptr;
+        if (!b->aggs.empty()) {
+          AggLaunch A; std::memset(&A, 0, sizeof(A));
+          A.n_aggs = (int32_t)b->aggs.size();
+          for (int i = 0; i < A.n_aggs; ++i) {
+            const nrtgpu_aggregation& a = b->aggs[(size_t)i];
+            A.a[i].kind = a.kind; A.a[i].column = a.column; A.a[i].value_type = a.value_type;
+            if (a.kind == NRTGPU_AGG_TERMS) {
+              const int32_t nb = b->ix->col_n_distinct[(size_t)a.column];
+              A.a[i].n_buckets = nb;
+              if ((rc_dbg = b->agg_counts[i].alloc((size_t)b->nq * (size_t)std::max(nb, 1)))) return rc_dbg;
+              NRT_CUDA_TRY(cudaMemsetAsync(b->agg_counts[i].p, 0, b->agg_counts[i].bytes(), st));
+              A.a[i].counts = b->agg_counts[i].p; A.codes[i] = b->ix->col_code[(size_t)a.column]->p;
+            } else {
+              if ((rc_dbg = b->agg_dvals[i].alloc((size_t)b->nq))) return rc_dbg;
+              // min starts at +inf / max at -inf in ordered-double space, sum at 0.0 (the "unset" values are applied at fetch)
+              const int fill = a.kind == NRTGPU_AGG_MIN ? 0xff : 0x00;
+              NRT_CUDA_TRY(cudaMemsetAsync(b->agg_dvals[i].p, fill, b->agg_dvals[i].bytes(), st));
+              A.a[i].dvals = b->agg_dvals[i].p;
+            }
+          }
+          if ((rc_dbg = b->agg_launch.upload_async(&A, 1, st))) return rc_dbg;
+          NRT_CUDA_TRY(cudaStreamSynchronize(st));   // A is a stack object
+          P.aggs = b->agg_launch.p;
+        }
         if (P.deadline_ns) {
           NRT_CUDA_TRY(cudaMemsetAsync(b->clock0.p, 0, sizeof(unsigned long long), st));
           NRT_CUDA_TRY(cudaMemsetAsync(b->timed_out.p, 0, b->timed_out.bytes(), st));
@@ -1016,6 +1074,45 @@ int nrtgpu_batch_fetch_ex(nrtgpu_batch* b, void* stream_, int32_t* out_docs, flo
   return batch_fetch_impl(b, stream_, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
 }
 
+// aggregation results of the last run -> caller buffers
+static int batch_fetch_aggs(nrtgpu_batch* b, cudaStream_t st, const nrtgpu_aggregation_result* out) {
+  const int nq = b->nq;
+  for (size_t i = 0; i < b->aggs.size(); ++i) {
+    const nrtgpu_aggregation& a = b->aggs[i];
+    const nrtgpu_aggregation_result& r = out[i];
+    if (a.kind == NRTGPU_AGG_TERMS) {
+      int rc;
+      const size_t n = (size_t)nq * a.size;
+      if ((rc = b->agg_keys.alloc(n)) || (rc = b->agg_cnts.alloc(n)) || (rc = b->agg_n.alloc((size_t)nq)) || (rc = b->agg_tot.alloc((size_t)nq)) ||
+          (rc = b->agg_other.alloc((size_t)nq))) return rc;
+      AggTermsLaunch T;
+      T.counts = b->agg_counts[i].p; T.n_buckets = b->ix->col_n_distinct[(size_t)a.column]; T.nq = nq; T.size = a.size; T.order_desc = a.order_desc != 0;
+      T.distinct = b->ix->col_distinct[(size_t)a.column]->p;
+      T.out_keys = b->agg_keys.p; T.out_counts = b->agg_cnts.p; T.out_n = b->agg_n.p; T.out_total_buckets = b->agg_tot.p; T.out_other = b->agg_other.p;
+      agg_terms_topk_kernel<<<nq, 256, 0, st>>>(T);
+      NRT_CUDA_TRY(cudaGetLastError());
+      if (r.bucket_keys) NRT_CUDA_TRY(cudaMemcpyAsync(r.bucket_keys, b->agg_keys.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      if (r.bucket_counts) NRT_CUDA_TRY(cudaMemcpyAsync(r.bucket_counts, b->agg_cnts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (r.n_buckets) NRT_CUDA_TRY(cudaMemcpyAsync(r.n_buckets, b->agg_n.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (r.total_buckets) NRT_CUDA_TRY(cudaMemcpyAsync(r.total_buckets, b->agg_tot.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (r.other_counts) NRT_CUDA_TRY(cudaMemcpyAsync(r.other_counts, b->agg_other.p, (size_t)nq * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      NRT_CUDA_TRY(cudaStreamSynchronize(st));   // the scratch is reused by the next terms aggregation
+    } else if (r.values) {
+      std::vector<unsigned long long> h((size_t)nq);
+      NRT_CUDA_TRY(cudaMemcpyAsync(h.data(), b->agg_dvals[i].p, (size_t)nq * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      NRT_CUDA_TRY(cudaStreamSynchronize(st));
+      for (int q = 0; q < nq; ++q) {
+        double v;
+        if (a.kind == NRTGPU_AGG_SUM) std::memcpy(&v, &h[(size_t)q], sizeof(v));
+        else if (a.kind == NRTGPU_AGG_MAX) v = h[(size_t)q] == 0ull ? -DBL_MAX : ordered_to_double(h[(size_t)q]);              // MaxCollectorManager.UNSET_VALUE
+        else v = h[(size_t)q] == 0xffffffffffffffffull ? DBL_MAX : ordered_to_double(h[(size_t)q]);                          // MinCollectorManager.UNSET_VALUE
+        r.values[q] = v;
+      }
+    }
+  }
+  return NRTGPU_OK;
+}
+
 // deadline / terminateAfter of the batch (SearchCutoffWrapper / TerminateAfterWrapper semantics, see include/nrtgpu.h)
 static int batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* lim, cudaStream_t st) {
   b->limits_active = false; b->disallow_partial = false; b->timeout_sec = 0.0; b->terminate_after_max_recall = 0;
@@ -1144,7 +1241,8 @@ static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int3
                             const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold, int32_t flags,
                             const nrtgpu_search_limits* limits, void* stream, int32_t* d_record, int32_t* out_docs, float* out_scores,
                             int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation, uint8_t* out_hit_timeout,
-                            uint8_t* out_terminated_early, const nrtgpu_sort* sort = nullptr, int64_t* out_sort_values = nullptr) {
+                            uint8_t* out_terminated_early, const nrtgpu_sort* sort = nullptr, int64_t* out_sort_values = nullptr,
+                            const nrtgpu_aggregation* aggs = nullptr, int32_t n_aggs = 0, const nrtgpu_aggregation_result* agg_out = nullptr) {
   if (!ix) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool: NULL index");
   // take a cached workspace (device buffers survive between calls: no cudaMalloc on the request path)
   nrtgpu_batch* b = nullptr;
@@ -1154,7 +1252,7 @@ static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int3
   }
   if (!b) b = new nrtgpu_batch;
   b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
-  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream, sort);
+  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, (cudaStream_t)stream, sort, aggs, n_aggs);
   if (!rc) rc = batch_set_limits(b, limits, (cudaStream_t)stream);
   if (!rc && d_record) rc = nrtgpu_batch_bind_packed(b, d_record);
   if (!rc) rc = nrtgpu_batch_run(b, stream);
@@ -1166,6 +1264,7 @@ static int search_bool_impl(nrtgpu_index* ix, const nrtgpu_clause* clauses, int3
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; }
       }
       if (!rc) rc = batch_fetch_impl(b, stream, out_docs, out_scores, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early);
+      if (!rc && n_aggs > 0 && agg_out) rc = batch_fetch_aggs(b, (cudaStream_t)stream, agg_out);
     }
   }
   b->bound_docs = nullptr; b->bound_scores = nullptr; b->bound_counts = nullptr; b->bound_total = nullptr; b->bound_flags = nullptr;
@@ -1204,6 +1303,108 @@ int nrtgpu_search_sorted(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t
   return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, INT32_MAX, flags, limits, stream, nullptr,
                           out_docs, nullptr, out_counts, out_total_hits, out_relation, out_hit_timeout, out_terminated_early,
                           sort, out_sort_values);
+}
+
+int nrtgpu_search_bool_aggs(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                            const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t flags,
+                            const nrtgpu_aggregation* aggs, int32_t n_aggs, const nrtgpu_aggregation_result* results,
+                            void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                            int64_t* out_total_hits) {
+  if (n_aggs <= 0 || !aggs || !results) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_search_bool_aggs: no aggregations");
+  return search_bool_impl(ix, clauses, n_clauses, queries, nq, top_k, INT32_MAX, flags, nullptr, stream, nullptr, out_docs, out_scores,
+                          out_counts, out_total_hits, nullptr, nullptr, nullptr, nullptr, nullptr, aggs, n_aggs, results);
+}
+
+int nrtgpu_score_docs(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                      const nrtgpu_query* queries, int32_t nq, int32_t n_hits, const int32_t* docs,
+                      const int32_t* counts, void* stream, uint8_t* out_matches, float* out_scores) {
+  if (!ix || !docs || !out_matches || !out_scores || n_hits <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_score_docs: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  nrtgpu_batch* b = nullptr;
+  { std::lock_guard<std::mutex> g(ix->ws_mu); if (!ix->ws_free.empty()) { b = ix->ws_free.back(); ix->ws_free.pop_back(); } }
+  if (!b) b = new nrtgpu_batch;
+  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, 1, INT32_MAX, 0, st);
+  const size_t n = (size_t)nq * n_hits;
+  if (!rc) rc = b->sd_docs.upload_async(docs, n, st);
+  if (!rc && counts) rc = b->sd_counts.upload_async(counts, (size_t)nq, st);
+  if (!rc) rc = b->sd_match.alloc(n);
+  if (!rc) rc = b->sd_scores.alloc(n);
+  if (!rc) {
+    ScoreDocsLaunch S; S.ix = ix->view(); S.clauses = b->clauses.p; S.queries = b->queries.p; S.nq = nq; S.n_hits = n_hits;
+    S.docs = b->sd_docs.p; S.counts = counts ? b->sd_counts.p : nullptr; S.out_matches = b->sd_match.p; S.out_scores = b->sd_scores.p;
+    score_docs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_matches, b->sd_match.p, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, b->sd_scores.p, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; }
+  }
+  { std::lock_guard<std::mutex> g(ix->ws_mu); ix->ws_free.push_back(b); }
+  return rc;
+}
+
+int nrtgpu_rescore_query(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,
+                         const nrtgpu_query* queries, int32_t nq, int32_t n_hits, const int32_t* counts,
+                         int32_t window, double query_weight, double rescore_weight, void* stream,
+                         int32_t* docs, float* scores, int32_t* out_counts) {
+  if (!ix || !docs || !scores || n_hits <= 0 || window <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_query: bad argument");
+  if (n_hits > kHybCap) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_rescore_query: more than 4096 hits per query");
+  cudaStream_t st = (cudaStream_t)stream;
+  nrtgpu_batch* b = nullptr;
+  { std::lock_guard<std::mutex> g(ix->ws_mu); if (!ix->ws_free.empty()) { b = ix->ws_free.back(); ix->ws_free.pop_back(); } }
+  if (!b) b = new nrtgpu_batch;
+  int rc = batch_build(b, ix, clauses, n_clauses, queries, nq, 1, INT32_MAX, 0, st);
+  const size_t n = (size_t)nq * n_hits;
+  // Lucene QueryRescorer.rescore(searcher, hits, topN = windowSize): EVERY first-pass hit is combined and the list
+  // re-sorted (score desc, doc asc); then the first topN are kept
+  std::vector<int32_t> wc((size_t)nq);
+  for (int q = 0; q < nq; ++q) {
+    wc[(size_t)q] = counts ? counts[q] : n_hits;
+    if (wc[(size_t)q] < 0 || wc[(size_t)q] > n_hits) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_query: counts out of range");
+  }
+  if (!rc) rc = b->sd_docs.upload_async(docs, n, st);
+  if (!rc) rc = b->sd_first.upload_async(scores, n, st);
+  if (!rc) rc = b->sd_counts.upload_async(wc.data(), (size_t)nq, st);
+  if (!rc) rc = b->sd_match.alloc(n);
+  if (!rc) rc = b->sd_scores.alloc(n);
+  if (!rc) {
+    ScoreDocsLaunch S; S.ix = ix->view(); S.clauses = b->clauses.p; S.queries = b->queries.p; S.nq = nq; S.n_hits = n_hits;
+    S.docs = b->sd_docs.p; S.counts = b->sd_counts.p; S.out_matches = b->sd_match.p; S.out_scores = b->sd_scores.p;
+    score_docs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S);
+    RescoreLaunch P;
+    P.nq = nq; P.n_hits = n_hits; P.counts = b->sd_counts.p; P.docs = b->sd_docs.p; P.scores = b->sd_first.p;
+    P.second_matches = b->sd_match.p; P.second_scores = b->sd_scores.p; P.query_weight = query_weight; P.rescore_weight = rescore_weight;
+    rescore_combine_kernel<<<nq, kHybThreads, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(docs, b->sd_docs.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores, b->sd_first.p, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = NRTGPU_ERR_CUDA; }
+    if (!rc && out_counts) for (int q = 0; q < nq; ++q) out_counts[q] = std::min(wc[(size_t)q], window);
+  }
+  { std::lock_guard<std::mutex> g(ix->ws_mu); ix->ws_free.push_back(b); }
+  return rc;
+}
+
+int nrtgpu_fetch_columns(nrtgpu_index* ix, const int32_t* col_ids, int32_t n_cols, const int32_t* docs, int32_t n,
+                         void* stream, int64_t* out_values, uint8_t* out_has) {
+  if (!ix || !col_ids || !docs || !out_values || !out_has || n_cols <= 0 || n <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_fetch_columns: bad argument");
+  for (int i = 0; i < n_cols; ++i) if (col_ids[i] < 0 || col_ids[i] >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_fetch_columns: column out of range");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> g(ix->fetch_mu);
+  int rc;
+  const size_t total = (size_t)n_cols * (size_t)n;
+  if ((rc = ix->f_cols.upload_async(col_ids, (size_t)n_cols, st)) || (rc = ix->f_docs.upload_async(docs, (size_t)n, st)) ||
+      (rc = ix->f_vals.alloc(total)) || (rc = ix->f_has.alloc(total))) return rc;
+  FetchLaunch F; F.ix = ix->view(); F.col_ids = ix->f_cols.p; F.n_cols = n_cols; F.docs = ix->f_docs.p; F.n = n;
+  F.out_values = ix->f_vals.p; F.out_has = ix->f_has.p;
+  fetch_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_values, ix->f_vals.p, total * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_has, ix->f_has.p, total, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
+  return NRTGPU_OK;
 }
 
 int nrtgpu_search_bool_packed(nrtgpu_index* ix, const nrtgpu_clause* clauses, int32_t n_clauses,

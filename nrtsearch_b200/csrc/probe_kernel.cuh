@@ -29,6 +29,7 @@
 #pragma once
 #include "stream_kernel.cuh"
 #include "sort_kernel.cuh"
+#include "collect_kernel.cuh"
 
 namespace nrtgpu {
 namespace v3 {
@@ -103,6 +104,7 @@ struct ProbeLaunch {
   int32_t sort_kind, sort_reverse;
   const uint32_t* sort_codes;    // [n_docs] codes of the sort column (0 = doc without a value)
   const uint32_t* sort_missing_code;   // [1] code of the sort's missing value
+  const AggLaunch* aggs;         // additional collectors (generic instantiation; device pointer, NULL: none)
 };
 
 struct alignas(128) ProbeSmem {
@@ -777,6 +779,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
                 float score;
                 if (!evaluate_doc(L, sm, doc[j], v, &score)) continue;
                 ++my_hits;
+                if (L.aggs) agg_collect(*L.aggs, L.ix, qi, doc[j]);   // additional collectors see every matching doc
                 if (L.sort_kind == NRTGPU_SORT_RELEVANCE) entry = make_key(score, doc[j]);
                 else {   // TopFieldCollector: the key is the doc's sort value (order-preserving code), ties by doc id
                   uint32_t code = 0;

@@ -22,8 +22,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native
-from ._native import (Clause, CollectionTimeoutException, NrtGpuError, NrtGpuUnsupported, Query as CQuery, SearchLimits,
-                      Sort as CSort, check)
+from ._native import (Aggregation as CAgg, AggregationResult as CAggResult, Clause, CollectionTimeoutException, NrtGpuError,
+                      NrtGpuUnsupported, Query as CQuery, SearchLimits, Sort as CSort, check)
 from .index import HostShard, PinnedDesc
 
 TOTAL_HITS_THRESHOLD = 1000  # SearchRequestProcessor.TOTAL_HITS_THRESHOLD (:102)
@@ -180,6 +180,37 @@ class SortFieldCollector:
     sort: SortType = None
     timeout_sec: float = 0.0
     terminate_after: int = 0
+
+
+@dataclass(frozen=True)
+class TermsCollector:
+    """TermsCollector over a numeric doc-value field ({Int,Long,Float,Double}TermsCollectorManager): `size` buckets ordered
+    by count (BucketOrder COUNT, desc by default)."""
+    column: int
+    size: int
+    order_desc: bool = True
+    field_type: str = "long"
+
+
+@dataclass(frozen=True)
+class MinCollector:
+    column: int
+    field_type: str = "long"
+
+
+@dataclass(frozen=True)
+class MaxCollector:
+    column: int
+    field_type: str = "long"
+
+
+@dataclass(frozen=True)
+class SumCollector:
+    column: int
+    field_type: str = "long"
+
+
+_VALUE_TYPE = {"int": 0, "long": 0, "float": 1, "double": 2}
 
 
 @dataclass
@@ -412,6 +443,67 @@ class GpuIndexSearcher:
                                              C.c_void_p(stream), out.docs.ctypes.data, out.sort_values.ctypes.data, out.counts.ctypes.data,
                                              out.total_hits.ctypes.data, out.relation.ctypes.data, None, None))
         return out
+
+    def search_with_collectors(self, queries: Sequence[object], collector: RelevanceCollector, additional: Sequence[object],
+                               stream: int = 0):
+        """IndexSearcher.search with additional collectors (SearchCollectorManager fan-out): returns (BatchResult, results)
+        where results[i] is a float64 [nq] array (min / max / sum) or a dict of bucket arrays (terms)."""
+        carr, ncl, qarr, nq = compile_queries(queries)
+        k = collector.num_hits_to_collect
+        out = BatchResult(np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32), np.zeros(nq, np.int64),
+                          np.zeros(nq, np.uint8))
+        aggs = (CAgg * len(additional))()
+        res = (CAggResult * len(additional))()
+        outs = []
+        for i, a in enumerate(additional):
+            vt = _VALUE_TYPE[a.field_type]
+            if isinstance(a, TermsCollector):
+                aggs[i] = CAgg(1, a.column, vt, a.size, 1 if a.order_desc else 0, 0)
+                o = {"keys": np.zeros((nq, a.size), np.int64), "counts": np.zeros((nq, a.size), np.int32), "n": np.zeros(nq, np.int32),
+                     "total_buckets": np.zeros(nq, np.int32), "other_counts": np.zeros(nq, np.int64)}
+                res[i] = CAggResult(None, o["keys"].ctypes.data, o["counts"].ctypes.data, o["n"].ctypes.data,
+                                    o["total_buckets"].ctypes.data, o["other_counts"].ctypes.data)
+            else:
+                kind = 2 if isinstance(a, MinCollector) else 3 if isinstance(a, MaxCollector) else 4
+                aggs[i] = CAgg(kind, a.column, vt, 0, 0, 0)
+                o = np.zeros(nq, np.float64)
+                res[i] = CAggResult(o.ctypes.data, None, None, None, None, None)
+            outs.append(o)
+        check(self._lib.nrtgpu_search_bool_aggs(self.index.handle, carr, ncl, qarr, nq, k, 0, aggs, len(additional), res, C.c_void_p(stream),
+                                                out.docs.ctypes.data, out.scores.ctypes.data, out.counts.ctypes.data,
+                                                out.total_hits.ctypes.data))
+        return out, outs
+
+    def score_docs(self, queries: Sequence[object], docs: np.ndarray, counts: Optional[np.ndarray] = None, stream: int = 0):
+        """Second pass of QueryRescorer: query q on its own hit list -> (matches uint8 [nq, n], scores float32 [nq, n])."""
+        carr, ncl, qarr, nq = compile_queries(queries)
+        d = np.ascontiguousarray(docs, np.int32)
+        cn = None if counts is None else np.ascontiguousarray(counts, np.int32)
+        m, s = np.zeros(d.shape, np.uint8), np.zeros(d.shape, np.float32)
+        check(self._lib.nrtgpu_score_docs(self.index.handle, carr, ncl, qarr, nq, d.shape[1], d.ctypes.data, None if cn is None else cn.ctypes.data,
+                                          C.c_void_p(stream), m.ctypes.data, s.ctypes.data))
+        return m, s
+
+    def rescore_query(self, queries: Sequence[object], docs: np.ndarray, scores: np.ndarray, counts: np.ndarray, window: int,
+                      query_weight: float, rescore_weight: float, stream: int = 0):
+        """QueryRescore (QueryRescore.java:39-57) end to end on the device: returns docs, scores, counts of the rescored lists."""
+        carr, ncl, qarr, nq = compile_queries(queries)
+        d = np.ascontiguousarray(docs, np.int32).copy()
+        s = np.ascontiguousarray(scores, np.float32).copy()
+        cn = np.ascontiguousarray(counts, np.int32)
+        oc = np.zeros(nq, np.int32)
+        check(self._lib.nrtgpu_rescore_query(self.index.handle, carr, ncl, qarr, nq, d.shape[1], cn.ctypes.data, window, query_weight,
+                                             rescore_weight, C.c_void_p(stream), d.ctypes.data, s.ctypes.data, oc.ctypes.data))
+        return d, s, oc
+
+    def fetch_columns(self, columns: Sequence[int], docs: np.ndarray, stream: int = 0):
+        """Fetch phase on doc-value columns: values int64 [n_cols, n], has uint8 [n_cols, n] for the hits `docs`."""
+        cols = np.ascontiguousarray(columns, np.int32)
+        d = np.ascontiguousarray(docs, np.int32).reshape(-1)
+        vals, has = np.zeros((len(cols), len(d)), np.int64), np.zeros((len(cols), len(d)), np.uint8)
+        check(self._lib.nrtgpu_fetch_columns(self.index.handle, cols.ctypes.data, len(cols), d.ctypes.data, len(d), C.c_void_p(stream),
+                                             vals.ctypes.data, has.ctypes.data))
+        return vals, has
 
     def search(self, query, collector: RelevanceCollector) -> TopDocs:
         return self.search_batch([query], collector).top_docs(0)

@@ -95,6 +95,9 @@ def lib() -> C.CDLL:
                                         C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_search_sorted.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32,
                                         C.c_int32, C.POINTER(OrcSort), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_match_bitmap.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_void_p]
+        L.orc_score_docs.argtypes = [C.POINTER(OrcIndex), C.POINTER(OrcClause), C.POINTER(OrcQuery), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_merge_topk.restype = None
         L.orc_merge_topk.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
         L.orc_vector_score_f32.restype = C.c_float
@@ -263,6 +266,29 @@ def search_sorted(oix: OracleIndex, carr, ncl: int, qarr, nq: int, top_k: int, k
     if rc != 0:
         raise ValueError(f"orc_search_sorted failed ({rc})")
     return docs, vals, counts, total
+
+
+def match_bitmap(oix: OracleIndex, carr, qarr, qi: int) -> np.ndarray:
+    """0/1 per doc: the docs query qi matches (the stream the reference's additional collectors see)."""
+    out = np.zeros(oix.ix.n_docs, np.uint8)
+    q = C.cast(qarr, C.POINTER(OrcQuery))
+    rc = lib().orc_match_bitmap(C.byref(oix.ix), C.cast(carr, C.POINTER(OrcClause)), C.byref(q[qi]), out.ctypes.data)
+    if rc != 0:
+        raise ValueError("orc_match_bitmap failed")
+    return out
+
+
+def score_docs(oix: OracleIndex, carr, qarr, nq: int, docs, counts=None):
+    docs = np.ascontiguousarray(docs, np.int32)
+    n_hits = docs.shape[1]
+    cn = None if counts is None else np.ascontiguousarray(counts, np.int32)
+    m = np.zeros((nq, n_hits), np.uint8)
+    s = np.zeros((nq, n_hits), np.float32)
+    rc = lib().orc_score_docs(C.byref(oix.ix), C.cast(carr, C.POINTER(OrcClause)), C.cast(qarr, C.POINTER(OrcQuery)), nq, n_hits,
+                              docs.ctypes.data, None if cn is None else cn.ctypes.data, m.ctypes.data, s.ctypes.data)
+    if rc != 0:
+        raise ValueError("orc_score_docs failed")
+    return m, s
 
 
 def merge_topk(docs, scores, counts, top_k):

@@ -117,12 +117,14 @@ typedef struct {
   /* sort-by-field (reference SortFieldCollector.java:44-105 -> Lucene TopFieldCollector): sort_kind 1 = numeric doc-value
    * column, 2 = doc id; a doc without a value sorts as missing_value (NumberFieldDef.java:275-276) */
   int sort_kind, sort_reverse; const int64_t* sort_col; const uint8_t* sort_has; int64_t sort_missing; uint64_t after_k;
+  uint8_t* match_bitmap;   /* optional: every collected doc is flagged (what the additional collectors see) */
 } collector_t;
 static inline uint64_t sort_k(const collector_t* c, int64_t v) {
   uint64_t u = (uint64_t)v ^ 0x8000000000000000ull;
   return c->sort_reverse ? u : ~u;
 }
 static inline void collect(collector_t* c, int32_t doc, float score) {
+  if (c->match_bitmap) c->match_bitmap[doc] = 1;
   if (c->terminate_after > 0) {
     int64_t cur = ++c->seen;
     if (cur > c->terminate_after) {
@@ -353,7 +355,7 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
                       int64_t threshold, int mode, window_t* w, float (*field_cache)[256], uint8_t* cache_ready,
                       int32_t* out_docs, float* out_scores, int32_t* out_count, int64_t* out_total, uint8_t* out_rel,
                       int64_t terminate_after, int64_t max_recall, uint8_t* out_terminated,
-                      const orc_sort* sort, int64_t after_value, int64_t* out_values) {
+                      const orc_sort* sort, int64_t after_value, int64_t* out_values, uint8_t* match_bitmap) {
   cl_t cl[64];
   int ncl = q->clause_end - q->clause_begin;
   *out_count = 0; *out_total = 0; *out_rel = 0;
@@ -364,6 +366,8 @@ static void run_query(const orc_index* ix, const orc_clause* cls, const orc_quer
   col.pq.h = (hit_t*)malloc(sizeof(hit_t) * (size_t)(top_k > 0 ? top_k : 1)); col.pq.cap = top_k; col.top_k = top_k;
   col.has_after = q->has_after; col.after_score = q->after_score; col.after_doc = q->after_doc - ix->doc_base;
   col.terminate_after = terminate_after; col.max_recall = max_recall > terminate_after ? max_recall : terminate_after;
+  col.match_bitmap = match_bitmap;
+  if (match_bitmap) mode = 0;
   if (terminate_after > 0) mode = 0;   /* the wrapper sees every matching doc: exhaustive evaluation */
   if (sort && sort->kind) {
     mode = 0;
@@ -455,7 +459,7 @@ static int search_all(const orc_index* ix, const orc_clause* clauses, const orc_
       run_query(ix, clauses, &queries[qi], top_k, thr, mode, w, fc, ready, out_docs + (size_t)qi * top_k,
                 out_scores + (size_t)qi * top_k, &out_counts[qi], &out_total[qi], &out_rel[qi],
                 terminate_after, terminate_after_max_recall, out_terminated ? &out_terminated[qi] : NULL,
-                sort, after_values ? after_values[qi] : 0, out_values ? out_values + (size_t)qi * top_k : NULL);
+                sort, after_values ? after_values[qi] : 0, out_values ? out_values + (size_t)qi * top_k : NULL, NULL);
       if (out_counts[qi] < 0) {
 #pragma omp atomic write
         bad = 1;
@@ -463,6 +467,78 @@ static int search_all(const orc_index* ix, const orc_clause* clauses, const orc_
     }
     free(w); free(fc); free(ready);
   }
+  return bad ? -1 : 0;
+}
+
+/* every doc matching ONE query, as a 0/1 byte per doc (the doc stream the reference's additional collectors -- terms /
+ * min / max / sum, SearchCollectorManager.java:192-198 -- receive) */
+int orc_match_bitmap(const orc_index* ix, const orc_clause* clauses, const orc_query* query, uint8_t* out_bitmap /*[n_docs], zeroed*/) {
+  window_t* w = (window_t*)malloc(sizeof(window_t));
+  int nf = ix->n_fields > 0 ? ix->n_fields : 1;
+  float (*fc)[256] = (float (*)[256])malloc(sizeof(float) * 256 * (size_t)nf);
+  uint8_t* ready = (uint8_t*)calloc((size_t)nf, 1);
+  int32_t d[1]; float s[1]; int32_t cnt; int64_t tot; uint8_t rel;
+  run_query(ix, clauses, query, 1, INT32_MAX, 0, w, fc, ready, d, s, &cnt, &tot, &rel, 0, 0, NULL, NULL, 0, NULL, out_bitmap);
+  free(w); free(fc); free(ready);
+  return cnt < 0 ? -1 : 0;
+}
+
+/* QueryRescorer second pass: query q on its own hit list (Lucene QueryRescorer.rescore advances the second query's scorer
+ * to every first-pass hit; reference src/main/java/com/yelp/nrtsearch/server/rescore/QueryRescore.java:52-57) */
+int orc_score_docs(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq, int32_t n_hits,
+                   const int32_t* docs, const int32_t* counts, uint8_t* out_matches, float* out_scores) {
+  int nf = ix->n_fields > 0 ? ix->n_fields : 1;
+  float (*fc)[256] = (float (*)[256])malloc(sizeof(float) * 256 * (size_t)nf);
+  uint8_t* ready = (uint8_t*)calloc((size_t)nf, 1);
+  int bad = 0;
+  for (int q = 0; q < nq && !bad; ++q) {
+    cl_t cl[64];
+    const orc_query* qq = &queries[q];
+    int ncl = qq->clause_end - qq->clause_begin;
+    if (ncl > 64) { bad = 1; break; }
+    ncl = build_clauses(ix, clauses, qq, cl, fc, ready);
+    if (ncl < 0) { bad = 1; break; }
+    int n_req = 0, n_should = 0;
+    for (int i = 0; i < ncl; ++i) {
+      if (cl[i].occur == ORC_MUST || cl[i].occur == ORC_FILTER) n_req++;
+      if (cl[i].occur == ORC_SHOULD) n_should++;
+    }
+    int msm = qq->min_should_match;
+    int need_should = msm > 0 ? msm : (n_req == 0 ? 1 : 0);
+    int n = counts ? counts[q] : n_hits;
+    for (int h = 0; h < n_hits; ++h) {
+      size_t o = (size_t)q * n_hits + h;
+      out_matches[o] = 0; out_scores[o] = 0.0f;
+      if (h >= n) continue;
+      int64_t d = (int64_t)docs[o] - ix->doc_base;
+      if (d < 0 || d >= ix->n_docs) continue;
+      if (ix->live_docs && !ix->live_docs[d]) continue;
+      if (msm > n_should || (n_req == 0 && n_should == 0)) continue;
+      double must_sum = 0.0, should_sum = 0.0; int req_cnt = 0, should_cnt = 0, excluded = 0;
+      for (int i = 0; i < ncl; ++i) {
+        cl_t* c = &cl[i];
+        int present = 0; float s = 0.0f;
+        if (c->kind == ORC_TERM) {
+          int64_t p = lower_bound_i32(c->docs, 0, c->n, (int32_t)d);
+          if (p < c->n && c->docs[p] == (int32_t)d) { present = 1; if (c->occur == ORC_MUST || c->occur == ORC_SHOULD) s = clause_term_score(c, (int32_t)d, c->freqs[p]); }
+        } else if (c->kind == ORC_RANGE_I64) {
+          if (!(c->has && !c->has[d])) { int64_t v = c->col[d]; present = v >= c->lo && v <= c->hi; }
+          s = c->const_score;
+        } else { present = 1; s = c->const_score; }
+        if (!present) continue;
+        switch (c->occur) {
+          case ORC_MUST: must_sum += (double)s; req_cnt++; break;
+          case ORC_FILTER: req_cnt++; break;
+          case ORC_SHOULD: should_sum += (double)s; should_cnt++; break;
+          default: excluded = 1; break;
+        }
+      }
+      if (excluded || req_cnt != n_req || should_cnt < need_should) continue;
+      out_matches[o] = 1;
+      out_scores[o] = combine_score(n_req, msm, must_sum, should_sum, should_cnt);
+    }
+  }
+  free(fc); free(ready);
   return bad ? -1 : 0;
 }
 
