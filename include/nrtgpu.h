@@ -325,6 +325,46 @@ int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const in
                            int32_t* docs, float* scores, const uint8_t* second_matches,
                            const float* second_scores, double query_weight, double rescore_weight);
 
+/* ---- NRT refresh without rebuilding images (ShardSearcherFactory.newSearcher(reader, previous), ShardState.java:506-526).
+ * A shard is searched through ONE image per Lucene leaf (segment); the adaptor numbers (field, term) once per shard, so
+ * clause ids mean the same term in every leaf. A new reader version keeps the images of the leaves it shares with the
+ * previous one and builds images only for the NEW leaves (nrtgpu_index_build with the leaf's docBase); what changes for
+ * the old leaves is
+ *   - their liveDocs (deletes):               nrtgpu_index_set_live_docs   (NULL = no deletes)
+ *   - the index-wide statistics BM25 uses:     nrtgpu_index_update_stats    (docFreq per term, docCount and
+ *     sumTotalTermFreq per field; refreshes the idf inputs, the length caches and the index-time impact bounds).
+ * Both wait for searches in flight on the image. nrtgpu_searcher = the leaves of one reader version: every leaf runs the
+ * batch, the per-leaf pages are merged on the device (TopDocs.merge), totalHits summed, relation GTE if any leaf's is.
+ * The searcher does not own the leaves. */
+int nrtgpu_index_set_live_docs(nrtgpu_index* ix, const uint8_t* live_docs /*[n_docs] 0/1 or NULL*/);
+int nrtgpu_index_update_stats(nrtgpu_index* ix, const int64_t* term_df /*[n_terms] or NULL = unchanged*/,
+                              const int64_t* field_doc_count /*[n_fields]*/, const int64_t* field_sum_ttf /*[n_fields]*/);
+typedef struct nrtgpu_searcher nrtgpu_searcher;
+int nrtgpu_searcher_create(nrtgpu_ctx* ctx, nrtgpu_index* const* leaves, int32_t n_leaves, nrtgpu_searcher** out);
+int nrtgpu_searcher_search_bool(nrtgpu_searcher* s, const nrtgpu_clause* clauses, int32_t n_clauses,
+                                const nrtgpu_query* queries, int32_t nq, int32_t top_k,
+                                int32_t total_hits_threshold, int32_t flags, const nrtgpu_search_limits* limits,
+                                void* stream, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                                int64_t* out_total_hits, uint8_t* out_relation);
+int nrtgpu_searcher_close(nrtgpu_searcher* s);
+
+/* Request micro-batcher: the reference's search API is ONE query per RPC (clientlib/src/main/proto/yelp/nrtsearch/
+ * luceneserver.proto:164), each on its own SERVER-pool thread (GrpcServerExecutorSupplier.java:68-75). Handler threads call
+ * nrtgpu_batcher_submit (blocking) with one flat BooleanQuery; a worker thread owned by the batcher groups the waiting requests
+ * that share (top_k, totalHitsThreshold) into one nrtgpu_search_bool call as soon as max_batch of them wait or the oldest has
+ * waited max_wait_us, and scatters the results. A request that fails compilation is re-run alone, so it cannot fail its
+ * neighbours. nrtgpu_diagnostics carries what SearchResponse.Diagnostics reports per search (SearchHandler.java:261,280,321):
+ * time queued, time of the batched search, and the size of the batch the request rode in. */
+typedef struct nrtgpu_batcher nrtgpu_batcher;
+typedef struct { double queue_ms; double search_ms; int32_t batch_size; int32_t reserved; } nrtgpu_diagnostics;
+int nrtgpu_batcher_create(nrtgpu_index* ix, int32_t max_batch, int32_t max_wait_us, nrtgpu_batcher** out);
+int nrtgpu_batcher_submit(nrtgpu_batcher* b, const nrtgpu_clause* clauses, int32_t n_clauses, int32_t min_should_match,
+                          int32_t top_k, int32_t total_hits_threshold, int32_t* out_docs, float* out_scores,
+                          int32_t* out_count, int64_t* out_total_hits, uint8_t* out_relation,
+                          nrtgpu_diagnostics* diag /* or NULL */);
+int nrtgpu_batcher_stats(nrtgpu_batcher* b, int64_t* n_batches, int64_t* n_requests);
+int nrtgpu_batcher_close(nrtgpu_batcher* b);   /* drains the queue, joins the worker */
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,10 @@ class Sort(C.Structure):
                 ("missing_value", C.c_int64), ("after_values", C.c_void_p)]
 
 
+class Diagnostics(C.Structure):
+    _fields_ = [("queue_ms", C.c_double), ("search_ms", C.c_double), ("batch_size", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Aggregation(C.Structure):
     _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("value_type", C.c_int32), ("size", C.c_int32),
                 ("order_desc", C.c_int32), ("reserved", C.c_int32)]
@@ -92,7 +96,7 @@ NRTGPU_SYMBOLS = [
     "nrtgpu_index_close", "nrtgpu_index_device_bytes", "nrtgpu_search_bool", "nrtgpu_batch_prepare",
     "nrtgpu_batch_run", "nrtgpu_batch_fetch", "nrtgpu_batch_device_results", "nrtgpu_batch_stats",
     "nrtgpu_batch_stage_ms", "nrtgpu_batch_reset_timing", "nrtgpu_batch_bind_output", "nrtgpu_batch_free", "nrtgpu_search_knn", "nrtgpu_search_knn_timed", "nrtgpu_merge_topk_device",
-    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified", "nrtgpu_packed_words", "nrtgpu_search_sorted", "nrtgpu_search_bool_aggs", "nrtgpu_score_docs", "nrtgpu_rescore_query", "nrtgpu_fetch_columns", "nrtgpu_search_bool_ex", "nrtgpu_search_bool_packed", "nrtgpu_batch_set_limits", "nrtgpu_batch_fetch_ex", "nrtgpu_batch_bind_packed", "nrtgpu_merge_topk_packed",
+    "nrtgpu_blend_rrf", "nrtgpu_rescore_combine", "nrtgpu_knn_last_uncertified", "nrtgpu_packed_words", "nrtgpu_search_sorted", "nrtgpu_search_bool_aggs", "nrtgpu_score_docs", "nrtgpu_rescore_query", "nrtgpu_fetch_columns", "nrtgpu_index_set_live_docs", "nrtgpu_index_update_stats", "nrtgpu_searcher_create", "nrtgpu_searcher_search_bool", "nrtgpu_searcher_close", "nrtgpu_batcher_create", "nrtgpu_batcher_submit", "nrtgpu_batcher_stats", "nrtgpu_batcher_close", "nrtgpu_search_bool_ex", "nrtgpu_search_bool_packed", "nrtgpu_batch_set_limits", "nrtgpu_batch_fetch_ex", "nrtgpu_batch_bind_packed", "nrtgpu_merge_topk_packed",
 ]
 
 _gpu = None
@@ -144,6 +148,17 @@ def gpu_lib() -> C.CDLL:
         lib.nrtgpu_rescore_query.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nrtgpu_fetch_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nrtgpu_index_set_live_docs.argtypes = [C.c_void_p, C.c_void_p]
+        lib.nrtgpu_index_update_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nrtgpu_searcher_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+        lib.nrtgpu_searcher_search_bool.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.POINTER(Query), C.c_int32, C.c_int32, C.c_int32,
+                                                    C.c_int32, C.POINTER(SearchLimits), C.c_void_p] + [C.c_void_p] * 5
+        lib.nrtgpu_searcher_close.argtypes = [C.c_void_p]
+        lib.nrtgpu_batcher_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.nrtgpu_batcher_submit.argtypes = [C.c_void_p, C.POINTER(Clause), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Diagnostics)]
+        lib.nrtgpu_batcher_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.nrtgpu_batcher_close.argtypes = [C.c_void_p]
         lib.nrtgpu_batch_set_limits.argtypes = [C.c_void_p, C.POINTER(SearchLimits)]
         lib.nrtgpu_batch_fetch_ex.argtypes = [C.c_void_p] * 9
         lib.nrtgpu_packed_words.argtypes = [C.c_int32, C.c_int32]

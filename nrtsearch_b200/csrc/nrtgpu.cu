@@ -10,6 +10,10 @@
 #include "hybrid_kernel.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -36,25 +40,31 @@ struct nrtgpu_ctx {
 
 // index-time impacts: max over a term's postings of x = tf * cache[norm] (what Lucene keeps as competitive (freq, norm)
 // pairs in its skip data); the BM25 score is monotone in x, so score(weight, max x) bounds the whole list.
+// One warp per term (lists of thousands of postings take a whole CTA's worth of iterations, the millions of tiny lists one
+// each): no per-posting dictionary search, no atomics.
 __global__ void term_max_x_kernel(const int64_t* __restrict__ term_off, int n_terms, const int32_t* __restrict__ term_field,
                                   const int32_t* __restrict__ docs, const uint8_t* __restrict__ f8,
                                   const int64_t* __restrict__ exc_pos, const int32_t* __restrict__ exc_freq, int n_exc,
-                                  const uint8_t* const* __restrict__ norms, const float* __restrict__ caches, int64_t P,
-                                  unsigned int* __restrict__ out_bits) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  int lo = 0, hi = n_terms;   // last term with term_off[t] <= p
-  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (term_off[mid] <= p) lo = mid; else hi = mid; }
-  const int t = lo, f = term_field[t];
-  float freq = (float)f8[p];
-  if (f8[p] == 255) {
-    int a = 0, b = n_exc;
-    while (a < b) { int m = (a + b) >> 1; if (exc_pos[m] < p) a = m + 1; else b = m; }
-    if (a < n_exc && exc_pos[a] == p) freq = (float)exc_freq[a];
-  }
+                                  const uint8_t* const* __restrict__ norms, const float* __restrict__ caches,
+                                  float* __restrict__ out) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_terms) return;
+  const int t = (int)warp, f = term_field[t];
   const uint8_t* nrm = norms[f];
-  const float x = __fmul_rn(freq, caches[f * 256 + (nrm ? nrm[docs[p]] : 1)]);
-  atomicMax(out_bits + t, __float_as_uint(x));   // x > 0: float order == unsigned order
+  const float* cache = caches + f * 256;
+  float m = 0.0f;
+  for (int64_t p = term_off[t] + lane; p < term_off[t + 1]; p += 32) {
+    float freq = (float)f8[p];
+    if (f8[p] == 255) {
+      int a = 0, b = n_exc;
+      while (a < b) { const int mid = (a + b) >> 1; if (exc_pos[mid] < p) a = mid + 1; else b = mid; }
+      if (a < n_exc && exc_pos[a] == p) freq = (float)exc_freq[a];
+    }
+    m = fmaxf(m, __fmul_rn(freq, cache[nrm ? nrm[docs[p]] : 1]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[t] = m;
 }
 
 // 2-bit planes: four docs per byte, min(tf, 3) each
@@ -140,6 +150,7 @@ struct nrtgpu_index {
   std::vector<int32_t> term_gran;    // row of the granule offset table per term, -1 for short lists
   std::vector<int64_t> field_doc_count, field_sum_ttf;
   std::vector<uint8_t> field_has_norms;
+  std::vector<float> field_k1, field_b;
   // device image
   DevBuf<int32_t> post_docs;
   DevBuf<uint8_t> post_f8;
@@ -271,6 +282,32 @@ struct nrtgpu_batch {
 };
 
 static void free_batch(nrtgpu_batch* b) { delete b; }
+
+// index-time impacts: max over a term's postings of tf * cache[norm]; depends on the index-wide avgdl through cache[]
+static int compute_term_max_x(nrtgpu_index* ix) {
+  ix->term_max_x.assign((size_t)ix->n_terms, 0.0f);
+  const int64_t P = ix->n_terms ? ix->term_off[(size_t)ix->n_terms] : 0;
+  if (P <= 0) return NRTGPU_OK;
+  int rc;
+  DevBuf<int64_t> d_off; DevBuf<int32_t> d_tf; DevBuf<float> d_mx;
+  if ((rc = d_off.upload(ix->term_off.data(), ix->term_off.size()))) return rc;
+  if ((rc = d_tf.upload(ix->term_field.data(), ix->term_field.size()))) return rc;
+  if ((rc = d_mx.alloc((size_t)ix->n_terms))) return rc;
+  const int64_t threads = (int64_t)ix->n_terms * 32;
+  term_max_x_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_off.p, ix->n_terms, d_tf.p, ix->post_docs.p, ix->post_f8.p,
+                                                                 ix->exc_pos.p, ix->exc_freq.p, (int)ix->exc_pos.n, ix->norms_ptrs.p,
+                                                                 ix->caches.p, d_mx.p);
+  NRT_CUDA_TRY(cudaGetLastError());
+  NRT_CUDA_TRY(cudaMemcpy(ix->term_max_x.data(), d_mx.p, (size_t)ix->n_terms * sizeof(float), cudaMemcpyDeviceToHost));
+  return NRTGPU_OK;
+}
+
+static int upload_live_docs(nrtgpu_index* ix, const uint8_t* live_docs) {
+  if (!live_docs) { ix->live_bits.n = 0; if (ix->live_bits.p) { cudaFree(ix->live_bits.p); ix->live_bits.p = nullptr; ix->live_bits.cap = 0; } return NRTGPU_OK; }
+  std::vector<uint32_t> bits(((size_t)ix->n_docs + 31) / 32, 0u);
+  for (int32_t i = 0; i < ix->n_docs; ++i) if (live_docs[i]) bits[(size_t)i >> 5] |= 1u << (i & 31);
+  return ix->live_bits.upload(bits.data(), bits.size());
+}
 extern "C" {
 static int batch_fetch_aggs(nrtgpu_batch* b, cudaStream_t st, const nrtgpu_aggregation_result* out);
 static int batch_set_limits(nrtgpu_batch* b, const nrtgpu_search_limits* lim, cudaStream_t st);
@@ -442,6 +479,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
         min_norm[f] = (uint8_t)(mn == 256 ? 0 : mn);
       }
       float k1 = d->field_k1 ? d->field_k1[f] : 1.2f, b = d->field_b ? d->field_b[f] : 0.75f;
+      ix->field_k1.push_back(k1); ix->field_b.push_back(b);
       int64_t dc = d->field_doc_count[f];
       float avgdl = dc > 0 ? (float)((double)d->field_sum_ttf[f] / (double)dc) : 1.0f;
       bm25_cache(k1, b, avgdl, &caches[(size_t)f * 256]);
@@ -496,24 +534,8 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if ((rc = ix->col_has_ptrs.upload(ph.data(), ph.size()))) return rc;
   }
   // index-time impacts (list-wide score bounds for MAXSCORE)
-  ix->term_max_x.assign((size_t)d->n_terms, 0.0f);
-  if (P > 0) {
-    DevBuf<int64_t> d_off; DevBuf<int32_t> d_tf; DevBuf<unsigned int> d_mx;
-    if ((rc = d_off.upload(ix->term_off.data(), ix->term_off.size()))) return rc;
-    if ((rc = d_tf.upload(ix->term_field.data(), ix->term_field.size()))) return rc;
-    if ((rc = d_mx.alloc((size_t)d->n_terms))) return rc;
-    NRT_CUDA_TRY(cudaMemset(d_mx.p, 0, d_mx.bytes()));
-    term_max_x_kernel<<<(unsigned)((P + 255) / 256), 256>>>(d_off.p, d->n_terms, d_tf.p, ix->post_docs.p, ix->post_f8.p,
-                                                            ix->exc_pos.p, ix->exc_freq.p, (int)ix->exc_pos.n, ix->norms_ptrs.p,
-                                                            ix->caches.p, P, d_mx.p);
-    NRT_CUDA_TRY(cudaGetLastError());
-    NRT_CUDA_TRY(cudaMemcpy(ix->term_max_x.data(), d_mx.p, (size_t)d->n_terms * sizeof(float), cudaMemcpyDeviceToHost));
-  }
-  if (d->live_docs) {
-    std::vector<uint32_t> bits(((size_t)d->n_docs + 31) / 32, 0u);
-    for (int32_t i = 0; i < d->n_docs; ++i) if (d->live_docs[i]) bits[i >> 5] |= 1u << (i & 31);
-    if ((rc = ix->live_bits.upload(bits.data(), bits.size()))) return rc;
-  }
+  if ((rc = compute_term_max_x(ix.get()))) return rc;
+  if (d->live_docs && (rc = upload_live_docs(ix.get(), d->live_docs))) return rc;
   // vectors
   if (d->vec_dims > 0 && d->vec_count > 0) {
     if (!d->vectors) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL vectors");
@@ -566,6 +588,31 @@ int nrtgpu_index_close(nrtgpu_index* ix) {
 }
 
 int64_t nrtgpu_index_device_bytes(const nrtgpu_index* ix) { return ix ? ix->device_bytes : 0; }
+
+int nrtgpu_index_set_live_docs(nrtgpu_index* ix, const uint8_t* live_docs) {
+  if (!ix) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_set_live_docs: NULL index");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  NRT_CUDA_TRY(cudaDeviceSynchronize());   // searches in flight on this image finish against the old bitmap
+  return upload_live_docs(ix, live_docs);
+}
+
+int nrtgpu_index_update_stats(nrtgpu_index* ix, const int64_t* term_df, const int64_t* field_doc_count, const int64_t* field_sum_ttf) {
+  if (!ix || !field_doc_count || !field_sum_ttf) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_update_stats: NULL argument");
+  NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+  NRT_CUDA_TRY(cudaDeviceSynchronize());
+  if (term_df) ix->term_df.assign(term_df, term_df + ix->n_terms);
+  ix->field_doc_count.assign(field_doc_count, field_doc_count + ix->n_fields);
+  ix->field_sum_ttf.assign(field_sum_ttf, field_sum_ttf + ix->n_fields);
+  std::vector<float> caches((size_t)ix->n_fields * 256);
+  for (int f = 0; f < ix->n_fields; ++f) {
+    const int64_t dc = ix->field_doc_count[(size_t)f];
+    const float avgdl = dc > 0 ? (float)((double)ix->field_sum_ttf[(size_t)f] / (double)dc) : 1.0f;
+    bm25_cache(ix->field_k1[(size_t)f], ix->field_b[(size_t)f], avgdl, &caches[(size_t)f * 256]);
+  }
+  int rc;
+  if ((rc = ix->caches.upload(caches.data(), caches.size()))) return rc;
+  return compute_term_max_x(ix);   // the impacts are functions of the length cache
+}
 
 // ---- batch compilation: flat BooleanQuery -> DevQuery/DevClause, driver selection, work list ----
 // compile + upload a batch into `b` (buffers are reused when large enough); asynchronous on `st`
@@ -746,7 +793,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   // (tf-pattern bound, deferred scoring, MAXSCORE): their work items come first
   auto is_simple = [&](int qi) {
     const DevQuery& o = dq[(size_t)qi];
-    return !sorted && n_aggs == 0 && o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && ix->live_bits.p == nullptr && o.n_req == 0 &&
+    return !sorted && n_aggs == 0 && o.single_field >= 0 && !o.has_nonterm && !o.nonterm_scoring && (b->use_probe || ix->live_bits.p == nullptr) && o.n_req == 0 &&
            o.not_term_mask == 0 && o.msm <= 1 && !o.dense_driver;
   };
   // 0: probe kernel, simple; 1: probe kernel, generic (a posting list leads); 2: window/stream kernel (no list can lead)
@@ -1526,5 +1573,61 @@ int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const in
   NRT_CUDA_TRY(cudaMemcpy(scores, ds.p, n * 4, cudaMemcpyDeviceToHost));
   return NRTGPU_OK;
 }
+
+// ---- searcher over several leaf images of one shard (NRT: a new reader version adds images for the NEW leaves only)
+struct nrtgpu_searcher {
+  nrtgpu_ctx* ctx = nullptr;
+  std::vector<nrtgpu_index*> leaves;
+  std::mutex mu;
+  DevBuf<int32_t> records, merged;   // [n_leaves][words], [words]
+  std::vector<int32_t> host;
+};
+
+int nrtgpu_searcher_create(nrtgpu_ctx* ctx, nrtgpu_index* const* leaves, int32_t n_leaves, nrtgpu_searcher** out) {
+  if (!ctx || !leaves || n_leaves <= 0 || !out) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_searcher_create: bad argument");
+  std::unique_ptr<nrtgpu_searcher> s(new nrtgpu_searcher);
+  s->ctx = ctx;
+  for (int i = 0; i < n_leaves; ++i) {
+    if (!leaves[i] || leaves[i]->ctx != ctx) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_searcher_create: leaf of another context");
+    s->leaves.push_back(leaves[i]);
+  }
+  *out = s.release();
+  return NRTGPU_OK;
+}
+
+int nrtgpu_searcher_close(nrtgpu_searcher* s) { delete s; return NRTGPU_OK; }
+
+int nrtgpu_searcher_search_bool(nrtgpu_searcher* s, const nrtgpu_clause* clauses, int32_t n_clauses,
+                                const nrtgpu_query* queries, int32_t nq, int32_t top_k, int32_t total_hits_threshold,
+                                int32_t flags, const nrtgpu_search_limits* limits, void* stream, int32_t* out_docs,
+                                float* out_scores, int32_t* out_counts, int64_t* out_total_hits, uint8_t* out_relation) {
+  if (!s || !out_docs || !out_scores || !out_counts) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_searcher_search_bool: NULL argument");
+  if (nq <= 0 || top_k <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_searcher_search_bool: nq and top_k must be > 0");
+  NRT_CUDA_TRY(cudaSetDevice(s->ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> g(s->mu);
+  const int64_t words = nrtgpu_packed_words(nq, top_k);
+  const int n_leaves = (int)s->leaves.size();
+  int rc;
+  if ((rc = s->records.alloc((size_t)words * n_leaves)) || (rc = s->merged.alloc((size_t)words))) return rc;
+  for (int l = 0; l < n_leaves; ++l)   // every leaf runs the whole batch (LeafCollector per segment), results stay on the device
+    if ((rc = nrtgpu_search_bool_packed(s->leaves[(size_t)l], clauses, n_clauses, queries, nq, top_k, total_hits_threshold, flags, limits,
+                                        stream, s->records.p + (size_t)l * words))) return rc;
+  // TopDocs.merge over the leaves (LazyQueueTopScoreDocCollectorManager.java:137-144)
+  if ((rc = nrtgpu_merge_topk_packed(s->ctx, n_leaves, nq, top_k, s->records.p, s->merged.p, stream))) return rc;
+  s->host.resize((size_t)words);
+  NRT_CUDA_TRY(cudaMemcpyAsync(s->host.data(), s->merged.p, (size_t)words * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
+  const int64_t n = (int64_t)nq * top_k;
+  int64_t w = 2 * n + 2ll * nq; w = (w + 1) & ~1ll;
+  std::memcpy(out_docs, s->host.data(), (size_t)n * 4);
+  std::memcpy(out_scores, s->host.data() + n, (size_t)n * 4);
+  std::memcpy(out_counts, s->host.data() + 2 * n, (size_t)nq * 4);
+  if (out_relation) for (int q = 0; q < nq; ++q) out_relation[q] = (uint8_t)(s->host[(size_t)(2 * n + nq + q)] & 1);
+  if (out_total_hits) std::memcpy(out_total_hits, s->host.data() + w, (size_t)nq * 8);
+  return NRTGPU_OK;
+}
+
+#include "batcher.inc"
 
 }  // extern "C"

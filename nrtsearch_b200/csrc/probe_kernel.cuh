@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       if (kSimple) {
         ess = all & ~ne;
         int cnt_first = -1;
-        if (complete && ne) {   // the densest non-essential list with a plane contributes its posting count unread
+        if (complete && ne && !L.ix.live_bits) {   // the densest non-essential list with a plane contributes its posting count unread
           uint32_t best = 0;
           for (int s = 0; s < n_term; ++s)
             if (((ne >> s) & 1u) && sm.s_kind[s] == kPlane && sm.s_ib[s] - sm.s_ia[s] >= best) { best = sm.s_ib[s] - sm.s_ia[s]; cnt_first = s; }
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     const long long t_setup = L.stats ? clock64() : 0ll;
 
     const bool dense = !kSimple && sm.q.dense_driver != 0;
+    const uint32_t* live = L.ix.live_bits;
     const uint32_t sort_missing = (!kSimple && L.sort_kind == NRTGPU_SORT_COLUMN) ? *L.sort_missing_code : 0u;
     int g0 = g_lo;
     if (drv_mask == 0u && !dense) g0 = g_hi;   // nothing leads (every list non-essential): the slice cannot contribute
@@ -770,6 +771,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
               }
               uint64_t entry;
               if (kSimple) {
+                if (live && !((live[doc[j] >> 5] >> (doc[j] & 31)) & 1u)) continue;   // deleted docs are neither counted nor collected
                 if ((v & cntbefore) == 0u) ++my_hits;
                 if (!t_ess || (v & candbelow) != 0u) continue;   // counted only / emitted by a lower list
                 if (sm.ubt[__dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u)] < theta_s) continue;   // cannot reach the top-k

@@ -309,6 +309,18 @@ class GpuIndex:
         self.handle = h
         self.n_docs, self.doc_base = shard.n_docs, shard.doc_base
 
+    def set_live_docs(self, live_docs: Optional[np.ndarray]):
+        """Deletes of a new reader version (LeafReader.getLiveDocs): refreshed in place, no image rebuild."""
+        lv = None if live_docs is None else np.ascontiguousarray(live_docs, np.uint8)
+        check(self._lib.nrtgpu_index_set_live_docs(self.handle, None if lv is None else lv.ctypes.data))
+
+    def update_stats(self, term_df: Optional[np.ndarray], field_doc_count: Sequence[int], field_sum_ttf: Sequence[int]):
+        """Index-wide BM25 statistics changed (a leaf was added elsewhere in the shard): idf inputs, length caches, impacts."""
+        df = None if term_df is None else np.ascontiguousarray(term_df, np.int64)
+        dc = np.ascontiguousarray(field_doc_count, np.int64)
+        tt = np.ascontiguousarray(field_sum_ttf, np.int64)
+        check(self._lib.nrtgpu_index_update_stats(self.handle, None if df is None else df.ctypes.data, dc.ctypes.data, tt.ctypes.data))
+
     @property
     def device_bytes(self) -> int:
         return int(self._lib.nrtgpu_index_device_bytes(self.handle))
@@ -522,6 +534,69 @@ class GpuIndexSearcher:
                                           None if b is None else b.ctypes.data, None if f is None else f.ctypes.data,
                                           C.c_void_p(stream), docs.ctypes.data, scores.ctypes.data, counts.ctypes.data))
         return docs, scores, counts
+
+
+class GpuLeafSearcher:
+    """IndexSearcher over the leaf images of one reader version (nrtgpu_searcher_*): every leaf runs the batch, pages are
+    merged on the device (TopDocs.merge). A new NRT reader version = the old leaves' images + images of the new leaves."""
+
+    def __init__(self, ctx: GpuContext, leaves: Sequence[GpuIndex]):
+        self._lib = _native.gpu_lib()
+        arr = (C.c_void_p * len(leaves))(*[l.handle for l in leaves])
+        h = C.c_void_p()
+        check(self._lib.nrtgpu_searcher_create(ctx.handle, arr, len(leaves), C.byref(h)))
+        self.handle, self.leaves = h, list(leaves)
+
+    def search_batch(self, queries: Sequence[object], collector: RelevanceCollector, stream: int = 0) -> BatchResult:
+        carr, ncl, qarr, nq = compile_queries(queries)
+        k = collector.num_hits_to_collect
+        out = BatchResult(np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32), np.zeros(nq, np.int64),
+                          np.zeros(nq, np.uint8))
+        lim = collector.limits()
+        check(self._lib.nrtgpu_searcher_search_bool(self.handle, carr, ncl, qarr, nq, k, collector.total_hits_threshold, 0,
+                                                    None if lim is None else C.byref(lim), C.c_void_p(stream), out.docs.ctypes.data,
+                                                    out.scores.ctypes.data, out.counts.ctypes.data, out.total_hits.ctypes.data,
+                                                    out.relation.ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            self._lib.nrtgpu_searcher_close(self.handle)
+            self.handle = None
+
+
+class GpuBatcher:
+    """Request micro-batcher (nrtgpu_batcher_*): SearchHandler threads submit ONE query each and block; a native worker
+    thread turns the waiting requests into batched nrtgpu_search_bool calls. The Java adaptor's counterpart is
+    jni/java/.../GpuIndexSearcher.java (GpuBatcher.forIndex)."""
+
+    def __init__(self, index: GpuIndex, max_batch: int = 256, max_wait_us: int = 200):
+        self._lib = _native.gpu_lib()
+        h = C.c_void_p()
+        check(self._lib.nrtgpu_batcher_create(index.handle, max_batch, max_wait_us, C.byref(h)))
+        self.handle = h
+
+    def submit(self, query, collector: RelevanceCollector):
+        """Blocking: returns (TopDocs, Diagnostics) of the one query."""
+        carr, ncl, qarr, _ = compile_queries([query])
+        k = collector.num_hits_to_collect
+        docs, scores = np.zeros(k, np.int32), np.zeros(k, np.float32)
+        cnt, tot, rel = C.c_int32(), C.c_int64(), C.c_uint8()
+        diag = _native.Diagnostics()
+        check(self._lib.nrtgpu_batcher_submit(self.handle, carr, ncl, qarr[0].min_should_match, k, collector.total_hits_threshold,
+                                              docs.ctypes.data, scores.ctypes.data, C.byref(cnt), C.byref(tot), C.byref(rel), C.byref(diag)))
+        n = cnt.value
+        return TopDocs(TotalHits(tot.value, Relation(rel.value)), [ScoreDoc(int(d), float(s)) for d, s in zip(docs[:n], scores[:n])]), diag
+
+    def stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(self._lib.nrtgpu_batcher_stats(self.handle, C.byref(a), C.byref(b)))
+        return {"batches": a.value, "requests": b.value}
+
+    def close(self):
+        if self.handle:
+            self._lib.nrtgpu_batcher_close(self.handle)
+            self.handle = None
 
 
 def blend_rrf(ctx: GpuContext, docs: np.ndarray, counts: np.ndarray, boosts: Sequence[float], rank_constant: int,

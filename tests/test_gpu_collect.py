@@ -104,3 +104,39 @@ def test_query_rescorer_second_pass_and_fetch(setup):
     vals, has = s.fetch_columns([1, 2, 0], flat)
     assert np.array_equal(vals[0], sh.columns[1][flat]) and np.array_equal(vals[2], sh.columns[0][flat]) and has[0].all()
     assert np.array_equal(has[1], sh.column_has[2][flat]) and np.array_equal(vals[1][has[1] != 0], sh.columns[2][flat][has[1] != 0])
+
+
+def test_micro_batcher_matches_direct_search(setup):
+    """96 handler threads submit one query each (the reference's one-query-per-RPC API); the native batcher groups them.
+    Every caller gets exactly what a direct search returns, bad requests fail alone, and requests really share batches."""
+    import threading
+    from nrtsearch_b200 import NrtGpuError
+    from nrtsearch_b200.search import GpuBatcher
+    sh, qs, gix, _ = setup
+    direct = GpuIndexSearcher(gix).search_batch(qs, RelevanceCollector(15, INT_MAX))
+    b = GpuBatcher(gix, max_batch=64, max_wait_us=20_000)
+    results, errors = {}, {}
+
+    def worker(i):
+        try:
+            if i % 17 == 5:
+                results[i] = b.submit(TermQuery(10**8), RelevanceCollector(15, INT_MAX))   # out-of-range term: must fail alone
+            else:
+                results[i] = b.submit(qs[i % len(qs)], RelevanceCollector(15, INT_MAX))
+        except NrtGpuError as e:
+            errors[i] = e
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(96)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    st = b.stats()
+    b.close()
+    bad = {i for i in range(96) if i % 17 == 5}
+    assert set(errors) == bad and all("term id out of range" in str(e) for e in errors.values())
+    for i in set(range(96)) - bad:
+        td, diag = results[i]
+        q = i % len(qs)
+        n = direct.counts[q]
+        assert [sd.doc for sd in td.score_docs] == direct.docs[q, :n].tolist()
+        assert np.array_equal(np.array([sd.score for sd in td.score_docs], np.float32).view(np.uint32), direct.scores[q, :n].view(np.uint32))
+        assert td.total_hits.value == direct.total_hits[q] and diag.batch_size >= 1 and diag.search_ms > 0
+    assert st["requests"] >= 96 - len(bad) and st["batches"] < st["requests"], st   # requests shared batches
