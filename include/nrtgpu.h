@@ -62,6 +62,7 @@ enum { NRTGPU_SHOULD = 0, NRTGPU_MUST = 1, NRTGPU_FILTER = 2, NRTGPU_MUST_NOT = 
 enum { NRTGPU_TERM = 0, NRTGPU_RANGE_I64 = 1, NRTGPU_MATCH_ALL = 2 };
 /* VectorSimilarityFunction (reference VectorFieldDef.java:77-88) */
 enum { NRTGPU_SIM_L2 = 0, NRTGPU_SIM_DOT = 1, NRTGPU_SIM_COSINE = 2, NRTGPU_SIM_MIP = 3 };
+enum { NRTGPU_VEC_FLOAT32 = 0, NRTGPU_VEC_INT8 = 1 };
 
 /* Host-side description of one shard, i.e. what the adaptor reads out of the LeafReaders
  * (terms()/postings()/getNormValues()/getNumericDocValues()/getFloatVectorValues()). Term ids are the
@@ -89,8 +90,11 @@ typedef struct {
   int32_t vec_dims;                 /* 0 = none */
   int32_t vec_similarity;
   int32_t vec_count;                /* number of vectors (ord -> doc via vec_docs, NULL = identity) */
-  const float* vectors;             /* [vec_count * vec_dims] */
+  const float* vectors;             /* [vec_count * vec_dims] float32, or int8 when vec_element_type == NRTGPU_VEC_INT8 */
   const int32_t* vec_docs;
+  int32_t vec_element_type;         /* NRTGPU_VEC_FLOAT32 (FloatVectorFieldDef) or NRTGPU_VEC_INT8 (ByteVectorFieldDef: scores by
+                                       VectorFieldDef.java:870-881, i.e. DOT_PRODUCT = 0.5 + dot / (dims * 2^15); queries are passed
+                                       as floats holding the byte values) */
 } nrtgpu_shard_desc;
 
 int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* desc, nrtgpu_index** out);
@@ -319,6 +323,14 @@ int nrtgpu_blend_rrf(nrtgpu_ctx* ctx, int32_t n_retrievers, int32_t nq, int32_t 
                      const int32_t* docs, const int32_t* counts, const float* boosts,
                      int32_t rank_constant, int32_t top_out, int32_t* out_docs, float* out_scores,
                      int32_t* out_counts, int32_t* out_total);
+
+/* Score-order blend (WeightedScoreOrderBlenderOperation.java:50-73 with WeightedScoreDoc.java:57-77): every hit contributes
+ * score * boost of its retriever; a doc found by several retrievers combines them, in retriever declaration order and in
+ * float, by MAX (default), SUM or AVG (running average). scores [R][nq][top_in]; other arguments as nrtgpu_blend_rrf. */
+enum { NRTGPU_BLEND_MAX = 1, NRTGPU_BLEND_SUM = 2, NRTGPU_BLEND_AVG = 3 };
+int nrtgpu_blend_scores(nrtgpu_ctx* ctx, int32_t score_mode, int32_t n_retrievers, int32_t nq, int32_t top_in,
+                        const int32_t* docs, const float* scores, const int32_t* counts, const float* boosts,
+                        int32_t top_out, int32_t* out_docs, float* out_scores, int32_t* out_counts, int32_t* out_total);
 
 /* QueryRescore.combine + re-sort for nq hit lists (HOST buffers, in place): [nq][n_hits]. */
 int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const int32_t* counts,

@@ -18,6 +18,9 @@ struct RrfLaunch {
   const int32_t* docs;    // [R][nq][top_in]
   const int32_t* counts;  // [R][nq]
   const float* boosts;    // [R]
+  const float* scores;    // [R][nq][top_in] retriever scores (score-order blending) or NULL
+  int32_t mode;           // 0: weighted RRF; 1 / 2 / 3: WeightedScoreDoc.ScoreMode MAX / SUM / AVG of score * boost
+                          // (reference .../blender/score/WeightedScoreDoc.java:57-77, float ops in retriever order)
   int32_t R, nq, top_in, rank_constant, top_out;
   int32_t* out_docs; float* out_scores; int32_t* out_counts; int32_t* out_total;
 };
@@ -51,11 +54,21 @@ __global__ void __launch_bounds__(kHybThreads) rrf_blend_kernel(RrfLaunch P) {
       const uint32_t d = (uint32_t)(k >> 32);
       const bool head = (i == 0) || ((uint32_t)((~keys[i - 1]) >> 32) != d);
       if (head) {
-        float s = __fdiv_rn(P.boosts[(k >> 16) & 0xffff], (float)(P.rank_constant + (int)(k & 0xffff) + 1));
+        auto contrib = [&](uint64_t kk) {
+          const int r = (int)((kk >> 16) & 0xffff), rank0 = (int)(kk & 0xffff);
+          if (P.mode == 0) return __fdiv_rn(P.boosts[r], (float)(P.rank_constant + rank0 + 1));
+          return __fmul_rn(P.scores[((size_t)r * P.nq + q) * P.top_in + rank0], P.boosts[r]);
+        };
+        float s = contrib(k);
+        int have = 1;
         for (int j = i + 1; j < n; ++j) {
           const uint64_t kj = ~keys[j];
           if ((uint32_t)(kj >> 32) != d) break;
-          s = __fadd_rn(s, __fdiv_rn(P.boosts[(kj >> 16) & 0xffff], (float)(P.rank_constant + (int)(kj & 0xffff) + 1)));
+          const float w = contrib(kj);
+          if (P.mode == 0 || P.mode == 2) s = __fadd_rn(s, w);
+          else if (P.mode == 1) s = fmaxf(s, w);
+          else s = __fdiv_rn(__fadd_rn(__fmul_rn(s, (float)have), w), (float)(have + 1));
+          ++have;
         }
         out = make_key(s, (int32_t)d);
         atomicAdd(&n_heads, 1);

@@ -185,11 +185,29 @@ struct KnnRescoreLaunch {
   int32_t* unsafe; float eps_rel; float dmax;
 };
 
+// VectorSimilarityFunction.compare -> score, float vectors (VectorFieldDef.java:664-673) and byte vectors (:870-881: the same
+// except DOT_PRODUCT = 0.5 + dot / (dims * 2^15)); sim carries kKnnByteFlag for byte vectors
+constexpr int kKnnByteFlag = 0x100;
+__device__ __forceinline__ float knn_map_score(int sim, int dims, double dot, double na, double nb, double d2) {
+  const int base = sim & 0xff;
+  float s;
+  if (base == NRTGPU_SIM_L2) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, (float)d2));
+  else if (base == NRTGPU_SIM_DOT) {
+    if (sim & kKnnByteFlag) s = __fadd_rn(0.5f, __fdiv_rn((float)dot, (float)(dims * (1 << 15))));
+    else { s = __fdiv_rn(__fadd_rn(1.0f, (float)dot), 2.0f); s = s > 0.f ? s : 0.f; }
+  } else if (base == NRTGPU_SIM_COSINE) { const float cs = (float)(dot / sqrt(na * nb)); s = __fdiv_rn(__fadd_rn(1.0f, cs), 2.0f); s = s > 0.f ? s : 0.f; }
+  else { const float t = (float)dot; s = t < 0.f ? __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(-1.0f, t))) : __fadd_rn(t, 1.0f); }
+  return s;
+}
+
 // largest final score a vector whose APPROXIMATE score is <= th can have (monotone score mapping applied to th + error bound)
-__device__ __forceinline__ float knn_score_upper_bound(int sim, double th, double qn, double dmax, double eps_rel, float boost) {
+__device__ __forceinline__ float knn_score_upper_bound(int sim_flags, int dims, double th, double qn, double dmax, double eps_rel, float boost) {
   const double slack = 1.0 + 1e-3;   // rsqrt / float norm / accumulation rounding on top of the operand rounding
+  const int sim = sim_flags & 0xff;
   double s;
-  if (sim == NRTGPU_SIM_COSINE) {            // approx = dot / |d|  (|q| cos)
+  if (sim == NRTGPU_SIM_DOT && (sim_flags & kKnnByteFlag)) {
+    s = 0.5 + (th + eps_rel * slack * qn * dmax) / ((double)dims * 32768.0);
+  } else if (sim == NRTGPU_SIM_COSINE) {            // approx = dot / |d|  (|q| cos)
     const double c = (th + eps_rel * slack * qn) / fmax(qn, 1e-300);
     s = (1.0 + fmin(c, 1.0)) / 2.0;
   } else if (sim == NRTGPU_SIM_L2) {         // approx = 2 dot - |d|^2 = |q|^2 - dist^2
@@ -233,11 +251,7 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
     }
     if (lane == 0) {
       // VectorSimilarityFunction.compare (reference VectorFieldDef.java:664-673 restates the mapping)
-      float s;
-      if (L.sim == NRTGPU_SIM_L2) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, (float)d2));
-      else if (L.sim == NRTGPU_SIM_DOT) { s = __fdiv_rn(__fadd_rn(1.0f, (float)dot), 2.0f); s = s > 0.f ? s : 0.f; }
-      else if (L.sim == NRTGPU_SIM_COSINE) { float cs = (float)(dot / sqrt(na * nb)); s = __fdiv_rn(__fadd_rn(1.0f, cs), 2.0f); s = s > 0.f ? s : 0.f; }
-      else { float t = (float)dot; s = t < 0.f ? __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(-1.0f, t))) : __fadd_rn(t, 1.0f); }
+      float s = knn_map_score(L.sim, L.dims, dot, na, nb, d2);
       s = __fmul_rn(s, boost);
       int doc = L.vec_docs ? L.vec_docs[ord] : ord;
       keys[c] = make_key(s, doc);
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(KnnRescoreLaunch L) {
       int bad = 0;
       if (n == L.kprime) {   // the list is full: vectors outside it exist, all with approximate scores <= the weakest candidate's
         const double th = (double)key_score(L.cand[(size_t)q * L.kprime + n - 1]);
-        const float ub = knn_score_upper_bound(L.sim, th, sqrt(q_norm2), (double)L.dmax, (double)L.eps_rel, boost);
+        const float ub = knn_score_upper_bound(L.sim, L.dims, th, sqrt(q_norm2), (double)L.dmax, (double)L.eps_rel, boost);
         bad = !(n >= L.k && ub < key_score(keys[L.k - 1]));
       }
       L.unsafe[q] = bad;
@@ -307,11 +321,7 @@ __global__ void __launch_bounds__(256) knn_exact_chunk_kernel(KnnExactLaunch L) 
           dot += __shfl_xor_sync(0xffffffffu, dot, o); na += __shfl_xor_sync(0xffffffffu, na, o);
           nb += __shfl_xor_sync(0xffffffffu, nb, o);  d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         }
-        float s;
-        if (L.sim == NRTGPU_SIM_L2) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, (float)d2));
-        else if (L.sim == NRTGPU_SIM_DOT) { s = __fdiv_rn(__fadd_rn(1.0f, (float)dot), 2.0f); s = s > 0.f ? s : 0.f; }
-        else if (L.sim == NRTGPU_SIM_COSINE) { const float cs = (float)(dot / sqrt(na * nb)); s = __fdiv_rn(__fadd_rn(1.0f, cs), 2.0f); s = s > 0.f ? s : 0.f; }
-        else { const float t = (float)dot; s = t < 0.f ? __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(-1.0f, t))) : __fadd_rn(t, 1.0f); }
+        const float s = knn_map_score(L.sim, L.dims, dot, na, nb, d2);
         key = make_key(__fmul_rn(s, boost), doc);
       }
     }
@@ -448,7 +458,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     int nc = n - base < cur ? n - base : cur;
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
     if (use_tc) {
-      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim;
+      tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim & 0xff;
       G.S = fused ? nullptr : dS; G.ldS = chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs; G.live_bits = d_live_bits;
       // default: one tile per CTA, 2 CTAs/SM (measured 4.9 ms at C4); the persistent double-buffered variant measured
@@ -465,7 +475,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       }
     } else {
       dim3 grid((nc + kKnnTile - 1) / kKnnTile, (nq + kKnnTile - 1) / kKnnTile);
-      knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim, dS, chunk);
+      knn_dot_tile_kernel<<<grid, 256, 0, st>>>(dQ, d_vec + (size_t)base * dims, d_norm2 + base, nq, nc, dims, sim & 0xff, dS, chunk);
     }
     NRT_CUDA_TRY(cudaGetLastError());
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -503,7 +513,8 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   int32_t* dUnsafe = nullptr;
   NRT_KNN_GET(14, dUnsafe, (size_t)nq * sizeof(int32_t));
   R.unsafe = dUnsafe; R.dmax = dmax;
-  R.eps_rel = use_tc ? 0.0078125f /* bf16 operands: 2^-7 |q||d| */ : (float)dims * 1.1920929e-7f /* fp32 FMA chain: dims * 2^-23 */;
+  // bf16 operands: 2^-7 |q||d|; fp32 FMA chain (and byte vectors, whose elements and products are exact in bf16 / fp32): dims * 2^-23
+  R.eps_rel = (use_tc && !(sim & kKnnByteFlag)) ? 0.0078125f : (float)dims * 1.1920929e-7f;
   knn_rescore_kernel<<<nq, 256, 0, st>>>(R);
   NRT_CUDA_TRY(cudaGetLastError());
   if (stage_ms) {

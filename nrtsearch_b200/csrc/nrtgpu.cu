@@ -30,13 +30,6 @@ using namespace nrtgpu;
 
 #define NRT_FAIL(code, msg) do { set_error(msg); return (code); } while (0)
 
-struct nrtgpu_ctx {
-  int device = 0;
-  int sm_count = 0;
-  bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
-  bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
-  bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
-};
 
 // index-time impacts: max over a term's postings of x = tf * cache[norm] (what Lucene keeps as competitive (freq, norm)
 // pairs in its skip data); the BM25 score is monotone in x, so score(weight, max x) bounds the whole list.
@@ -138,6 +131,16 @@ struct DevBuf {
 
 }  // namespace
 
+struct nrtgpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
+  std::mutex hyb_mu;             // O(k) hybrid stages share one pooled device scratch (no cudaMalloc per call)
+  DevBuf<int32_t> hyb_scratch;
+  bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
+  bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
+};
+
 struct nrtgpu_index {
   nrtgpu_ctx* ctx = nullptr;
   int32_t n_docs = 0, doc_base = 0, n_terms = 0, n_fields = 0, n_columns = 0;
@@ -178,6 +181,7 @@ struct nrtgpu_index {
   DevBuf<uint32_t> live_bits;
   // vectors
   int32_t vec_dims = 0, vec_sim = 0, vec_count = 0;
+  bool vec_is_byte = false;   // byte vector field (ByteVectorFieldDef): same image, byte score mapping
   DevBuf<float> vectors;
   DevBuf<__nv_bfloat16> vec_bf16;   // bf16 copy of the corpus for the tensor-core candidate stage (dims % 8 == 0)
   CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16
@@ -539,9 +543,16 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
   // vectors
   if (d->vec_dims > 0 && d->vec_count > 0) {
     if (!d->vectors) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL vectors");
+    if (d->vec_element_type != NRTGPU_VEC_FLOAT32 && d->vec_element_type != NRTGPU_VEC_INT8) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: bad vec_element_type");
     if (d->vec_dims > 4096) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: vector dims > 4096 (VectorFieldDef.java:96)");
     ix->vec_dims = d->vec_dims; ix->vec_sim = d->vec_similarity; ix->vec_count = d->vec_count;
-    if ((rc = ix->vectors.upload(d->vectors, (size_t)d->vec_count * d->vec_dims))) return rc;
+    ix->vec_is_byte = d->vec_element_type == NRTGPU_VEC_INT8;
+    if (ix->vec_is_byte) {   // bytes are held as exact floats (every int8 is exact in fp32 and in bf16)
+      const int8_t* src = reinterpret_cast<const int8_t*>(d->vectors);
+      std::vector<float> tmp((size_t)d->vec_count * d->vec_dims);
+      for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (float)src[i];
+      if ((rc = ix->vectors.upload(tmp.data(), tmp.size()))) return rc;
+    } else if ((rc = ix->vectors.upload(d->vectors, (size_t)d->vec_count * d->vec_dims))) return rc;
     if (d->vec_docs) { if ((rc = ix->vec_docs.upload(d->vec_docs, (size_t)d->vec_count))) return rc; }
     if ((rc = ix->vec_norm2.alloc((size_t)d->vec_count))) return rc;
     if ((rc = knn_prepare_norms(ix->vectors.p, ix->vec_count, ix->vec_dims, ix->vec_norm2.p))) return rc;
@@ -1486,7 +1497,7 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
   const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
   std::lock_guard<std::mutex> g(ix->knn_mu);
-  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
+  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim | (ix->vec_is_byte ? kKnnByteFlag : 0),
                          ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr, ix->vec_ab.p,
                          &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
@@ -1500,7 +1511,7 @@ int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, 
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
   const bool tcp = ix->vec_tc && !(getenv("NRTGPU_KNN_SIMT") != nullptr);
   std::lock_guard<std::mutex> g(ix->knn_mu);
-  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim,
+  return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim | (ix->vec_is_byte ? kKnnByteFlag : 0),
                          ix->doc_base, ix->n_docs, queries, nq, k, nullptr, nullptr, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms, ix->vec_ab.p,
                          &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
@@ -1508,43 +1519,64 @@ int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, 
 
 int32_t nrtgpu_knn_last_uncertified(const nrtgpu_index* ix) { return ix ? ix->knn_last_uncertified : 0; }
 
-namespace {
-struct DevTmp {   // scoped device scratch for the O(k) hybrid stages
-  void* p = nullptr;
-  ~DevTmp() { if (p) cudaFree(p); }
-  int get(size_t bytes) { NRT_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 1)); return NRTGPU_OK; }
-};
-}  // namespace
-
-int nrtgpu_blend_rrf(nrtgpu_ctx* ctx, int32_t R, int32_t nq, int32_t top_in, const int32_t* docs, const int32_t* counts,
-                     const float* boosts, int32_t rank_constant, int32_t top_out, int32_t* out_docs, float* out_scores,
-                     int32_t* out_counts, int32_t* out_total) {
-  if (!ctx || !docs || !counts || !boosts || !out_docs || !out_scores || !out_counts || !out_total)
-    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend_rrf: NULL argument");
-  if (R <= 0 || nq <= 0 || top_in <= 0 || top_out <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend_rrf: sizes must be > 0");
-  if ((int64_t)R * top_in > kHybCap || top_in > 65535 || R > 65535) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_blend_rrf: more than 4096 hits per query");
+// weighted RRF (mode 0) or score-order (MAX / SUM / AVG) blend of R retrievers' lists; HOST buffers, pooled device scratch
+static int blend_impl(nrtgpu_ctx* ctx, int32_t mode, int32_t R, int32_t nq, int32_t top_in, const int32_t* docs, const float* scores,
+                      const int32_t* counts, const float* boosts, int32_t rank_constant, int32_t top_out, int32_t* out_docs,
+                      float* out_scores, int32_t* out_counts, int32_t* out_total) {
+  if (!ctx || !docs || !counts || !boosts || !out_docs || !out_scores || !out_counts || !out_total || (mode != 0 && !scores))
+    NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend: NULL argument");
+  if (R <= 0 || nq <= 0 || top_in <= 0 || top_out <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend: sizes must be > 0");
+  if ((int64_t)R * top_in > kHybCap || top_in > 65535 || R > 65535) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_blend: more than 4096 hits per query");
+  for (int64_t i = 0; i < (int64_t)R * nq; ++i)
+    if (counts[i] < 0 || counts[i] > top_in) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend: counts[] outside [0, top_in]");
   // WeightedRrfBlenderOperation.java:47-49: rankConstant <= 0 selects DEFAULT_K = 60
   const int k = rank_constant > 0 ? rank_constant : 60;
   NRT_CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t nd = (size_t)R * nq * top_in, nc = (size_t)R * nq, no = (size_t)nq * top_out;
-  DevTmp dd, dc, db, od, os, oc, ot;
+  std::lock_guard<std::mutex> g(ctx->hyb_mu);
   int rc;
-  if ((rc = dd.get(nd * 4)) || (rc = dc.get(nc * 4)) || (rc = db.get((size_t)R * 4)) || (rc = od.get(no * 4)) ||
-      (rc = os.get(no * 4)) || (rc = oc.get((size_t)nq * 4)) || (rc = ot.get((size_t)nq * 4))) return rc;
-  NRT_CUDA_TRY(cudaMemcpy(dd.p, docs, nd * 4, cudaMemcpyHostToDevice));
-  NRT_CUDA_TRY(cudaMemcpy(dc.p, counts, nc * 4, cudaMemcpyHostToDevice));
-  NRT_CUDA_TRY(cudaMemcpy(db.p, boosts, (size_t)R * 4, cudaMemcpyHostToDevice));
+  // one pooled allocation, carved up (all parts 4-byte types)
+  const size_t words = nd * 2 + nc + (size_t)R + no * 2 + (size_t)nq * 2;
+  if ((rc = ctx->hyb_scratch.alloc(words))) return rc;
+  int32_t* p = ctx->hyb_scratch.p;
+  int32_t* d_docs = p; p += nd;
+  float* d_scores = (float*)p; p += nd;
+  int32_t* d_counts = p; p += nc;
+  float* d_boosts = (float*)p; p += R;
+  int32_t* d_od = p; p += no;
+  float* d_os = (float*)p; p += no;
+  int32_t* d_oc = p; p += nq;
+  int32_t* d_ot = p;
+  cudaStream_t st = 0;
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_docs, docs, nd * 4, cudaMemcpyHostToDevice, st));
+  if (mode != 0) NRT_CUDA_TRY(cudaMemcpyAsync(d_scores, scores, nd * 4, cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_counts, counts, nc * 4, cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_boosts, boosts, (size_t)R * 4, cudaMemcpyHostToDevice, st));
   RrfLaunch P;
-  P.docs = (const int32_t*)dd.p; P.counts = (const int32_t*)dc.p; P.boosts = (const float*)db.p;
+  P.docs = d_docs; P.counts = d_counts; P.boosts = d_boosts; P.scores = mode != 0 ? d_scores : nullptr; P.mode = mode;
   P.R = R; P.nq = nq; P.top_in = top_in; P.rank_constant = k; P.top_out = top_out;
-  P.out_docs = (int32_t*)od.p; P.out_scores = (float*)os.p; P.out_counts = (int32_t*)oc.p; P.out_total = (int32_t*)ot.p;
-  rrf_blend_kernel<<<nq, kHybThreads>>>(P);
+  P.out_docs = d_od; P.out_scores = d_os; P.out_counts = d_oc; P.out_total = d_ot;
+  rrf_blend_kernel<<<nq, kHybThreads, 0, st>>>(P);
   NRT_CUDA_TRY(cudaGetLastError());
-  NRT_CUDA_TRY(cudaMemcpy(out_docs, od.p, no * 4, cudaMemcpyDeviceToHost));
-  NRT_CUDA_TRY(cudaMemcpy(out_scores, os.p, no * 4, cudaMemcpyDeviceToHost));
-  NRT_CUDA_TRY(cudaMemcpy(out_counts, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-  NRT_CUDA_TRY(cudaMemcpy(out_total, ot.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_docs, d_od, no * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_scores, d_os, no * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_counts, d_oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(out_total, d_ot, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
   return NRTGPU_OK;
+}
+
+int nrtgpu_blend_rrf(nrtgpu_ctx* ctx, int32_t R, int32_t nq, int32_t top_in, const int32_t* docs, const int32_t* counts,
+                     const float* boosts, int32_t rank_constant, int32_t top_out, int32_t* out_docs, float* out_scores,
+                     int32_t* out_counts, int32_t* out_total) {
+  return blend_impl(ctx, 0, R, nq, top_in, docs, nullptr, counts, boosts, rank_constant, top_out, out_docs, out_scores, out_counts, out_total);
+}
+
+int nrtgpu_blend_scores(nrtgpu_ctx* ctx, int32_t score_mode, int32_t R, int32_t nq, int32_t top_in, const int32_t* docs,
+                        const float* scores, const int32_t* counts, const float* boosts, int32_t top_out, int32_t* out_docs,
+                        float* out_scores, int32_t* out_counts, int32_t* out_total) {
+  if (score_mode < NRTGPU_BLEND_MAX || score_mode > NRTGPU_BLEND_AVG) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_blend_scores: bad score mode");
+  return blend_impl(ctx, score_mode, R, nq, top_in, docs, scores, counts, boosts, 0, top_out, out_docs, out_scores, out_counts, out_total);
 }
 
 int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const int32_t* counts, int32_t* docs, float* scores,
@@ -1553,24 +1585,33 @@ int nrtgpu_rescore_combine(nrtgpu_ctx* ctx, int32_t nq, int32_t n_hits, const in
   if (!ctx || !docs || !scores || !second_matches || !second_scores) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_combine: NULL argument");
   if (nq <= 0 || n_hits <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_combine: sizes must be > 0");
   if (n_hits > kHybCap) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_rescore_combine: more than 4096 hits per query");
+  if (counts) for (int q = 0; q < nq; ++q) if (counts[q] < 0 || counts[q] > n_hits) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_rescore_combine: counts[] outside [0, n_hits]");
   NRT_CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t n = (size_t)nq * n_hits;
-  DevTmp dd, ds, dm, d2, dc;
+  std::lock_guard<std::mutex> g(ctx->hyb_mu);
   int rc;
-  if ((rc = dd.get(n * 4)) || (rc = ds.get(n * 4)) || (rc = dm.get(n)) || (rc = d2.get(n * 4)) || (rc = dc.get((size_t)nq * 4))) return rc;
-  NRT_CUDA_TRY(cudaMemcpy(dd.p, docs, n * 4, cudaMemcpyHostToDevice));
-  NRT_CUDA_TRY(cudaMemcpy(ds.p, scores, n * 4, cudaMemcpyHostToDevice));
-  NRT_CUDA_TRY(cudaMemcpy(dm.p, second_matches, n, cudaMemcpyHostToDevice));
-  NRT_CUDA_TRY(cudaMemcpy(d2.p, second_scores, n * 4, cudaMemcpyHostToDevice));
-  if (counts) NRT_CUDA_TRY(cudaMemcpy(dc.p, counts, (size_t)nq * 4, cudaMemcpyHostToDevice));
+  if ((rc = ctx->hyb_scratch.alloc(n * 3 + (n + 3) / 4 + (size_t)nq))) return rc;
+  int32_t* p = ctx->hyb_scratch.p;
+  int32_t* d_docs = p; p += n;
+  float* d_scores = (float*)p; p += n;
+  float* d_second = (float*)p; p += n;
+  int32_t* d_counts = p; p += nq;
+  uint8_t* d_match = (uint8_t*)p;
+  cudaStream_t st = 0;
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_docs, docs, n * 4, cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_scores, scores, n * 4, cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_match, second_matches, n, cudaMemcpyHostToDevice, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(d_second, second_scores, n * 4, cudaMemcpyHostToDevice, st));
+  if (counts) NRT_CUDA_TRY(cudaMemcpyAsync(d_counts, counts, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
   RescoreLaunch P;
-  P.nq = nq; P.n_hits = n_hits; P.counts = counts ? (const int32_t*)dc.p : nullptr;
-  P.docs = (int32_t*)dd.p; P.scores = (float*)ds.p; P.second_matches = (const uint8_t*)dm.p; P.second_scores = (const float*)d2.p;
+  P.nq = nq; P.n_hits = n_hits; P.counts = counts ? d_counts : nullptr;
+  P.docs = d_docs; P.scores = d_scores; P.second_matches = d_match; P.second_scores = d_second;
   P.query_weight = query_weight; P.rescore_weight = rescore_weight;
-  rescore_combine_kernel<<<nq, kHybThreads>>>(P);
+  rescore_combine_kernel<<<nq, kHybThreads, 0, st>>>(P);
   NRT_CUDA_TRY(cudaGetLastError());
-  NRT_CUDA_TRY(cudaMemcpy(docs, dd.p, n * 4, cudaMemcpyDeviceToHost));
-  NRT_CUDA_TRY(cudaMemcpy(scores, ds.p, n * 4, cudaMemcpyDeviceToHost));
+  NRT_CUDA_TRY(cudaMemcpyAsync(docs, d_docs, n * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaMemcpyAsync(scores, d_scores, n * 4, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA_TRY(cudaStreamSynchronize(st));
   return NRTGPU_OK;
 }
 

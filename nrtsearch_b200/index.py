@@ -140,9 +140,11 @@ class PinnedDesc:
         d.column_has = C.cast(has, C.POINTER(N.u8p))
         d.live_docs = _ptr(arr(sh.live_docs, np.uint8), N.u8p)
         if sh.vectors is not None and len(sh.vectors):
-            v = arr(sh.vectors, np.float32)
+            byte_field = np.asarray(sh.vectors).dtype == np.int8   # ByteVectorFieldDef
+            v = arr(sh.vectors, np.int8 if byte_field else np.float32)
             d.vec_dims, d.vec_similarity, d.vec_count = v.shape[1], sh.vec_similarity, v.shape[0]
-            d.vectors = _ptr(v, N.f32p)
+            d.vectors = v.ctypes.data
+            d.vec_element_type = 1 if byte_field else 0
             d.vec_docs = _ptr(arr(sh.vec_docs, np.int32), N.i32p)
         self.desc = d
 

@@ -433,6 +433,21 @@ class GpuIndexSearcher:
                                               out.terminated_early.ctypes.data))
         return out
 
+    def knn_query(self, queries: np.ndarray, knn: KnnQuery, sim: int, boosts: Optional[np.ndarray] = None,
+                  filter_docs: Optional[np.ndarray] = None, stream: int = 0):
+        """KnnUtils.resolveKnnQueryAndBoost (:47-66) for a batch of query vectors under one KnnQuery configuration."""
+        knn.validate()
+        docs, scores, counts = self.knn(queries, knn.k, boosts, filter_docs, stream)
+        if knn.similarity_threshold is not None:   # MinThresholdQuery: drop hits scoring below the threshold's score
+            th = similarity_to_score(knn.similarity_threshold, sim, queries.shape[1])
+            for q in range(len(counts)):
+                b = np.float32(1.0) if boosts is None else np.float32(boosts[q])
+                keep = scores[q, :counts[q]] >= th * b
+                n = int(keep.sum())
+                docs[q, :n] = docs[q, :counts[q]][keep]; scores[q, :n] = scores[q, :counts[q]][keep]
+                docs[q, n:] = 0; scores[q, n:] = 0; counts[q] = n
+        return docs, scores, counts
+
     def search_sorted(self, queries: Sequence[object], collector: SortFieldCollector,
                       search_after: Optional[Sequence[Optional[FieldDoc]]] = None, stream: int = 0) -> SortedResult:
         """IndexSearcher.search(query, TopFieldCollectorManager(sort, numHits, after, threshold)) for a batch."""
@@ -599,6 +614,52 @@ class GpuBatcher:
             self.handle = None
 
 
+NUM_CANDIDATES_LIMIT = 10000   # VectorFieldDef.java:74
+
+
+@dataclass(frozen=True)
+class KnnQuery:
+    """KnnQuery of the search request as VectorFieldDef.getKnnQuery validates it (VectorFieldDef.java:401-425). The
+    reference runs HNSW with a beam of num_candidates PER LEAF and merges the leaves' lists to k
+    (NrtKnnFloatVectorQuery.java:43-64); here every leaf / shard is searched EXACTLY, so any num_candidates >= k yields the
+    same -- exact -- top k (recall 1.0); it is validated and otherwise unused. similarity_threshold wraps the query in
+    MinThresholdQuery(score >= similarityToScore(threshold)) (:590-593)."""
+    k: int
+    num_candidates: int
+    similarity_threshold: Optional[float] = None
+
+    def validate(self):
+        if self.k < 1:
+            raise ValueError("Vector search k must be >= 1")
+        if self.num_candidates < self.k:
+            raise ValueError("Vector search numCandidates must be >= k")
+        if self.num_candidates > NUM_CANDIDATES_LIMIT:
+            raise ValueError(f"Vector search numCandidates > {NUM_CANDIDATES_LIMIT}")
+
+
+def similarity_to_score(similarity: float, sim: int, dims: int = 0, byte_field: bool = False) -> np.float32:
+    """VectorFieldDef.similarityToScore (float :664-673, byte :870-881), float arithmetic."""
+    s = np.float32(similarity)
+    if sim == 0:
+        return np.float32(1.0) / (np.float32(1.0) + s * s)
+    if sim == 1 and byte_field:
+        return np.float32(0.5) + s / np.float32(dims * (1 << 15))
+    if sim in (1, 2):
+        return (np.float32(1.0) + s) / np.float32(2.0)
+    return np.float32(1.0) / (np.float32(1.0) + np.float32(-1.0) * s) if s < 0 else s + np.float32(1.0)
+
+
+def normalized_cosine_vectors(vectors: np.ndarray):
+    """What a `normalized_cosine` vector field does to its input (VectorFieldDef.java:308-332, 507-513, 568-573, 651-655):
+    magnitude = sqrt(float dot(v, v)); v /= magnitude (float); the field is then searched with DOT_PRODUCT and the magnitude is
+    kept in the <field>._magnitude float doc value. Returns (unit vectors float32, magnitudes float32)."""
+    v = np.ascontiguousarray(vectors, np.float32)
+    mag = np.sqrt(np.einsum("ij,ij->i", v, v, dtype=np.float32)).astype(np.float32)
+    if (mag == 0).any():
+        raise ValueError("Vector magnitude cannot be 0 when using cosine similarity")   # validateVectorForSearch :634-639
+    return (v / mag[:, None]).astype(np.float32), mag
+
+
 def blend_rrf(ctx: GpuContext, docs: np.ndarray, counts: np.ndarray, boosts: Sequence[float], rank_constant: int,
               top_hits: int):
     """BlenderOperation.blend with the weighted-RRF operation (BlenderOperation.java:76-87) for nq queries:
@@ -612,6 +673,23 @@ def blend_rrf(ctx: GpuContext, docs: np.ndarray, counts: np.ndarray, boosts: Seq
     check(_native.gpu_lib().nrtgpu_blend_rrf(ctx.handle, R, nq, top_in, d.ctypes.data, c.ctypes.data, b.ctypes.data,
                                              rank_constant, top_hits, od.ctypes.data, os_.ctypes.data, oc.ctypes.data,
                                              ot.ctypes.data))
+    return od, os_, oc, ot
+
+
+def blend_scores(ctx: GpuContext, mode: str, docs: np.ndarray, scores: np.ndarray, counts: np.ndarray, boosts: Sequence[float],
+                 top_hits: int):
+    """BlenderOperation.blend with WeightedScoreOrderBlenderOperation (MAX / SUM / AVG of score * boost): docs, scores
+    [R, nq, top_in], counts [R, nq] -> (docs [nq, top_hits], scores, counts, total)."""
+    d = np.ascontiguousarray(docs, np.int32)
+    s = np.ascontiguousarray(scores, np.float32)
+    c = np.ascontiguousarray(counts, np.int32)
+    b = np.ascontiguousarray(boosts, np.float32)
+    R, nq, top_in = d.shape
+    od, os_ = np.zeros((nq, top_hits), np.int32), np.zeros((nq, top_hits), np.float32)
+    oc, ot = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+    check(_native.gpu_lib().nrtgpu_blend_scores(ctx.handle, {"max": 1, "sum": 2, "avg": 3}[mode.lower()], R, nq, top_in, d.ctypes.data,
+                                                s.ctypes.data, c.ctypes.data, b.ctypes.data, top_hits, od.ctypes.data, os_.ctypes.data,
+                                                oc.ctypes.data, ot.ctypes.data))
     return od, os_, oc, ot
 
 

@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
                                     C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_blend_rrf.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.orc_blend_scores.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.orc_rescore_combine.restype = None
         L.orc_rescore_combine.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_double, C.c_double]
@@ -336,6 +338,20 @@ def blend_rrf(docs, counts, boosts, rank_constant: int, top_out: int):
     total = C.c_int32()
     n = lib().orc_blend_rrf(R, top_in, docs.ctypes.data, counts.ctypes.data, boosts.ctypes.data, rank_constant, top_out,
                             od.ctypes.data, os_.ctypes.data, C.byref(total))
+    return od[:n], os_[:n], total.value
+
+
+def blend_scores(mode: int, docs, scores, counts, boosts, top_out: int):
+    """Score-order blend of one query: docs/scores [R, top_in], mode 1 MAX / 2 SUM / 3 AVG."""
+    docs = np.ascontiguousarray(docs, np.int32)
+    scores = np.ascontiguousarray(scores, np.float32)
+    counts = np.ascontiguousarray(counts, np.int32)
+    boosts = np.ascontiguousarray(boosts, np.float32)
+    R, top_in = docs.shape
+    od, os_ = np.zeros(top_out, np.int32), np.zeros(top_out, np.float32)
+    total = C.c_int32()
+    n = lib().orc_blend_scores(mode, R, top_in, docs.ctypes.data, scores.ctypes.data, counts.ctypes.data, boosts.ctypes.data, top_out,
+                               od.ctypes.data, os_.ctypes.data, C.byref(total))
     return od[:n], os_[:n], total.value
 
 

@@ -595,7 +595,9 @@ float orc_vector_score_f32(const float* a, const float* b, int32_t dims, int32_t
     double x = a[i], y = b[i];
     dot += x * y; na += x * x; nb += y * y; d2 += (x - y) * (x - y);
   }
-  switch (sim) {
+  /* byte vectors (sim | 0x100; the values are the bytes): reference VectorFieldDef.java:870-881 -- only DOT_PRODUCT differs */
+  if (sim == (ORC_SIM_DOT | 0x100)) return 0.5f + (float)dot / (float)(dims * (1 << 15));
+  switch (sim & 0xff) {
     case ORC_SIM_L2: return 1.0f / (1.0f + (float)d2);
     case ORC_SIM_DOT: { float s = (1.0f + (float)dot) / 2.0f; return s > 0 ? s : 0; }
     case ORC_SIM_COSINE: { float c = (float)(dot / sqrt(na * nb)); float s = (1.0f + c) / 2.0f; return s > 0 ? s : 0; }
@@ -661,6 +663,37 @@ int orc_blend_rrf(int32_t n_retrievers, int32_t top_in, const int32_t* docs, con
   int o = n < top_out ? n : top_out;
   for (int i = 0; i < o; ++i) { out_docs[i] = m[i].doc; out_scores[i] = m[i].score; }
   free(m);
+  return o;
+}
+
+/* reference .../blender/operation/WeightedScoreOrderBlenderOperation.java:50-73 + .../blender/score/WeightedScoreDoc.java:57-77:
+ * first hit score = score * boost; later retrievers combine score * boost by MAX (1), SUM (2) or running AVG (3), float ops */
+int orc_blend_scores(int32_t mode, int32_t n_retrievers, int32_t top_in, const int32_t* docs, const float* scores,
+                     const int32_t* counts, const float* boosts, int32_t top_out, int32_t* out_docs, float* out_scores, int32_t* total) {
+  size_t cap = (size_t)n_retrievers * (size_t)top_in;
+  hit_t* m = (hit_t*)malloc(sizeof(hit_t) * (cap ? cap : 1));
+  int* have = (int*)malloc(sizeof(int) * (cap ? cap : 1));
+  int n = 0;
+  for (int r = 0; r < n_retrievers; ++r) {
+    for (int i = 0; i < counts[r]; ++i) {
+      int32_t d = docs[(size_t)r * top_in + i];
+      float w = scores[(size_t)r * top_in + i] * boosts[r];
+      int j = 0;
+      for (; j < n; ++j) if (m[j].doc == d) break;
+      if (j == n) { m[n].doc = d; m[n].score = w; m[n].k = 0; have[n] = 1; ++n; }
+      else {
+        if (mode == 1) m[j].score = m[j].score > w ? m[j].score : w;
+        else if (mode == 2) m[j].score = m[j].score + w;
+        else m[j].score = (m[j].score * (float)have[j] + w) / (float)(have[j] + 1);
+        have[j]++;
+      }
+    }
+  }
+  *total = n;
+  qsort(m, (size_t)n, sizeof(hit_t), hit_cmp_best_first);
+  int o = n < top_out ? n : top_out;
+  for (int i = 0; i < o; ++i) { out_docs[i] = m[i].doc; out_scores[i] = m[i].score; }
+  free(m); free(have);
   return o;
 }
 

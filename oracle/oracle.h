@@ -100,6 +100,8 @@ int orc_search_sorted(const orc_index* ix, const orc_clause* clauses, const orc_
                       int32_t n_threads, const orc_sort* sort, const int64_t* after_values, int32_t* out_docs,
                       int64_t* out_values, int32_t* out_counts, int64_t* out_total);
 
+int orc_blend_scores(int32_t mode, int32_t n_retrievers, int32_t top_in, const int32_t* docs, const float* scores,
+                     const int32_t* counts, const float* boosts, int32_t top_out, int32_t* out_docs, float* out_scores, int32_t* total);
 int orc_match_bitmap(const orc_index* ix, const orc_clause* clauses, const orc_query* query, uint8_t* out_bitmap);
 int orc_score_docs(const orc_index* ix, const orc_clause* clauses, const orc_query* queries, int32_t nq, int32_t n_hits,
                    const int32_t* docs, const int32_t* counts, uint8_t* out_matches, float* out_scores);

@@ -104,3 +104,21 @@ def test_hybrid_pipeline_equals_oracle_pipeline(gpu_ctx):
     for q in range(nq):
         wd, ws, wt = oracle.blend_rrf(np.stack([od[q], wkd[q]]), [oc[q], wkc[q]], [1.0, 2.0], 60, k)
         assert bt[q] == wt and np.array_equal(bd[q, :bc[q]], wd) and np.array_equal(bs[q, :bc[q]].view(np.uint32), ws.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode,code", [("max", 1), ("sum", 2), ("avg", 3)])
+def test_score_order_blender(gpu_ctx, mode, code):
+    """WeightedScoreOrderBlenderOperation.java:50-73 / WeightedScoreDoc.java:57-77: score * boost per retriever, combined by
+    MAX / SUM / running AVG in retriever order, float arithmetic; bit-exact vs the oracle (ties by doc asc, as for RRF)."""
+    from nrtsearch_b200.search import blend_scores
+    rng = np.random.default_rng(71)
+    R, nq, top_in, top_out = 3, 40, 60, 50
+    docs = np.stack([np.stack([rng.choice(500, size=top_in, replace=False) for _ in range(nq)]) for _ in range(R)]).astype(np.int32)
+    scores = np.sort(rng.random((R, nq, top_in)).astype(np.float32) * 10, axis=2)[:, :, ::-1].copy()
+    counts = rng.integers(0, top_in + 1, size=(R, nq)).astype(np.int32)
+    boosts = np.array([1.0, 0.35, 2.5], np.float32)
+    bd, bs, bc, bt = blend_scores(gpu_ctx, mode, docs, scores, counts, boosts, top_out)
+    for q in range(nq):
+        wd, ws, wt = oracle.blend_scores(code, docs[:, q], scores[:, q], counts[:, q], boosts, top_out)
+        assert bt[q] == wt and bc[q] == len(wd)
+        assert np.array_equal(bd[q, :bc[q]], wd) and np.array_equal(bs[q, :bc[q]].view(np.uint32), ws.view(np.uint32))

@@ -132,3 +132,34 @@ def test_knn_rank_safe_on_near_duplicates(gpu_ctx):
         check(gd, gs, gc, wd, ws, wc)
         if sim == ix.SIM_COSINE:
             assert unc >= 6, unc   # the six near-duplicate queries cannot be certified from bf16 scores
+
+
+@pytest.mark.parametrize("sim", [ix.SIM_L2, ix.SIM_DOT, ix.SIM_COSINE, ix.SIM_MIP])
+def test_knn_byte_vectors(gpu_ctx, sim):
+    """ByteVectorFieldDef (VectorFieldDef.java:870-881): int8 vectors, byte score mapping (DOT_PRODUCT = 0.5 + dot / (dims * 2^15))."""
+    rng = np.random.default_rng(11 + sim)
+    corpus = rng.integers(-128, 128, size=(9_000, 96), dtype=np.int8)
+    queries = rng.integers(-128, 128, size=(30, 96), dtype=np.int8).astype(np.float32)
+    gix = GpuIndex(gpu_ctx, vec_shard(corpus, sim))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(queries, 20)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(corpus.astype(np.float32), sim | 0x100, queries, 20)
+    check(gd, gs, gc, wd, ws, wc)
+
+
+def test_knn_normalized_cosine(gpu_ctx):
+    """nrtsearch's normalized_cosine (VectorFieldDef.java:308-332, 568-573, 651-655): vectors are L2-normalised at index and
+    query time (float division by the float magnitude), searched with DOT_PRODUCT; the magnitude goes to <field>._magnitude."""
+    from nrtsearch_b200.search import normalized_cosine_vectors
+    raw = ix.synth_vectors(8_000, 80) * 3.0
+    queries = ix.synth_vectors(25, 80, seed=ix.SEED_VQUERIES) * 0.2
+    unit, magnitude = normalized_cosine_vectors(raw)
+    qunit, _ = normalized_cosine_vectors(queries)
+    assert np.allclose(np.linalg.norm(unit, axis=1), 1.0, atol=1e-5) and np.allclose(magnitude, np.linalg.norm(raw, axis=1), rtol=1e-5)
+    gix = GpuIndex(gpu_ctx, vec_shard(unit, ix.SIM_DOT))
+    gd, gs, gc = GpuIndexSearcher(gix).knn(qunit, 30)
+    gix.close()
+    wd, ws, wc = oracle.knn_exact(unit, ix.SIM_DOT, qunit, 30)
+    check(gd, gs, gc, wd, ws, wc)
+    cd, cs, cc = oracle.knn_exact(raw, ix.SIM_COSINE, queries, 30)   # and it IS cosine similarity of the raw vectors
+    np.testing.assert_allclose(gs, cs, rtol=2e-5)

@@ -65,3 +65,38 @@ def test_query_terms_are_distinct_and_in_range(built):
     t = ix.synth_query_terms(1024, 3, 1_000_000)
     assert t.min() >= 10 and t.max() < 10_000
     assert all(len(set(r)) == 3 for r in t.tolist())
+
+
+def test_knn_query_validation_messages():
+    # VectorFieldDef.getKnnQuery :413-421
+    import pytest
+    from nrtsearch_b200.search import KnnQuery
+    with pytest.raises(ValueError, match="Vector search k must be >= 1"):
+        KnnQuery(0, 10).validate()
+    with pytest.raises(ValueError, match="numCandidates must be >= k"):
+        KnnQuery(10, 5).validate()
+    with pytest.raises(ValueError, match="numCandidates > 10000"):
+        KnnQuery(10, 10001).validate()
+    KnnQuery(10, 100).validate()
+
+
+def test_sort_missing_values_and_sortable_floats():
+    # IntFieldDef.java:103, LongFieldDef.java:103, FloatFieldDef.java:105, DoubleFieldDef.java:105; NumericUtils sortable encodings
+    from nrtsearch_b200.search import SortType, double_to_sortable_long, float_to_sortable_int
+    assert SortType(0, False, True, "int").missing_value() == 2**31 - 1 and SortType(0, True, False, "int").missing_value() == -(2**31)
+    assert SortType(0, False, True, "long").missing_value() == 2**63 - 1
+    xs = [-float("inf"), -3.5, -0.0, 0.0, 1e-30, 2.0, float("inf")]
+    assert [float_to_sortable_int(x) for x in xs] == sorted(float_to_sortable_int(x) for x in xs)
+    assert [double_to_sortable_long(x) for x in xs] == sorted(double_to_sortable_long(x) for x in xs)
+    assert SortType(0, False, True, "float").missing_value() == float_to_sortable_int(float("inf"))
+
+
+def test_packed_record_layout_roundtrip():
+    from nrtsearch_b200.shards import packed_words, unpack_record
+    nq, k = 5, 3
+    w = packed_words(nq, k)
+    assert w == ((2 * nq * k + 2 * nq + 1) & ~1) + 2 * nq
+    r = np.arange(w, dtype=np.int32)
+    d, s, c, f, t = unpack_record(r, nq, k)
+    assert d.shape == (nq, k) and s.shape == (nq, k) and len(c) == nq and len(f) == nq and len(t) == nq
+    assert d[0, 0] == 0 and c[0] == 2 * nq * k and f[0] == 2 * nq * k + nq
