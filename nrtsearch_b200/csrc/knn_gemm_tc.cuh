@@ -322,6 +322,128 @@ knn_gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
   }
 }
 
+// ---- 256 x 256 variant (default): one persistent CTA per SM, TWO 128 x 256 accumulators (all 512 TMEM columns) fed by the
+// same corpus tile -- 64 KB of operands per k-block for 2 x the flops of the 128 x 256 kernel (48 KB), i.e. a third less
+// L2 -> SM traffic per flop, which is what bounded the smaller tile (profiles/r1_final_counters.md: tensor pipe 18 %, L2 hit
+// 82 %) -- and a 3-stage TMA ring that keeps streaming across tiles. Warp 0 = TMA producer, warp 1 = MMA issuer (two
+// tcgen05.mma per 16-wide k-step), warps 4-11 = epilogue (warp w reads TMEM lane quadrant w % 4 of accumulator (w - 4) / 4).
+constexpr int BM2 = 256;
+constexpr int kStages2 = 3;
+constexpr int kGemm2Threads = 384;
+constexpr uint32_t kA2Bytes = BM2 * BK * 2, kStage2Bytes = kA2Bytes + kBBytes;
+constexpr uint32_t kTmem2Cols = 512;
+constexpr size_t kGemm2Smem = (size_t)kStages2 * kStage2Bytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+knn_gemm_bf16_256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
+  extern __shared__ uint8_t gemm_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)gemm_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)kStages2 * kA2Bytes;
+  uint64_t* full_bar = (uint64_t*)(base + (size_t)kStages2 * kStage2Bytes);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tmem_full = empty_bar + kStages2;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (P.M + BM2 - 1) / BM2, n_tiles = (P.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int num_kb = (P.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages2; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
+    bar_init(tmem_full, 1); bar_init(tmem_empty, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "r"(kTmem2Cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer: one continuous stream of k-blocks over all tiles of this CTA
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * BM2, n0 = (t / m_tiles) * BN;   // query tiles vary fastest (corpus tile shared via L2)
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages2;
+          bar_wait(&empty_bar[s], ((it / kStages2) & 1) ^ 1);
+          bar_expect_tx(&full_bar[s], kStage2Bytes);
+          tma_load_2d(smA + (size_t)s * kA2Bytes, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(smB + (size_t)s * kBBytes, &tmB, &full_bar[s], kb * BK, P.n_base + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        bar_wait(tmem_empty, (lt & 1) ^ 1);   // the epilogue has drained both accumulators of the previous tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages2;
+          bar_wait(&full_bar[s], (it / kStages2) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da0 = make_smem_desc(smA + (size_t)s * kA2Bytes);
+          const uint64_t da1 = make_smem_desc(smA + (size_t)s * kA2Bytes + 128 * BK * 2);   // query rows 128..255 of the tile
+          const uint64_t db = make_smem_desc(smB + (size_t)s * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / kUmmaK; ++k) {
+            umma_f16(tmem_base, da0 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_f16(tmem_base + (uint32_t)BN, da1 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue warps
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = half * 128 + quad * 32 + lane;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      const int m0 = (t % m_tiles) * BM2, n0 = (t / m_tiles) * BN;
+      const int gq = m0 + row;
+      bar_wait(tmem_full, lt & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == BN / 32 - 1) {   // every column of this thread's accumulator row is in registers: hand TMEM back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(tmem_empty)) : "memory");
+        }
+        epilogue_slice(P, v, gq, n0, c);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmem2Cols) : "memory");
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -440,13 +440,16 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   NRT_CUDA_TRY(cudaMemcpyAsync(dQ, h_queries, (size_t)nq * dims * sizeof(float), cudaMemcpyHostToDevice, st));
   NRT_CUDA_TRY(cudaMemsetAsync(dCn, 0, (size_t)nq * sizeof(int32_t), st));
   __nv_bfloat16* dQb = nullptr;
-  CUtensorMap tmQ;
+  CUtensorMap tmQ, tmQ256s;
+  const CUtensorMap* tmQ256 = nullptr;
   if (use_tc) {
     NRT_KNN_GET(13, dQb, (size_t)nq * dims * sizeof(__nv_bfloat16));
     tc::f32_to_bf16_kernel<<<256, 256, 0, st>>>(dQ, dQb, (size_t)nq * dims);
     NRT_CUDA_TRY(cudaGetLastError());
     int rc = tc::make_tensor_map_bf16(&tmQ, dQb, (uint64_t)nq, (uint64_t)dims, tc::BM);
     if (rc) return rc;
+    if ((rc = tc::make_tensor_map_bf16(&tmQ256s, dQb, (uint64_t)nq, (uint64_t)dims, tc::BM2))) return rc;
+    tmQ256 = &tmQ256s;
   }
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float gemm_ms = 0.f, select_ms = 0.f;
@@ -463,14 +466,19 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs; G.live_bits = d_live_bits;
       // default: one tile per CTA, 2 CTAs/SM (measured 4.9 ms at C4); the persistent double-buffered variant measured
       // 7.5 ms -- both are bound by L2 -> SM operand traffic (48 KB per 128x256x64 k-block), see DESIGN.md 4.3
-      static const bool simple_gemm = getenv("NRTGPU_KNN_GEMM_PERSISTENT") == nullptr;
-      const int tiles = ((nq + tc::BM - 1) / tc::BM) * ((nc + tc::BN - 1) / tc::BN);
-      if (simple_gemm) {
+      // NRTGPU_KNN_GEMM: "256" (default) = persistent 256 x 256 tiles, two TMEM accumulators; "128" = one 128 x 256 tile per
+      // CTA, 2 CTAs / SM (round 1); "p128" = persistent 128 x 256 with a double-buffered accumulator
+      static const int gemm_kind = [] { const char* e = getenv("NRTGPU_KNN_GEMM"); return !e ? 2 : (e[0] == 'p' ? 1 : (e[0] == '1' ? 0 : 2)); }();
+      static int sm_count = 0;
+      if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+      if (gemm_kind == 2 && tmQ256) {
+        const int tiles = ((nq + tc::BM2 - 1) / tc::BM2) * ((nc + tc::BN - 1) / tc::BN);
+        tc::knn_gemm_bf16_256_kernel<<<tiles < sm_count ? tiles : sm_count, tc::kGemm2Threads, tc::kGemm2Smem, st>>>(*tmQ256, *tm_corpus, G);
+      } else if (gemm_kind == 0 || gemm_kind == 2) {
         dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
         tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
       } else {
-        static int sm_count = 0;
-        if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+        const int tiles = ((nq + tc::BM - 1) / tc::BM) * ((nc + tc::BN - 1) / tc::BN);
         tc::knn_gemm_bf16_persistent_kernel<<<tiles < sm_count ? tiles : sm_count, tc::kGemmThreads, tc::kPGemmSmem, st>>>(tmQ, *tm_corpus, G);
       }
     } else {

@@ -137,6 +137,7 @@ struct nrtgpu_ctx {
   bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
   std::mutex hyb_mu;             // O(k) hybrid stages share one pooled device scratch (no cudaMalloc per call)
   DevBuf<int32_t> hyb_scratch;
+  bool order_lpt = false;        // NRTGPU_ORDER=lpt: query-major work order, longest query first
   bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
   bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
 };
@@ -342,7 +343,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
-  { const char* e = getenv("NRTGPU_ORDER"); c->order_by_cost = e && std::strcmp(e, "cost") == 0; }
+  { const char* e = getenv("NRTGPU_ORDER"); c->order_by_cost = e && (std::strcmp(e, "cost") == 0 || std::strcmp(e, "lpt") == 0); c->order_lpt = e && std::strcmp(e, "lpt") == 0; }
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint32_t>)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -356,6 +357,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v3::ProbeSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm2Smem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kPGemmSmem));
   *out = c.release();
   return NRTGPU_OK;
@@ -839,8 +841,13 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   b->n_lists = b->n_slices + (warm_ok ? 1 : 0);
   int32_t class_end[3] = {0, 0, 0};
   for (int cls = 0; cls < 3; ++cls) {
-    for (int s = 0; s < b->n_slices; ++s)
-      for (int qi : order) if (engine_class(qi) == cls) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+    if (ix->ctx->order_lpt && b->use_probe) {   // longest query first, its slices together (experiment: NRTGPU_ORDER=lpt)
+      for (int qi : order) if (engine_class(qi) == cls)
+        for (int s = 0; s < b->n_slices; ++s) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+    } else {
+      for (int s = 0; s < b->n_slices; ++s)
+        for (int qi : order) if (engine_class(qi) == cls) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+    }
     class_end[cls] = (int32_t)wq.size();
   }
   b->n_work = (int32_t)wq.size();
