@@ -75,6 +75,7 @@ struct GemmParams {
   const uint8_t* filter;  // per DOC 0/1 or NULL
   const int32_t* vec_docs;  // ordinal -> doc or NULL
   const uint32_t* live_bits;  // liveDocs bitmap or NULL
+  int debug;              // experiments only (NRTGPU_KNN_DEBUG): 1 = the epilogue drops every value (mainloop-only timing)
 };
 
 // one 32-column slice of an accumulator row: store the approximate scores (unfused) or keep the survivors (fused)
@@ -113,6 +114,61 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& P, const uint32
           }
         }
       }
+    }
+  }
+}
+
+// fused top-k' epilogue of one 32-column slice with the tile's (a, b) pairs staged in shared memory (one broadcast LDS.64
+// per column instead of a global load per element: the profile of the first 256 x 256 build had 40 % of its stall samples
+// on those loads, the tensor pipe waiting for the epilogue to hand the accumulators back)
+// Survivors of a row are buffered in shared memory (kSurvBuf keys per row, column-major so the lanes of a warp do not
+// collide) and appended to the query's chunk list with ONE atomicAdd per flush: a returning atomic per survivor cost every
+// warp a ~1 us round trip at ~30 columns per tile (different lanes survive at different columns), 2/3 of the kernel's time.
+constexpr int kSurvBuf = 4;
+constexpr int kSurvRows = 512;   // one buffer column per epilogue thread of the 256 x 256 kernel
+__device__ __forceinline__ void surv_flush(const GemmParams& P, uint64_t* surv, int row, int gq, int& nbuf) {
+  if (nbuf == 0) return;
+  const int pos = atomicAdd(P.cc_cnt + gq, nbuf);
+  for (int i = 0; i < nbuf; ++i)
+    if (pos + i < P.cc_cap) P.cc[(size_t)gq * P.cc_cap + pos + i] = surv[i * kSurvRows + row];
+  nbuf = 0;
+}
+
+__device__ __forceinline__ void epilogue_slice_fused(const GemmParams& P, const uint32_t (&v)[32], uint32_t ab_smem /*shared-space address of the tile's [BN] float2*/,
+                                                     float th, int gq, int n0, int c, uint64_t* surv, int row, int& nbuf) {
+  const int lim = gq < P.M ? P.N - (n0 + c * 32) : 0;   // columns of this slice inside the chunk (rows past M: none)
+  // branch-free pass: which of the 32 values can still enter the query's best k'? (two (a, b) pairs per LDS.128)
+  uint32_t mask = 0u;
+  const uint32_t sb = ab_smem + (uint32_t)(c * 32) * 8u;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float a0, b0, a1, b1;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(b0), "=f"(a1), "=f"(b1) : "r"(sb + (uint32_t)j * 8u));
+    const float x0 = fmaf(a0, __uint_as_float(v[j]), b0), x1 = fmaf(a1, __uint_as_float(v[j + 1]), b1);
+    mask |= (x0 >= th ? 1u : 0u) << j;
+    mask |= (x1 >= th ? 1u : 0u) << (j + 1);
+  }
+  if (lim < 32) mask &= lim > 0 ? ((1u << lim) - 1u) : 0u;
+  // columns in which ANY row of the warp has a survivor (about 4 of the 32 once the threshold is warm): only those are walked
+  const uint32_t warp_mask = __reduce_or_sync(0xffffffffu, mask);
+  if (warp_mask == 0u) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (!((warp_mask >> j) & 1u)) continue;   // warp-uniform
+    if (!((mask >> j) & 1u)) continue;
+    float a, b;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(sb + (uint32_t)j * 8u));
+    const float x = fmaf(a, __uint_as_float(v[j]), b);
+    const int ord = P.n_base + n0 + c * 32 + j;
+    bool ok = true;
+    if (P.filter || P.live_bits) {
+      const int doc = P.vec_docs ? P.vec_docs[ord] : ord;
+      if (P.filter) ok = P.filter[doc] != 0;
+      if (ok && P.live_bits) ok = (P.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+    }
+    if (ok) {
+      surv[nbuf * kSurvRows + row] = make_key(x, ord);
+      if (++nbuf == kSurvBuf) surv_flush(P, surv, row, gq, nbuf);
     }
   }
 }
@@ -328,11 +384,13 @@ knn_gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
 // 82 %) -- and a 3-stage TMA ring that keeps streaming across tiles. Warp 0 = TMA producer, warp 1 = MMA issuer (two
 // tcgen05.mma per 16-wide k-step), warps 4-11 = epilogue (warp w reads TMEM lane quadrant w % 4 of accumulator (w - 4) / 4).
 constexpr int BM2 = 256;
+
 constexpr int kStages2 = 3;
-constexpr int kGemm2Threads = 384;
+constexpr int kGemm2Threads = 640;   // warps 0 / 1: TMA / MMA, warps 4-19: epilogue (two warps per TMEM lane quadrant and accumulator, half the columns each)
+constexpr int kEpi2Threads = 512;
 constexpr uint32_t kA2Bytes = BM2 * BK * 2, kStage2Bytes = kA2Bytes + kBBytes;
 constexpr uint32_t kTmem2Cols = 512;
-constexpr size_t kGemm2Smem = (size_t)kStages2 * kStage2Bytes + 1024 + 256;
+constexpr size_t kGemm2Smem = (size_t)kStages2 * kStage2Bytes + 1024 + 256 + 2 * BN * sizeof(float2) + (size_t)kSurvBuf * kSurvRows * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 knn_gemm_bf16_256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
@@ -345,15 +403,20 @@ knn_gemm_bf16_256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = empty_bar + kStages2;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 1);
+  float2* ab_s = (float2*)(base + (size_t)kStages2 * kStage2Bytes + 256);   // [2][BN] (a, b) of the tile's vectors, double buffered
+  uint64_t* surv = (uint64_t*)(ab_s + 2 * BN);                                // [kSurvBuf][BM2] survivor keys per accumulator row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = (P.M + BM2 - 1) / BM2, n_tiles = (P.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int num_kb = (P.K + BK - 1) / BK;
+  // Tile order: t = blockIdx.x, + gridDim.x, ... in the m-fastest numbering. The host makes the grid a multiple of the query
+  // tiles when it can, so a CTA keeps ONE query tile for the whole launch (t % m_tiles is constant): an epilogue thread then
+  // serves the same query all along and appends its survivors with one atomic per full buffer, not one per tile.
 
   if (tid == 0) {
     for (int s = 0; s < kStages2; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
-    bar_init(tmem_full, 1); bar_init(tmem_empty, 256);
+    bar_init(tmem_full, 1); bar_init(tmem_empty, kEpi2Threads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -407,16 +470,29 @@ knn_gemm_bf16_256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {   // ===== epilogue warps
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int quad = warp & 3, half = ((warp - 4) >> 2) & 1, chalf = (warp - 4) >> 3;   // TMEM lane quadrant, accumulator, column half
     const int row = half * 128 + quad * 32 + lane;
+    const int et = tid - 128;   // epilogue thread 0..511: its own survivor buffer column
     int lt = 0;
+    int nbuf = 0, prev_gq = -1;   // survivors buffered for query prev_gq, flushed at the start of the next tile
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
       const int m0 = (t % m_tiles) * BM2, n0 = (t / m_tiles) * BN;
       const int gq = m0 + row;
+      const bool fused = P.S == nullptr;
+      float2* abt = ab_s + (lt & 1) * BN;
+      float th = 0.0f;
+      if (fused) {   // stage the tile's (a, b) pairs (256 epilogue threads, one pair each) while the MMAs run
+        if (et < BN) abt[et] = __ldg(P.ab + min(n0 + et, P.N - 1));
+        th = gq < P.M ? P.theta[gq] : 0.0f;
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // epilogue warps only; a thread is at most one tile ahead, so the
+                                                         // other buffer is not being read any more when it is rewritten
+        // survivors buffered for ANOTHER query (the CTA moved to a different query tile) go out now, while this tile's MMAs run
+        if (prev_gq >= 0 && prev_gq != gq) surv_flush(P, surv, et, prev_gq, nbuf);
+      }
       bar_wait(tmem_full, lt & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * BN + c * 32);
         asm volatile(
@@ -428,13 +504,193 @@ knn_gemm_bf16_256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == BN / 32 - 1) {   // every column of this thread's accumulator row is in registers: hand TMEM back to the MMA warp
+        if (c == (chalf + 1) * (BN / 64) - 1) {   // this thread's last slice is in registers: hand TMEM back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(tmem_empty)) : "memory");
         }
-        epilogue_slice(P, v, gq, n0, c);
+        if (P.debug & 1) continue;
+        if (fused) epilogue_slice_fused(P, v, s_u32(abt), th, gq, n0, c, surv, et, nbuf);
+        else epilogue_slice(P, v, gq, n0, c);
+      }
+      prev_gq = (fused && gq < P.M) ? gq : -1;
+    }
+    if (prev_gq >= 0) surv_flush(P, surv, et, prev_gq, nbuf);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmem2Cols) : "memory");
+  }
+}
+
+// ---- 256 x 128 tiles, DOUBLE-BUFFERED in TMEM (default): buffer b holds the two 128 x 128 accumulators of a tile (query rows
+// 0-127 and 128-255 against the same 128 corpus vectors) in columns [256 b, 256 b + 256); the MMAs of tile t + 1 run into the
+// other buffer while the 16 epilogue warps drain tile t, so the fused top-k' epilogue (the bottleneck of the single-buffered
+// 256 x 256 kernel: mainloop alone 1.14 ms = 82 % of the tensor peak, with epilogue 2.3 ms) leaves the critical path. A
+// survivor's value is re-read from TMEM by a one-column tcgen05.ld (warp-uniform loop over the columns in which any row
+// survives) instead of 32 predicated blocks. 4-stage TMA ring of 48 KB k-blocks.
+constexpr int BN3 = 128;
+constexpr int kStages3 = 4;
+constexpr uint32_t kB3Bytes = BN3 * BK * 2, kStage3Bytes = kA2Bytes + kB3Bytes;
+constexpr size_t kGemm3Smem = (size_t)kStages3 * kStage3Bytes + 1024 + 256 + 2 * BN3 * sizeof(float2) + (size_t)kSurvBuf * kSurvRows * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+knn_gemm_bf16_db_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams P) {
+  extern __shared__ uint8_t gemm_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)gemm_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)kStages3 * kA2Bytes;
+  uint64_t* full_bar = (uint64_t*)(base + (size_t)kStages3 * kStage3Bytes);
+  uint64_t* empty_bar = full_bar + kStages3;
+  uint64_t* tmem_full = empty_bar + kStages3;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  float2* ab_s = (float2*)(base + (size_t)kStages3 * kStage3Bytes + 256);   // [2][BN3]
+  uint64_t* surv = (uint64_t*)(ab_s + 2 * BN3);                              // [kSurvBuf][512]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (P.M + BM2 - 1) / BM2, n_tiles = (P.N + BN3 - 1) / BN3;
+  const int total = m_tiles * n_tiles;
+  const int num_kb = (P.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages3; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { bar_init(&tmem_full[b], 1); bar_init(&tmem_empty[b], kEpi2Threads); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "r"(kTmem2Cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * BM2, n0 = (t / m_tiles) * BN3;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages3;
+          bar_wait(&empty_bar[s], ((it / kStages3) & 1) ^ 1);
+          bar_expect_tx(&full_bar[s], kStage3Bytes);
+          tma_load_2d(smA + (size_t)s * kA2Bytes, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(smB + (size_t)s * kB3Bytes, &tmB, &full_bar[s], kb * BK, P.n_base + n0);
+        }
       }
     }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN3 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        const int b = lt & 1;
+        bar_wait(&tmem_empty[b], ((lt >> 1) & 1) ^ 1);   // the epilogue has drained this buffer (two tiles ago)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc0 = tmem_base + (uint32_t)(b * 2 * BN3), acc1 = acc0 + (uint32_t)BN3;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages3;
+          bar_wait(&full_bar[s], (it / kStages3) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da0 = make_smem_desc(smA + (size_t)s * kA2Bytes);
+          const uint64_t da1 = make_smem_desc(smA + (size_t)s * kA2Bytes + 128 * BK * 2);
+          const uint64_t db = make_smem_desc(smB + (size_t)s * kB3Bytes);
+#pragma unroll
+          for (int k = 0; k < BK / kUmmaK; ++k) {
+            umma_f16(acc0, da0 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_f16(acc1, da1 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[b]);
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue warps
+    const int quad = warp & 3, half = ((warp - 4) >> 2) & 1, chalf = (warp - 4) >> 3;   // TMEM lane quadrant, accumulator, column half
+    const int row = half * 128 + quad * 32 + lane;
+    const int et = tid - 128;
+    const bool fused = P.S == nullptr;
+    int lt = 0;
+    int nbuf = 0, prev_gq = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      const int b = lt & 1;
+      const int m0 = (t % m_tiles) * BM2, n0 = (t / m_tiles) * BN3;
+      const int gq = m0 + row;
+      float2* abt = ab_s + b * BN3;
+      float th = 0.0f;
+      if (fused) {
+        if (et < BN3) abt[et] = __ldg(P.ab + min(n0 + et, P.N - 1));
+        th = gq < P.M ? P.theta[gq] : 0.0f;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (prev_gq >= 0 && prev_gq != gq) surv_flush(P, surv, et, prev_gq, nbuf);
+      }
+      bar_wait(&tmem_full[b], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 2 * BN3 + half * BN3);
+#pragma unroll 1
+      for (int c = chalf * (BN3 / 64); c < (chalf + 1) * (BN3 / 64); ++c) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(lane_addr + (uint32_t)(c * 32)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (P.debug & 1) continue;
+        if (!fused) { epilogue_slice(P, v, gq, n0, c); continue; }
+        // branch-free pass over the slice: which values can still enter the query's best k'?
+        const int lim = gq < P.M ? P.N - (n0 + c * 32) : 0;
+        uint32_t mask = 0u;
+        const uint32_t sb = s_u32(abt) + (uint32_t)(c * 32) * 8u;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a0, b0, a1, b1;
+          asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(b0), "=f"(a1), "=f"(b1) : "r"(sb + (uint32_t)j * 8u));
+          const float x0 = fmaf(a0, __uint_as_float(v[j]), b0), x1 = fmaf(a1, __uint_as_float(v[j + 1]), b1);
+          mask |= (x0 >= th ? 1u : 0u) << j;
+          mask |= (x1 >= th ? 1u : 0u) << (j + 1);
+        }
+        if (lim < 32) mask &= lim > 0 ? ((1u << lim) - 1u) : 0u;
+        // survivors: warp-uniform walk over the columns in which any row survives; the value comes back by a one-column TMEM load
+        uint32_t warp_mask = __reduce_or_sync(0xffffffffu, mask);
+        while (warp_mask) {
+          const int j = __ffs(warp_mask) - 1;
+          warp_mask &= warp_mask - 1u;
+          uint32_t vj;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vj) : "r"(lane_addr + (uint32_t)(c * 32 + j)) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if ((mask >> j) & 1u) {
+            const float2 ab = abt[c * 32 + j];
+            const float x = fmaf(ab.x, __uint_as_float(vj), ab.y);
+            const int ord = P.n_base + n0 + c * 32 + j;
+            bool ok = true;
+            if (P.filter || P.live_bits) {
+              const int doc = P.vec_docs ? P.vec_docs[ord] : ord;
+              if (P.filter) ok = P.filter[doc] != 0;
+              if (ok && P.live_bits) ok = (P.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+            }
+            if (ok) {
+              surv[nbuf * kSurvRows + et] = make_key(x, ord);
+              if (++nbuf == kSurvBuf) surv_flush(P, surv, et, gq, nbuf);
+            }
+          }
+        }
+      }
+      // this thread is done with the buffer: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tmem_empty[b])) : "memory");
+      prev_gq = (fused && gq < P.M) ? gq : -1;
+    }
+    if (prev_gq >= 0) surv_flush(P, surv, et, prev_gq, nbuf);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

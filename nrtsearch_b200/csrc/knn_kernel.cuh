@@ -24,6 +24,7 @@ constexpr int kKnnKStep = 16;
 constexpr int kKnnChunk = 32768;   // docs per streamed chunk
 constexpr int kKnnSelThreads = 256;
 constexpr int kKnnCandCap = 4096;
+constexpr int kKnnWarmChunk = 32768;   // vectors scored through the unfused path to seed the thresholds of the fused chunks
 
 // per-vector squared magnitude (double accumulate -> float)
 __global__ void knn_norm2_kernel(const float* __restrict__ v, int n, int dims, float* __restrict__ out) {
@@ -116,6 +117,7 @@ struct KnnSelectLaunch {
   int kprime; int nq;
   uint64_t* cand;          // [nq][kprime] sorted desc keys (approx score, ord)
   int32_t* cand_cnt;       // [nq]
+  float* theta_out;        // optional [nq]: the k'-th best approximate score once the list is full (threshold of the fused chunks)
 };
 
 __global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLaunch L) {
@@ -170,7 +172,10 @@ __global__ void __launch_bounds__(kKnnSelThreads) knn_select_kernel(KnnSelectLau
   }
   const int keep = compact();
   for (int i = tid; i < keep; i += kKnnSelThreads) L.cand[(size_t)q * L.kprime + i] = buf[i];
-  if (tid == 0) L.cand_cnt[q] = keep;
+  if (tid == 0) {
+    L.cand_cnt[q] = keep;
+    if (L.theta_out && keep == L.kprime) L.theta_out[q] = key_score(buf[L.kprime - 1]);
+  }
 }
 
 // exact re-score (double accumulation, Lucene score mapping in float) + final top-k; one CTA per query
@@ -403,7 +408,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
                            int32_t* out_counts, const __nv_bfloat16* d_vec_bf16 = nullptr,
                            const CUtensorMap* tm_corpus = nullptr, float* stage_ms = nullptr, const float2* d_ab = nullptr,
                            KnnScratch* sc = nullptr, const uint32_t* d_live_bits = nullptr, float dmax = 0.0f,
-                           int32_t* n_uncertified = nullptr) {
+                           int32_t* n_uncertified = nullptr, const CUtensorMap* tm_corpus128 = nullptr) {
   KnnScratch local_scratch;   // only when the caller brings none (freed on return)
   if (!sc) sc = &local_scratch;
   const bool use_tc = d_vec_bf16 != nullptr && tm_corpus != nullptr && d_ab != nullptr;
@@ -427,7 +432,11 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   int chunk = n < chunk_max ? n : chunk_max;
   chunk = (chunk + 3) & ~3;   // keep score rows 16-byte aligned
   NRT_KNN_GET(4, dQ, (size_t)nq * dims * sizeof(float));
+  // fused mode: the first kKnnWarmChunk vectors go through the UNFUSED path (scores stored, knn_select_kernel) to seed
+  // every query's threshold; with an empty threshold the fused epilogue would have to keep every value it sees
+  const int warm = fused ? (n < kKnnWarmChunk ? ((n + 3) & ~3) : kKnnWarmChunk) : 0;
   if (!fused) NRT_KNN_GET(5, dS, (size_t)nq * chunk * sizeof(float));
+  else NRT_KNN_GET(5, dS, (size_t)nq * warm * sizeof(float));
   NRT_KNN_GET(6, dC, (size_t)nq * kprime * sizeof(uint64_t));
   NRT_KNN_GET(7, dCn, (size_t)nq * sizeof(int32_t));
   NRT_KNN_GET(8, dOD, (size_t)nq * k * sizeof(int32_t));
@@ -454,27 +463,40 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float gemm_ms = 0.f, select_ms = 0.f;
   if (stage_ms) for (auto& e : ev) NRT_CUDA_TRY(cudaEventCreate(&e));
-  // fused mode: the first chunks are small (every value survives an empty threshold) and double up to `chunk`
-  int cur = fused ? 2048 : chunk, n_done = 0;
+  // fused mode: warm-up chunk (unfused), then chunks of 64K, 128K, 256K, 256K, ...: with s vectors seen the expected survivors
+  // of a chunk of c vectors are k' * c / s per query (800, 533, 457, 213, ... at k' = 400), well inside the chunk buffer (cc_cap)
+  int cur = fused ? warm : chunk, n_done = 0;
   for (int base = 0; base < n; base += cur, ++n_done) {
-    if (fused && n_done >= 2 && cur < chunk) cur = cur * 2 < chunk ? cur * 2 : chunk;
+    if (fused && n_done >= 1) cur = n_done == 1 ? 65536 : (n_done == 2 ? 131072 : 262144);
     int nc = n - base < cur ? n - base : cur;
+    const bool warm_chunk = fused && n_done == 0;
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));
     if (use_tc) {
       tc::GemmParams G; G.M = nq; G.N = nc; G.K = dims; G.n_base = base; G.dnorm2 = d_norm2 + base; G.ab = d_ab + base; G.sim = sim & 0xff;
-      G.S = fused ? nullptr : dS; G.ldS = chunk;
+      G.S = (fused && !warm_chunk) ? nullptr : dS; G.ldS = fused ? warm : chunk;
       G.theta = dTheta; G.cc = dCC; G.cc_cnt = dCCn; G.cc_cap = cc_cap; G.filter = dF; G.vec_docs = d_vec_docs; G.live_bits = d_live_bits;
+      { static const int dbg = [] { const char* e = getenv("NRTGPU_KNN_DEBUG"); return e ? atoi(e) : 0; }(); G.debug = dbg; }
       // default: one tile per CTA, 2 CTAs/SM (measured 4.9 ms at C4); the persistent double-buffered variant measured
       // 7.5 ms -- both are bound by L2 -> SM operand traffic (48 KB per 128x256x64 k-block), see DESIGN.md 4.3
       // NRTGPU_KNN_GEMM: "256" (default) = persistent 256 x 256 tiles, two TMEM accumulators; "128" = one 128 x 256 tile per
       // CTA, 2 CTAs / SM (round 1); "p128" = persistent 128 x 256 with a double-buffered accumulator
-      static const int gemm_kind = [] { const char* e = getenv("NRTGPU_KNN_GEMM"); return !e ? 2 : (e[0] == 'p' ? 1 : (e[0] == '1' ? 0 : 2)); }();
+      // "db" (default) = 256 x 128 tiles double-buffered in TMEM
+      static const int gemm_kind = [] { const char* e = getenv("NRTGPU_KNN_GEMM"); return !e ? 3 : (e[0] == 'p' ? 1 : (e[0] == '1' ? 0 : (e[0] == '2' ? 2 : 3))); }();
       static int sm_count = 0;
       if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-      if (gemm_kind == 2 && tmQ256) {
-        const int tiles = ((nq + tc::BM2 - 1) / tc::BM2) * ((nc + tc::BN - 1) / tc::BN);
-        tc::knn_gemm_bf16_256_kernel<<<tiles < sm_count ? tiles : sm_count, tc::kGemm2Threads, tc::kGemm2Smem, st>>>(*tmQ256, *tm_corpus, G);
-      } else if (gemm_kind == 0 || gemm_kind == 2) {
+      if (gemm_kind == 3 && tmQ256 && tm_corpus128) {
+        const int m_tiles = (nq + tc::BM2 - 1) / tc::BM2;
+        const int tiles = m_tiles * ((nc + tc::BN3 - 1) / tc::BN3);
+        int grid = tiles < sm_count ? tiles : sm_count;
+        if (m_tiles <= grid) grid = grid / m_tiles * m_tiles;
+        tc::knn_gemm_bf16_db_kernel<<<grid, tc::kGemm2Threads, tc::kGemm3Smem, st>>>(*tmQ256, *tm_corpus128, G);
+      } else if (gemm_kind >= 2 && tmQ256) {
+        const int m_tiles = (nq + tc::BM2 - 1) / tc::BM2;
+        const int tiles = m_tiles * ((nc + tc::BN - 1) / tc::BN);
+        int grid = tiles < sm_count ? tiles : sm_count;
+        if (m_tiles <= grid) grid = grid / m_tiles * m_tiles;   // every CTA keeps one query tile (see the kernel's tile order)
+        tc::knn_gemm_bf16_256_kernel<<<grid, tc::kGemm2Threads, tc::kGemm2Smem, st>>>(*tmQ256, *tm_corpus, G);
+      } else if (gemm_kind != 1) {
         dim3 grid((nq + tc::BM - 1) / tc::BM, (nc + tc::BN - 1) / tc::BN);
         tc::knn_gemm_bf16_kernel<<<grid, tc::kGemmThreads, tc::kGemmSmem, st>>>(tmQ, *tm_corpus, G);
       } else {
@@ -487,12 +509,12 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     }
     NRT_CUDA_TRY(cudaGetLastError());
     if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[1], st));
-    if (fused) {
+    if (fused && !warm_chunk) {
       KnnMergeChunkLaunch Mg; Mg.cc = dCC; Mg.cc_cnt = dCCn; Mg.cc_cap = cc_cap; Mg.cand = dC; Mg.cand_cnt = dCn; Mg.kprime = kprime;
       Mg.theta = dTheta; Mg.overflow = dOvf;
       knn_merge_chunk_kernel<<<nq, kKnnSelThreads, 0, st>>>(Mg);
     } else {
-      KnnSelectLaunch S; S.S = dS; S.ldS = chunk; S.n_chunk = nc; S.chunk_base = base; S.filter = dF; S.live_bits = d_live_bits; S.vec_docs = d_vec_docs;
+      KnnSelectLaunch S; S.S = dS; S.ldS = fused ? warm : chunk; S.n_chunk = nc; S.theta_out = fused ? dTheta : nullptr; S.chunk_base = base; S.filter = dF; S.live_bits = d_live_bits; S.vec_docs = d_vec_docs;
       S.kprime = kprime; S.nq = nq; S.cand = dC; S.cand_cnt = dCn;
       knn_select_kernel<<<nq, kKnnSelThreads, 0, st>>>(S);
     }
@@ -512,7 +534,7 @@ inline int knn_search_host(const float* d_vec, const float* d_norm2, const int32
     if (ovf) {
       if (stage_ms) for (auto& e : ev) cudaEventDestroy(e);
       return knn_search_host(d_vec, d_norm2, d_vec_docs, n, dims, sim, doc_base, n_docs, h_queries, nq, k, h_boosts, h_filter, st,
-                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms, nullptr, sc, d_live_bits, dmax, n_uncertified);
+                             out_docs, out_scores, out_counts, nullptr, nullptr, stage_ms, nullptr, sc, d_live_bits, dmax, n_uncertified, nullptr);
     }
   }
   if (stage_ms) NRT_CUDA_TRY(cudaEventRecord(ev[0], st));

@@ -185,7 +185,8 @@ struct nrtgpu_index {
   bool vec_is_byte = false;   // byte vector field (ByteVectorFieldDef): same image, byte score mapping
   DevBuf<float> vectors;
   DevBuf<__nv_bfloat16> vec_bf16;   // bf16 copy of the corpus for the tensor-core candidate stage (dims % 8 == 0)
-  CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16
+  CUtensorMap vec_tmap;             // TMA tensor map over vec_bf16 (256-row boxes)
+  CUtensorMap vec_tmap128;          // ... (128-row boxes: the double-buffered GEMM's corpus tile)
   DevBuf<float2> vec_ab;            // per-vector (a, b) of the approximate score a * dot + b
   bool vec_tc = false;
   float vec_dmax = 0.0f;    // largest vector magnitude (error bound of the kNN candidate-stage certificate)
@@ -357,6 +358,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v3::ProbeSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm3Smem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm2Smem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kPGemmSmem));
   *out = c.release();
@@ -573,6 +575,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       tc::f32_to_bf16_kernel<<<1024, 256>>>(ix->vectors.p, ix->vec_bf16.p, (size_t)d->vec_count * d->vec_dims);
       NRT_CUDA_TRY(cudaGetLastError());
       if ((rc = tc::make_tensor_map_bf16(&ix->vec_tmap, ix->vec_bf16.p, (uint64_t)d->vec_count, (uint64_t)d->vec_dims, tc::BN))) return rc;
+      if ((rc = tc::make_tensor_map_bf16(&ix->vec_tmap128, ix->vec_bf16.p, (uint64_t)d->vec_count, (uint64_t)d->vec_dims, tc::BN3))) return rc;
       if ((rc = ix->vec_ab.alloc((size_t)d->vec_count))) return rc;
       knn_ab_kernel<<<(d->vec_count + 255) / 256, 256>>>(ix->vec_norm2.p, d->vec_count, d->vec_similarity, ix->vec_ab.p);
       NRT_CUDA_TRY(cudaGetLastError());
@@ -1507,7 +1510,7 @@ int nrtgpu_search_knn(nrtgpu_index* ix, const float* queries, int32_t nq, int32_
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim | (ix->vec_is_byte ? kKnnByteFlag : 0),
                          ix->doc_base, ix->n_docs, queries, nq, k, boosts, filter, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, nullptr, ix->vec_ab.p,
-                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
+                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified, tcp ? &ix->vec_tmap128 : nullptr);
 }
 
 int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, int32_t k, void* stream, int32_t* out_docs,
@@ -1521,7 +1524,7 @@ int nrtgpu_search_knn_timed(nrtgpu_index* ix, const float* queries, int32_t nq, 
   return knn_search_host(ix->vectors.p, ix->vec_norm2.p, ix->vec_docs.p, ix->vec_count, ix->vec_dims, ix->vec_sim | (ix->vec_is_byte ? kKnnByteFlag : 0),
                          ix->doc_base, ix->n_docs, queries, nq, k, nullptr, nullptr, (cudaStream_t)stream, out_docs,
                          out_scores, out_counts, tcp ? ix->vec_bf16.p : nullptr, tcp ? &ix->vec_tmap : nullptr, stage_ms, ix->vec_ab.p,
-                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified);
+                         &ix->knn_scratch, ix->live_bits.p, ix->vec_dmax, &ix->knn_last_uncertified, tcp ? &ix->vec_tmap128 : nullptr);
 }
 
 int32_t nrtgpu_knn_last_uncertified(const nrtgpu_index* ix) { return ix ? ix->knn_last_uncertified : 0; }
