@@ -95,6 +95,11 @@ typedef struct {
   int32_t vec_element_type;         /* NRTGPU_VEC_FLOAT32 (FloatVectorFieldDef) or NRTGPU_VEC_INT8 (ByteVectorFieldDef: scores by
                                        VectorFieldDef.java:870-881, i.e. DOT_PRODUCT = 0.5 + dot / (dims * 2^15); queries are passed
                                        as floats holding the byte values) */
+  const int64_t* const* column_offsets; /* NULL, or [n_columns]: a non-NULL entry makes column c MULTI-valued (SORTED_NUMERIC doc
+                                       values, reference NumberFieldDef.java multiValued): int64[n_docs+1] offsets into columns[c],
+                                       which then holds the flattened values, ascending within a doc. A range clause matches a doc
+                                       when ANY of its values lies in [lo, hi] (SortedNumericDocValuesRangeQuery). Sorting, terms /
+                                       min / max / sum collectors and fetch on such a column answer NRTGPU_ERR_UNSUPPORTED. */
 } nrtgpu_shard_desc;
 
 int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* desc, nrtgpu_index** out);

@@ -52,7 +52,7 @@ class ShardDesc(C.Structure):
         ("n_columns", C.c_int32), ("columns", C.POINTER(i64p)), ("column_has", C.POINTER(u8p)),
         ("live_docs", u8p),
         ("vec_dims", C.c_int32), ("vec_similarity", C.c_int32), ("vec_count", C.c_int32),
-        ("vectors", C.c_void_p), ("vec_docs", i32p), ("vec_element_type", C.c_int32),
+        ("vectors", C.c_void_p), ("vec_docs", i32p), ("vec_element_type", C.c_int32), ("column_offsets", C.POINTER(i64p)),
     ]
 
 

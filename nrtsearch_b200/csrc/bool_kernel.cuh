@@ -83,6 +83,8 @@ struct DevIndexView {
   const int64_t* const* col64;   // [n_columns] (NULL if stored as int32)
   const int32_t* const* col32;   // [n_columns] (NULL if stored as int64)
   const uint8_t* const* col_has; // [n_columns] (NULL = all)
+  const int64_t* const* colmv_off;  // [n_columns] multi-valued columns (SORTED_NUMERIC): doc d holds colmv_val[c][off[d] .. off[d + 1]),
+  const int64_t* const* colmv_val;  //              ascending; NULL entry = single-valued column
   const uint32_t* live_bits;     // bitmap or NULL
   const uint32_t* gran_tab;      // [n_rows][n_gran + 1] postings of the term below each stream-kernel granule (skip data)
   int32_t n_gran;
@@ -106,6 +108,22 @@ struct BoolLaunch {
   uint64_t* slice_keys;        // [nq][n_slices][top_k]
   int32_t* slice_cnt;          // [nq][n_slices]
 };
+
+// numeric range clause on one doc (IndexOrDocValuesQuery's doc-values side, reference IntFieldDef.java:124-158 inclusive
+// bounds): single-valued column = the value is in [lo, hi]; multi-valued (SortedNumericDocValuesRangeQuery) = ANY value is
+__device__ __forceinline__ bool range_matches(const DevIndexView& ix, int col, int32_t doc, int64_t lo, int64_t hi) {
+  const int64_t* off = ix.colmv_off ? ix.colmv_off[col] : nullptr;
+  if (off) {
+    const int64_t* v = ix.colmv_val[col];
+    int64_t a = off[doc], b = off[doc + 1];
+    while (a < b) { const int64_t m = (a + b) >> 1; if (v[m] < lo) a = m + 1; else b = m; }   // values of a doc are sorted
+    return a < off[doc + 1] && v[a] <= hi;
+  }
+  const uint8_t* has = ix.col_has[col];
+  if (has && !has[doc]) return false;
+  const int64_t x = ix.col32[col] ? (int64_t)__ldg(ix.col32[col] + doc) : __ldg(ix.col64[col] + doc);
+  return x >= lo && x <= hi;
+}
 
 template <typename SlotT>
 struct SlotTraits;
@@ -172,12 +190,7 @@ __device__ __forceinline__ bool evaluate_doc(const DevIndexView& ix, const BoolS
         s = bm25_score(c.weight, f, sm.cache[c.slot][nb]);
       }
     } else if (c.kind == NRTGPU_RANGE_I64) {
-      const uint8_t* has = ix.col_has[c.col];
-      present = !has || has[doc];
-      if (present) {
-        int64_t v = ix.col32[c.col] ? (int64_t)ix.col32[c.col][doc] : ix.col64[c.col][doc];
-        present = (v >= c.lo) && (v <= c.hi);
-      }
+      present = range_matches(ix, c.col, doc, c.lo, c.hi);
       s = c.weight;
     } else {
       present = true;

@@ -48,12 +48,7 @@ __device__ __forceinline__ bool eval_query_on_doc(const DevIndexView& ix, const 
         s = bm25_score(c.weight, f, ix.caches[c.field * 256 + nb]);
       }
     } else if (c.kind == NRTGPU_RANGE_I64) {
-      const uint8_t* has = ix.col_has[c.col];
-      present = !has || has[doc];
-      if (present) {
-        const int64_t v = ix.col32[c.col] ? (int64_t)ix.col32[c.col][doc] : ix.col64[c.col][doc];
-        present = (v >= c.lo) && (v <= c.hi);
-      }
+      present = range_matches(ix, c.col, doc, c.lo, c.hi);
       s = c.weight;
     } else {
       present = true;

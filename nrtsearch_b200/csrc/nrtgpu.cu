@@ -179,6 +179,9 @@ struct nrtgpu_index {
   DevBuf<const int64_t*> col64_ptrs;
   DevBuf<const int32_t*> col32_ptrs;
   DevBuf<const uint8_t*> col_has_ptrs;
+  std::vector<std::unique_ptr<DevBuf<int64_t>>> colmv_off;   // multi-valued columns: per-doc offsets (values sit in col64)
+  DevBuf<const int64_t*> colmv_off_ptrs, colmv_val_ptrs;
+  std::vector<uint8_t> col_multi;                            // [n_columns] 1 = multi-valued
   DevBuf<uint32_t> live_bits;
   // vectors
   int32_t vec_dims = 0, vec_sim = 0, vec_count = 0;
@@ -210,6 +213,7 @@ struct nrtgpu_index {
     v.exc_pos = exc_pos.p; v.exc_freq = exc_freq.p; v.n_exc = (int32_t)exc_pos.n;
     v.norms = norms_ptrs.p; v.caches = caches.p;
     v.col64 = col64_ptrs.p; v.col32 = col32_ptrs.p; v.col_has = col_has_ptrs.p;
+    v.colmv_off = colmv_off_ptrs.p; v.colmv_val = colmv_val_ptrs.p;
     v.live_bits = live_bits.p;
     v.dense_tf = dense_tf.p; v.dense_stride = dense_stride; v.dense_tf2 = dense_tf2.p;
     v.gran_tab = gran_tab.p; v.n_gran = gran_n;
@@ -391,6 +395,23 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     ix->term_field[t] = f;
     ix->term_df[t] = d->term_df ? d->term_df[t] : len;
   }
+  if (d->n_terms > 0 && d->term_off[0] != 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: term_off[0] must be 0");
+  if (P > 0 && (!d->post_docs || !d->post_freqs)) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL postings");
+  // every list strictly ascending and inside [0, n_docs): the kernels binary-search the lists and index per-doc arrays with them
+  for (int t = 0; t < d->n_terms; ++t) {
+    int32_t prev = -1;
+    for (int64_t p = d->term_off[t]; p < d->term_off[t + 1]; ++p) {
+      const int32_t doc = d->post_docs[p];
+      if (doc <= prev || doc >= d->n_docs) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: post_docs must be strictly ascending per term and < n_docs");
+      prev = doc;
+    }
+  }
+  if (d->vec_dims < 0 || d->vec_count < 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: negative vector size");
+  if (d->vec_dims > 0 && d->vec_count > 0) {
+    if (!d->vec_docs && d->vec_count > d->n_docs) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: vec_count > n_docs with an identity ord -> doc map");
+    if (d->vec_docs) for (int32_t i = 0; i < d->vec_count; ++i)
+      if (d->vec_docs[i] < 0 || d->vec_docs[i] >= d->n_docs) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: vec_docs out of range");
+  }
   ix->field_doc_count.assign(d->field_doc_count, d->field_doc_count + d->n_fields);
   ix->field_sum_ttf.assign(d->field_sum_ttf, d->field_sum_ttf + d->n_fields);
   // postings
@@ -501,12 +522,29 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     std::vector<const int64_t*> p64((size_t)d->n_columns, nullptr);
     std::vector<const int32_t*> p32((size_t)d->n_columns, nullptr);
     std::vector<const uint8_t*> ph((size_t)d->n_columns, nullptr);
+    std::vector<const int64_t*> pmo((size_t)d->n_columns, nullptr), pmv((size_t)d->n_columns, nullptr);
+    ix->col_multi.assign((size_t)d->n_columns, 0);
     for (int c = 0; c < d->n_columns; ++c) {
       ix->col64.emplace_back(new DevBuf<int64_t>);
       ix->col32.emplace_back(new DevBuf<int32_t>);
       ix->col_has.emplace_back(new DevBuf<uint8_t>);
+      ix->colmv_off.emplace_back(new DevBuf<int64_t>);
       const int64_t* h = d->columns[c];
       if (!h) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: NULL column");
+      const int64_t* mo = d->column_offsets ? d->column_offsets[c] : nullptr;
+      if (mo) {   // SORTED_NUMERIC: CSR of values per doc
+        if (mo[0] != 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: column_offsets[c][0] must be 0");
+        for (int32_t i = 0; i < d->n_docs; ++i) {
+          if (mo[i + 1] < mo[i]) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: column_offsets must be non-decreasing");
+          for (int64_t p = mo[i] + 1; p < mo[i + 1]; ++p)
+            if (h[p] < h[p - 1]) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_index_build: the values of a doc must be ascending (SortedNumericDocValues)");
+        }
+        ix->col_multi[(size_t)c] = 1;
+        if ((rc = ix->colmv_off.back()->upload(mo, (size_t)d->n_docs + 1))) return rc;
+        if ((rc = ix->col64.back()->upload(h, (size_t)std::max<int64_t>(mo[d->n_docs], 1)))) return rc;
+        pmo[c] = ix->colmv_off.back()->p; pmv[c] = ix->col64.back()->p;
+        continue;
+      }
       bool fits = true;
       for (int32_t i = 0; i < d->n_docs; ++i) if (h[i] < INT32_MIN || h[i] > INT32_MAX) { fits = false; break; }
       if (fits) {
@@ -528,6 +566,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
       for (int c = 0; c < d->n_columns; ++c) {
         ix->col_code.emplace_back(new DevBuf<uint32_t>);
         ix->col_distinct.emplace_back(new DevBuf<uint64_t>);
+        if (ix->col_multi[(size_t)c]) { ix->col_n_distinct.push_back(0); continue; }   // no sort / terms on a multi-valued column
         if ((rc = ix->col_code.back()->alloc((size_t)d->n_docs))) return rc;
         if ((rc = ix->col_distinct.back()->alloc((size_t)d->n_docs))) return rc;
         NRT_CUDA_TRY(cudaMemset(ix->col_code.back()->p, 0, ix->col_code.back()->bytes()));
@@ -540,6 +579,8 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
     if ((rc = ix->col64_ptrs.upload(p64.data(), p64.size()))) return rc;
     if ((rc = ix->col32_ptrs.upload(p32.data(), p32.size()))) return rc;
     if ((rc = ix->col_has_ptrs.upload(ph.data(), ph.size()))) return rc;
+    if ((rc = ix->colmv_off_ptrs.upload(pmo.data(), pmo.size()))) return rc;
+    if ((rc = ix->colmv_val_ptrs.upload(pmv.data(), pmv.size()))) return rc;
   }
   // index-time impacts (list-wide score bounds for MAXSCORE)
   if ((rc = compute_term_max_x(ix.get()))) return rc;
@@ -589,6 +630,7 @@ int nrtgpu_index_build(nrtgpu_ctx* ctx, const nrtgpu_shard_desc* d, nrtgpu_index
   for (auto& b : ix->col64) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col32) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col_has) ix->device_bytes += (int64_t)b->bytes();
+  for (auto& b : ix->colmv_off) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col_code) ix->device_bytes += (int64_t)b->bytes();
   for (auto& b : ix->col_distinct) ix->device_bytes += (int64_t)b->bytes();
   NRT_CUDA_TRY(cudaDeviceSynchronize());
@@ -646,6 +688,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
       if (a.kind < NRTGPU_AGG_TERMS || a.kind > NRTGPU_AGG_SUM) NRT_FAIL(NRTGPU_ERR_INVALID, "bad aggregation kind");
       if (!ix || a.column < 0 || a.column >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "aggregation column out of range");
       if (a.value_type < 0 || a.value_type > 2) NRT_FAIL(NRTGPU_ERR_INVALID, "bad aggregation value_type");
+      if (ix->col_multi[(size_t)a.column]) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "aggregation on a multi-valued column");
       if (a.kind == NRTGPU_AGG_TERMS) {
         if (a.size <= 0 || a.size > kAggChunk) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "terms aggregation: size must be in [1, 2048]");
         const int64_t cells = (int64_t)nq * ix->col_n_distinct[(size_t)a.column];
@@ -662,6 +705,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     if (sort->kind != NRTGPU_SORT_COLUMN && sort->kind != NRTGPU_SORT_DOCID) NRT_FAIL(NRTGPU_ERR_INVALID, "bad sort kind");
     if (sort->kind == NRTGPU_SORT_COLUMN && (sort->column < 0 || sort->column >= ix->n_columns))
       NRT_FAIL(NRTGPU_ERR_INVALID, "sort column out of range (field does not support sorting: no doc values)");
+    if (sort->kind == NRTGPU_SORT_COLUMN && ix->col_multi[(size_t)sort->column]) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sort on a multi-valued column");
     if (ix->ctx->engine_stream) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sorted search needs the probe engine");
     total_hits_threshold = INT32_MAX;   // every match is visited: exact totalHits
   }
@@ -1458,6 +1502,7 @@ int nrtgpu_fetch_columns(nrtgpu_index* ix, const int32_t* col_ids, int32_t n_col
                          void* stream, int64_t* out_values, uint8_t* out_has) {
   if (!ix || !col_ids || !docs || !out_values || !out_has || n_cols <= 0 || n <= 0) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_fetch_columns: bad argument");
   for (int i = 0; i < n_cols; ++i) if (col_ids[i] < 0 || col_ids[i] >= ix->n_columns) NRT_FAIL(NRTGPU_ERR_INVALID, "nrtgpu_fetch_columns: column out of range");
+  for (int i = 0; i < n_cols; ++i) if (ix->col_multi[(size_t)col_ids[i]]) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "nrtgpu_fetch_columns: multi-valued column");
   NRT_CUDA_TRY(cudaSetDevice(ix->ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> g(ix->fetch_mu);

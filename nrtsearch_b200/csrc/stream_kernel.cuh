@@ -195,12 +195,7 @@ __device__ __noinline__ bool evaluate_doc_generic(const StreamLaunch& L, const S
         s = (b <= (uint32_t)kTfTab) ? sm.tbl[c.slot][b][nb] : term_score_slow(L, c, doc, b, nb);
       }
     } else if (c.kind == NRTGPU_RANGE_I64) {
-      const uint8_t* has = L.ix.col_has[c.col];
-      present = !has || has[doc];
-      if (present) {
-        int64_t v = L.ix.col32[c.col] ? (int64_t)__ldg(L.ix.col32[c.col] + doc) : __ldg(L.ix.col64[c.col] + doc);
-        present = (v >= c.lo) && (v <= c.hi);
-      }
+      present = range_matches(L.ix, c.col, doc, c.lo, c.hi);
       s = c.weight;
     } else {
       present = true;

@@ -43,6 +43,9 @@ class HostShard:
     term_df: Optional[np.ndarray] = None      # int64[n_terms] index-wide docFreq
     columns: List[np.ndarray] = field(default_factory=list)        # int64[n_docs] each
     column_has: List[Optional[np.ndarray]] = field(default_factory=list)
+    # multi-valued columns (SORTED_NUMERIC): column_offsets[i] = int64[n_docs+1], columns[i] = the flattened values
+    # (ascending within a doc); None / missing entry = single-valued column
+    column_offsets: List[Optional[np.ndarray]] = field(default_factory=list)
     live_docs: Optional[np.ndarray] = None    # uint8[n_docs]
     vectors: Optional[np.ndarray] = None      # float32[n_vec, dims]
     vec_similarity: int = SIM_COSINE
@@ -51,6 +54,9 @@ class HostShard:
     @property
     def n_terms(self) -> int:
         return len(self.term_off) - 1
+
+    def _mv(self, i: int) -> Optional[np.ndarray]:
+        return self.column_offsets[i] if i < len(self.column_offsets) else None
 
     def df(self, term: int) -> int:
         return int(self.term_off[term + 1] - self.term_off[term])
@@ -83,7 +89,10 @@ class HostShard:
             fields=[TextField(None if f.norms is None else np.ascontiguousarray(f.norms[lo:hi]), f.doc_count,
                               f.sum_total_term_freq, f.k1, f.b) for f in self.fields],
             term_field=self.term_field, term_df=np.ascontiguousarray(global_df.astype(np.int64)),
-            columns=[np.ascontiguousarray(c[lo:hi]) for c in self.columns],
+            columns=[np.ascontiguousarray(c[lo:hi]) if self._mv(i) is None else
+                     np.ascontiguousarray(c[int(self._mv(i)[lo]):int(self._mv(i)[hi])]) for i, c in enumerate(self.columns)],
+            column_offsets=[None if self._mv(i) is None else np.ascontiguousarray(self._mv(i)[lo:hi + 1] - self._mv(i)[lo])
+                            for i in range(len(self.columns))],
             column_has=[None if h is None else np.ascontiguousarray(h[lo:hi]) for h in self.column_has],
             live_docs=None if self.live_docs is None else np.ascontiguousarray(self.live_docs[lo:hi]),
             vectors=sub_vec, vec_similarity=self.vec_similarity, vec_docs=sub_vdocs)
@@ -135,9 +144,13 @@ class PinnedDesc:
             cols[i] = _ptr(arr(c, np.int64), N.i64p)
             h = sh.column_has[i] if i < len(sh.column_has) else None
             has[i] = _ptr(arr(h, np.uint8), N.u8p)
-        self.keep += [cols, has]
+        offs = (N.i64p * max(nc, 1))()
+        for i in range(nc):
+            offs[i] = _ptr(arr(sh._mv(i), np.int64), N.i64p)
+        self.keep += [cols, has, offs]
         d.columns = C.cast(cols, C.POINTER(N.i64p))
         d.column_has = C.cast(has, C.POINTER(N.u8p))
+        d.column_offsets = C.cast(offs, C.POINTER(N.i64p))
         d.live_docs = _ptr(arr(sh.live_docs, np.uint8), N.u8p)
         if sh.vectors is not None and len(sh.vectors):
             byte_field = np.asarray(sh.vectors).dtype == np.int8   # ByteVectorFieldDef

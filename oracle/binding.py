@@ -35,7 +35,7 @@ class OrcIndex(C.Structure):
         ("n_fields", C.c_int32), ("norms", C.POINTER(u8p)), ("field_doc_count", i64p), ("field_sum_ttf", i64p),
         ("field_k1", f32p), ("field_b", f32p),
         ("n_columns", C.c_int32), ("columns", C.POINTER(i64p)), ("column_has", C.POINTER(u8p)),
-        ("live_docs", u8p), ("term_max_x", f32p),
+        ("live_docs", u8p), ("term_max_x", f32p), ("column_offsets", C.POINTER(i64p)),
     ]
 
 
@@ -184,9 +184,15 @@ class OracleIndex:
             cols[i] = ptr(arr(c, np.int64), i64p)
             h = sh.column_has[i] if i < len(sh.column_has) else None
             has[i] = ptr(arr(h, np.uint8), u8p)
-        self.keep += [cols, has]
+        offs = (i64p * max(nc, 1))()
+        mv = getattr(sh, "column_offsets", None) or []
+        for i in range(nc):
+            o = mv[i] if i < len(mv) else None
+            offs[i] = ptr(arr(o, np.int64), i64p)
+        self.keep += [cols, has, offs]
         ix.columns = C.cast(cols, C.POINTER(i64p))
         ix.column_has = C.cast(has, C.POINTER(u8p))
+        ix.column_offsets = C.cast(offs, C.POINTER(i64p))
         ix.live_docs = ptr(arr(sh.live_docs, np.uint8), u8p)
         ix.term_max_x = C.cast(None, f32p)
         self.ix = ix

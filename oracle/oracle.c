@@ -159,9 +159,21 @@ typedef struct {
   float weight; const float* cache; const uint8_t* norms;
   float max_score; /* upper bound over the whole list (pruned mode) */
   /* RANGE */
-  const int64_t* col; const uint8_t* has; int64_t lo, hi;
+  const int64_t* col; const uint8_t* has; const int64_t* mv_off; int64_t lo, hi;
   float const_score;
 } cl_t;
+
+/* numeric range on one doc. Single-valued column: the value lies in [lo, hi] (IntFieldDef.java:124-158, inclusive
+ * bounds after the exclusive ones were stepped). Multi-valued column (SORTED_NUMERIC; Lucene
+ * SortedNumericDocValuesRangeQuery): ANY of the doc's values does; a doc with no value never matches. */
+static int range_clause_matches(const cl_t* c, int64_t d) {
+  if (c->mv_off) {
+    for (int64_t p = c->mv_off[d]; p < c->mv_off[d + 1]; ++p) if (c->col[p] >= c->lo && c->col[p] <= c->hi) return 1;
+    return 0;
+  }
+  if (c->has && !c->has[d]) return 0;
+  return c->col[d] >= c->lo && c->col[d] <= c->hi;
+}
 
 static inline float clause_term_score(const cl_t* c, int32_t doc, int32_t freq) {
   uint8_t nb = c->norms ? c->norms[doc] : 1;
@@ -220,6 +232,7 @@ static int build_clauses(const orc_index* ix, const orc_clause* cls, const orc_q
     } else if (c->kind == ORC_RANGE_I64) {
       if (c->id < 0 || c->id >= ix->n_columns) return -1;
       o->col = ix->columns[c->id]; o->has = ix->column_has ? ix->column_has[c->id] : NULL;
+      o->mv_off = ix->column_offsets ? ix->column_offsets[c->id] : NULL;
       o->lo = c->lo; o->hi = c->hi; o->const_score = c->boost;
     } else if (c->kind == ORC_MATCH_ALL) {
       o->const_score = c->boost;
@@ -275,9 +288,7 @@ static void search_one_exhaustive(const orc_index* ix, cl_t* cl, int ncl, int ms
       } else if (c->kind == ORC_RANGE_I64) {
         for (int j = 0; j < wn; ++j) {
           int64_t d = base + j;
-          if (c->has && !c->has[d]) continue;
-          int64_t v = c->col[d];
-          if (v >= c->lo && v <= c->hi) window_apply(w, j, c->occur, c->const_score);
+          if (range_clause_matches(c, d)) window_apply(w, j, c->occur, c->const_score);
         }
       } else {
         for (int j = 0; j < wn; ++j) window_apply(w, j, c->occur, c->const_score);
@@ -522,7 +533,7 @@ int orc_score_docs(const orc_index* ix, const orc_clause* clauses, const orc_que
           int64_t p = lower_bound_i32(c->docs, 0, c->n, (int32_t)d);
           if (p < c->n && c->docs[p] == (int32_t)d) { present = 1; if (c->occur == ORC_MUST || c->occur == ORC_SHOULD) s = clause_term_score(c, (int32_t)d, c->freqs[p]); }
         } else if (c->kind == ORC_RANGE_I64) {
-          if (!(c->has && !c->has[d])) { int64_t v = c->col[d]; present = v >= c->lo && v <= c->hi; }
+          present = range_clause_matches(c, d);
           s = c->const_score;
         } else { present = 1; s = c->const_score; }
         if (!present) continue;

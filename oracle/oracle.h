@@ -80,6 +80,8 @@ typedef struct {
   const uint8_t* const* column_has;  /* [n_columns] -> [n_docs] 0/1 or NULL = all docs have a value */
   const uint8_t* live_docs;          /* [n_docs] 0/1 or NULL = all live */
   const float* term_max_x;           /* [n_terms] index-time impact max(freq*cache[norm]) or NULL */
+  const int64_t* const* column_offsets; /* NULL, or [n_columns] -> int64[n_docs+1] for a MULTI-valued column (SORTED_NUMERIC):
+                                          doc d holds columns[c][off[d] .. off[d+1]); NULL entry = single valued */
 } orc_index;
 
 /* fills term_max_x[n_terms] (index-time impacts; call once after the index arrays are set) */

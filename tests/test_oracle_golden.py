@@ -117,6 +117,22 @@ def test_range_query_hit_set():
         assert float(s[0, 0]) == 1.0   # constant-score query
 
 
+def test_multivalued_range_matches_any_value():
+    # IntFieldDefTest's "multi_stored" docs (:131-141): doc 1 holds {Integer.MIN_VALUE, 15}, doc 2 holds {1, 15}; a third doc
+    # has no value. SortedNumericDocValuesRangeQuery: a doc matches when ANY value is inside the inclusive range.
+    imin = -(2**31)
+    vals = np.array([imin, 15, 1, 15], np.int64)
+    off = np.array([0, 2, 4, 4], np.int64)
+    sh, vocab = shard_from_token_docs([["a".split(), "a".split(), "a".split()]], columns=[vals])
+    sh.column_offsets = [off]
+    oix = oracle.OracleIndex(sh)
+    for lo, hi, docs in ((15, 15, [0, 1]), (0, 10, [1]), (imin, imin, [0]), (2, 14, []), (16, 2**31 - 1, []), (imin, 2**31 - 1, [0, 1])):
+        d, s, c, t, r = oracle.search(oix, [(1, 1, 0, 1.0, lo, hi)], [(0, 1, 0, 0, 0, 0.0)], 10)
+        assert list(d[0, :c[0]]) == docs and t[0] == len(docs), (lo, hi)
+    sub = sh.doc_range(1, 3)     # a doc-range shard re-bases the offsets
+    assert list(sub.column_offsets[0]) == [0, 2, 2] and list(sub.columns[0]) == [1, 15]
+
+
 def test_match_all_scores_one():
     # MultiFunctionScoreQueryTest.testNoFunctionsMatchAll (:117-126): every doc, score 1.0
     sh, vocab = shard_from_token_docs([["a b".split(), "c".split(), "d".split(), "e".split()]])
