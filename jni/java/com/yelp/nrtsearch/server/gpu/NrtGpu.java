@@ -35,4 +35,40 @@ public final class NrtGpu {
   public static native int rescoreCombine(
       long ctx, int nq, int nHits, ByteBuffer counts, ByteBuffer docs, ByteBuffer scores,
       ByteBuffer secondMatches, ByteBuffer secondScores, double queryWeight, double rescoreWeight);
+
+  /** limits = nrtgpu_search_limits or null; outHitTimeout / outTerminatedEarly may be null. */
+  public static native int searchBoolEx(
+      long index, ByteBuffer clauses, int nClauses, ByteBuffer queries, int nq, int topK,
+      int totalHitsThreshold, int flags, ByteBuffer limits, ByteBuffer outDocs,
+      ByteBuffer outScores, ByteBuffer outCounts, ByteBuffer outTotalHits, ByteBuffer outRelation,
+      ByteBuffer outHitTimeout, ByteBuffer outTerminatedEarly);
+
+  public static native int searchSorted(
+      long index, ByteBuffer clauses, int nClauses, ByteBuffer queries, int nq, int topK, int flags,
+      ByteBuffer sort, ByteBuffer limits, ByteBuffer outDocs, ByteBuffer outSortValues,
+      ByteBuffer outCounts, ByteBuffer outTotalHits, ByteBuffer outRelation,
+      ByteBuffer outHitTimeout, ByteBuffer outTerminatedEarly);
+
+  public static native int scoreDocs(
+      long index, ByteBuffer clauses, int nClauses, ByteBuffer queries, int nq, int nHits,
+      ByteBuffer docs, ByteBuffer counts, ByteBuffer outMatches, ByteBuffer outScores);
+
+  public static native int fetchColumns(
+      long index, ByteBuffer colIds, int nCols, ByteBuffer docs, int n, ByteBuffer outValues,
+      ByteBuffer outHas);
+
+  public static native int indexSetLiveDocs(long index, ByteBuffer liveDocs);
+
+  public static native int indexUpdateStats(
+      long index, ByteBuffer termDf, ByteBuffer fieldDocCount, ByteBuffer fieldSumTtf);
+
+  public static native long batcherCreate(long index, int maxBatch, int maxWaitUs);
+
+  /** Blocks until the batch this request rode in is back; diag = nrtgpu_diagnostics (24 bytes) or null. */
+  public static native int batcherSubmit(
+      long batcher, ByteBuffer clauses, int nClauses, int minShouldMatch, int topK,
+      int totalHitsThreshold, ByteBuffer outDocs, ByteBuffer outScores, ByteBuffer outCount,
+      ByteBuffer outTotalHits, ByteBuffer outRelation, ByteBuffer diag);
+
+  public static native void batcherClose(long batcher);
 }

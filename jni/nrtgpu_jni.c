@@ -15,6 +15,7 @@ static jint fail(JNIEnv* env, int rc) {
   if (rc == NRTGPU_OK) return 0;
   const char* cls = rc == NRTGPU_ERR_INVALID ? "java/lang/IllegalArgumentException"
                   : rc == NRTGPU_ERR_UNSUPPORTED ? "java/lang/UnsupportedOperationException"
+                  : rc == NRTGPU_ERR_TIMEOUT ? "com/yelp/nrtsearch/server/search/collectors/CollectionTimeoutException"
                   : "java/lang/RuntimeException";   /* -> Status.INTERNAL in SearchHandler.handle (:136-145) */
   (*env)->ThrowNew(env, (*env)->FindClass(env, cls), nrtgpu_last_error());
   return rc;
@@ -68,4 +69,70 @@ JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_rescoreCombine(
                                           (int32_t*)ADDR(env, docs), (float*)ADDR(env, scores),
                                           (const uint8_t*)ADDR(env, secondMatches), (const float*)ADDR(env, secondScores),
                                           queryWeight, rescoreWeight));
+}
+
+/* limits: a direct ByteBuffer laid out as nrtgpu_search_limits (or null); sort: nrtgpu_sort */
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_searchBoolEx(
+    JNIEnv* env, jclass c, jlong ix, jobject clauses, jint nClauses, jobject queries, jint nq, jint topK,
+    jint totalHitsThreshold, jint flags, jobject limits, jobject outDocs, jobject outScores, jobject outCounts,
+    jobject outTotalHits, jobject outRelation, jobject outHitTimeout, jobject outTerminatedEarly) {
+  return fail(env, nrtgpu_search_bool_ex((nrtgpu_index*)(intptr_t)ix, (const nrtgpu_clause*)ADDR(env, clauses), nClauses,
+                                         (const nrtgpu_query*)ADDR(env, queries), nq, topK, totalHitsThreshold, flags,
+                                         (const nrtgpu_search_limits*)ADDR(env, limits), NULL, (int32_t*)ADDR(env, outDocs),
+                                         (float*)ADDR(env, outScores), (int32_t*)ADDR(env, outCounts),
+                                         (int64_t*)ADDR(env, outTotalHits), (uint8_t*)ADDR(env, outRelation),
+                                         (uint8_t*)ADDR(env, outHitTimeout), (uint8_t*)ADDR(env, outTerminatedEarly)));
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_searchSorted(
+    JNIEnv* env, jclass c, jlong ix, jobject clauses, jint nClauses, jobject queries, jint nq, jint topK, jint flags,
+    jobject sort, jobject limits, jobject outDocs, jobject outSortValues, jobject outCounts, jobject outTotalHits,
+    jobject outRelation, jobject outHitTimeout, jobject outTerminatedEarly) {
+  return fail(env, nrtgpu_search_sorted((nrtgpu_index*)(intptr_t)ix, (const nrtgpu_clause*)ADDR(env, clauses), nClauses,
+                                        (const nrtgpu_query*)ADDR(env, queries), nq, topK, flags,
+                                        (const nrtgpu_sort*)ADDR(env, sort), (const nrtgpu_search_limits*)ADDR(env, limits), NULL,
+                                        (int32_t*)ADDR(env, outDocs), (int64_t*)ADDR(env, outSortValues),
+                                        (int32_t*)ADDR(env, outCounts), (int64_t*)ADDR(env, outTotalHits),
+                                        (uint8_t*)ADDR(env, outRelation), (uint8_t*)ADDR(env, outHitTimeout),
+                                        (uint8_t*)ADDR(env, outTerminatedEarly)));
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_scoreDocs(
+    JNIEnv* env, jclass c, jlong ix, jobject clauses, jint nClauses, jobject queries, jint nq, jint nHits, jobject docs,
+    jobject counts, jobject outMatches, jobject outScores) {
+  return fail(env, nrtgpu_score_docs((nrtgpu_index*)(intptr_t)ix, (const nrtgpu_clause*)ADDR(env, clauses), nClauses,
+                                     (const nrtgpu_query*)ADDR(env, queries), nq, nHits, (const int32_t*)ADDR(env, docs),
+                                     (const int32_t*)ADDR(env, counts), NULL, (uint8_t*)ADDR(env, outMatches),
+                                     (float*)ADDR(env, outScores)));
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_fetchColumns(
+    JNIEnv* env, jclass c, jlong ix, jobject colIds, jint nCols, jobject docs, jint n, jobject outValues, jobject outHas) {
+  return fail(env, nrtgpu_fetch_columns((nrtgpu_index*)(intptr_t)ix, (const int32_t*)ADDR(env, colIds), nCols,
+                                        (const int32_t*)ADDR(env, docs), n, NULL, (int64_t*)ADDR(env, outValues),
+                                        (uint8_t*)ADDR(env, outHas)));
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_indexSetLiveDocs(JNIEnv* env, jclass c, jlong ix, jobject live) {
+  return fail(env, nrtgpu_index_set_live_docs((nrtgpu_index*)(intptr_t)ix, (const uint8_t*)ADDR(env, live)));
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_indexUpdateStats(
+    JNIEnv* env, jclass c, jlong ix, jobject termDf, jobject fieldDocCount, jobject fieldSumTtf) {
+  return fail(env, nrtgpu_index_update_stats((nrtgpu_index*)(intptr_t)ix, (const int64_t*)ADDR(env, termDf),
+                                             (const int64_t*)ADDR(env, fieldDocCount), (const int64_t*)ADDR(env, fieldSumTtf)));
+}
+/* micro-batcher: one per searcher version; submit blocks the calling gRPC handler thread until its batch is back.
+ * diag: 24-byte direct buffer laid out as nrtgpu_diagnostics, or null */
+JNIEXPORT jlong JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_batcherCreate(JNIEnv* env, jclass c, jlong ix, jint maxBatch, jint maxWaitUs) {
+  nrtgpu_batcher* b = NULL;
+  if (fail(env, nrtgpu_batcher_create((nrtgpu_index*)(intptr_t)ix, maxBatch, maxWaitUs, &b))) return 0;
+  return (jlong)(intptr_t)b;
+}
+JNIEXPORT jint JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_batcherSubmit(
+    JNIEnv* env, jclass c, jlong b, jobject clauses, jint nClauses, jint minShouldMatch, jint topK, jint totalHitsThreshold,
+    jobject outDocs, jobject outScores, jobject outCount, jobject outTotalHits, jobject outRelation, jobject diag) {
+  return fail(env, nrtgpu_batcher_submit((nrtgpu_batcher*)(intptr_t)b, (const nrtgpu_clause*)ADDR(env, clauses), nClauses,
+                                         minShouldMatch, topK, totalHitsThreshold, (int32_t*)ADDR(env, outDocs),
+                                         (float*)ADDR(env, outScores), (int32_t*)ADDR(env, outCount),
+                                         (int64_t*)ADDR(env, outTotalHits), (uint8_t*)ADDR(env, outRelation),
+                                         (nrtgpu_diagnostics*)ADDR(env, diag)));
+}
+JNIEXPORT void JNICALL Java_com_yelp_nrtsearch_server_gpu_NrtGpu_batcherClose(JNIEnv* env, jclass c, jlong b) {
+  nrtgpu_batcher_close((nrtgpu_batcher*)(intptr_t)b);
 }
