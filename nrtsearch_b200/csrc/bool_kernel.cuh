@@ -430,29 +430,44 @@ constexpr int kMergeCap = 4096;
 
 __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch M) {
   __shared__ uint64_t keys[kMergeCap];
+  __shared__ int32_t s_cnt[kMergeThreads];
+  __shared__ int32_t s_nz[kMergeThreads];   // the non-empty lists of a chunk of list counts
+  __shared__ int32_t s_nnz;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
-  int have = 0;  // sorted best-so-far in keys[0..have)
-  int l = 0;
-  while (l < M.n_lists) {
-    // append as many whole lists as fit
+  int have = 0;        // keys[0..have) hold the best so far
+  bool dirty = false;  // ... unsorted / not yet cut to top_k
+  auto sort_and_cut = [&]() {
+    const int m = next_pow2(have < 2 ? 2 : have);
     __syncthreads();
-    int fill = have;
-    int l_end = l;
-    while (l_end < M.n_lists) {
-      int c = M.slice_cnt[(size_t)q * M.n_lists + l_end];
-      if (fill + c > kMergeCap) break;
-      const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + l_end) * M.top_k;
-      for (int i = tid; i < c; i += kMergeThreads) keys[fill + i] = src[i];
-      fill += c; ++l_end;
-    }
-    l = l_end;
-    int m = next_pow2(fill < 2 ? 2 : fill);
-    for (int i = fill + tid; i < m; i += kMergeThreads) keys[i] = 0ull;
+    for (int i = have + tid; i < m; i += kMergeThreads) keys[i] = 0ull;
     __syncthreads();
     block_bitonic_sort_desc(keys, m);
-    have = fill < M.top_k ? fill : M.top_k;
+    have = have < M.top_k ? have : M.top_k;
+    dirty = false;
+    __syncthreads();
+  };
+  // the list counts are read kMergeThreads at a time (most lists of a query whose work items were not split are empty);
+  // non-empty lists are appended while they fit, the buffer sorted and cut to top_k when the next one does not
+  for (int l0 = 0; l0 < M.n_lists; l0 += kMergeThreads) {
+    __syncthreads();
+    if (tid == 0) s_nnz = 0;
+    __syncthreads();
+    const int l = l0 + tid;
+    const int c = l < M.n_lists ? M.slice_cnt[(size_t)q * M.n_lists + l] : 0;
+    if (c > 0) { const int p = atomicAdd(&s_nnz, 1); s_nz[p] = l; s_cnt[p] = c; }
+    __syncthreads();
+    const int nnz = s_nnz;
+    for (int i0 = 0; i0 < nnz; ++i0) {
+      const int cnt = s_cnt[i0];
+      if (have + cnt > kMergeCap) sort_and_cut();
+      const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
+      for (int i = tid; i < cnt; i += kMergeThreads) keys[have + i] = src[i];
+      have += cnt; dirty = true;
+    }
   }
+  if (dirty) sort_and_cut();
+  if (M.n_lists <= 0) have = 0;
   __syncthreads();
   for (int i = tid; i < have; i += kMergeThreads) {
     uint64_t k = keys[i];

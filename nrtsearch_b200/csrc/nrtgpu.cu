@@ -137,6 +137,8 @@ struct nrtgpu_ctx {
   bool engine_stream = false;   // NRTGPU_ENGINE=stream: round-1 window/stream kernel for every <= 4-term query (A/B runs)
   std::mutex hyb_mu;             // O(k) hybrid stages share one pooled device scratch (no cudaMalloc per call)
   DevBuf<int32_t> hyb_scratch;
+  int64_t item_postings = 32768; // NRTGPU_ITEM_POSTINGS: floor of the postings a (query, slice) may hold before it is split into 2..16 parts
+  int64_t item_share = 12;       // NRTGPU_ITEM_SHARE: ... and it is split when it exceeds 1/share of the postings per resident CTA
   bool order_lpt = false;        // NRTGPU_ORDER=lpt: query-major work order, longest query first
   bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
   bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
@@ -231,7 +233,7 @@ struct nrtgpu_batch {
   // work list layout (<= 4-term batches): [probe simple | probe generic | stream (window kernel: no posting list can lead)]
   int32_t n_probe_simple = 0, n_probe_generic = 0, n_stream = 0;
   bool use_probe = false;
-  DevBuf<uint32_t> sbounds;            // probe kernel: [nq][4][n_slices + 2] slice-boundary posting offsets
+  DevBuf<uint32_t> sbounds;            // probe kernel: [nq][4][n_slices * parts_max + 2] part-boundary posting offsets
   DevBuf<unsigned int> work_counter;   // probe kernel: queue heads [2]
   DevBuf<unsigned long long> probe_stats;
   bool wide_slots = false;
@@ -269,6 +271,7 @@ struct nrtgpu_batch {
   int64_t terminate_after_max_recall = 0;
   std::vector<DevClause> h_dc; std::vector<DevQuery> h_dq; std::vector<int32_t> h_wq, h_ws;   // host copies the async uploads read
   int32_t slice_docs = 0;
+  int32_t parts_max = 1;       // probe kernel: parts a (query, slice) work item may be split into (power of two)
   int64_t threshold = INT32_MAX;
   int32_t n_gran = 0;
   DevBuf<uint64_t> theta;
@@ -348,6 +351,8 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
+  { const char* e = getenv("NRTGPU_ITEM_POSTINGS"); if (e && atoll(e) > 0) c->item_postings = atoll(e); }
+  { const char* e = getenv("NRTGPU_ITEM_SHARE"); if (e && atoll(e) > 0) c->item_share = atoll(e); }
   { const char* e = getenv("NRTGPU_ORDER"); c->order_by_cost = e && (std::strcmp(e, "cost") == 0 || std::strcmp(e, "lpt") == 0); c->order_lpt = e && std::strcmp(e, "lpt") == 0; }
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint32_t>)));
@@ -357,10 +362,10 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(v2::StreamSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(v3::ProbeSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(v3::ProbeSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm3Smem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm2Smem));
@@ -885,15 +890,46 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
       if (has_warm[(size_t)qi]) { wq.push_back(qi); ws.push_back(0 | (1 << 24)); }
     }
   }
-  b->n_lists = b->n_slices + (warm_ok ? 1 : 0);
+  // heavy (query, slice) pairs are split into 2..16 parts of equal granule ranges, so that no single work item is a
+  // large share of the launch (the longest item bounds the kernel time from below: what limits small shards)
+  const int gran_per_slice = (int)(slice_docs / v2::kGran);
+  const int n_gran_h = std::max<int>(1, (int)(((int64_t)ix->n_docs + v2::kGran - 1) / v2::kGran));
+  std::vector<uint8_t> lparts((size_t)nq, 0);
+  int lp_max = 0;
+  if (b->use_probe) {
+    int64_t total_cost = 0;
+    for (int qi : order) total_cost += cost[qi];
+    const int64_t item_max = std::max<int64_t>(ix->ctx->item_postings, total_cost / ((int64_t)v3::kCtasPerSm * ix->ctx->sm_count * ix->ctx->item_share));
+    for (int qi : order) {
+      const int64_t per_slice = cost[qi] / std::max(1, (int)b->n_slices);
+      int lp = 0;
+      while (lp < 4 && (per_slice >> lp) > item_max && (gran_per_slice >> (lp + 1)) >= 8) ++lp;
+      lparts[(size_t)qi] = (uint8_t)lp;
+      lp_max = std::max(lp_max, lp);
+    }
+  }
+  b->parts_max = 1 << lp_max;
+  b->n_lists = b->n_slices * b->parts_max + (warm_ok ? 1 : 0);
+  auto push_items = [&](int qi, int s) {   // the parts of (query, slice) that hold at least one granule
+    const int lp = lparts[(size_t)qi], P = 1 << lp;
+    const int g_count = std::min(gran_per_slice, n_gran_h - s * gran_per_slice);
+    const int fine = (gran_per_slice + b->parts_max - 1) / b->parts_max, kfine = b->parts_max >> lp;   // as the kernel decodes them
+    const bool behind_warm = s == 0 && has_warm[(size_t)qi];
+    for (int p = 0; p < P; ++p) {
+      int lo = std::min(g_count, p * kfine * fine), hi = (p + 1) * kfine >= b->parts_max ? g_count : std::min(g_count, (p + 1) * kfine * fine);
+      if (behind_warm) lo = std::max(lo, std::min(g_count, (int)v2::kWarmGran));
+      if (P > 1 && lo >= hi) continue;
+      wq.push_back(qi); ws.push_back(s | (p << 16) | (lp << 20) | (behind_warm ? (2 << 24) : 0));
+    }
+  };
   int32_t class_end[3] = {0, 0, 0};
   for (int cls = 0; cls < 3; ++cls) {
     if (ix->ctx->order_lpt && b->use_probe) {   // longest query first, its slices together (experiment: NRTGPU_ORDER=lpt)
       for (int qi : order) if (engine_class(qi) == cls)
-        for (int s = 0; s < b->n_slices; ++s) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+        for (int s = 0; s < b->n_slices; ++s) push_items(qi, s);
     } else {
       for (int s = 0; s < b->n_slices; ++s)
-        for (int qi : order) if (engine_class(qi) == cls) { wq.push_back(qi); ws.push_back(s | ((s == 0 && has_warm[(size_t)qi]) ? (2 << 24) : 0)); }
+        for (int qi : order) if (engine_class(qi) == cls) push_items(qi, s);
     }
     class_end[cls] = (int32_t)wq.size();
   }
@@ -942,12 +978,12 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     if (b->n_probe_simple + b->n_probe_generic > 0) {
       // probe kernel: posting offsets of every (query, term slot) at the slice boundaries only (skip data for the long
       // lists, one lower_bound for the short ones); the granule offsets inside a slice are read from gran_tab by the kernel
-      const int64_t total = (int64_t)nq * v3::kT * (b->n_slices + 2);
+      const int64_t total = (int64_t)nq * v3::kT * ((int64_t)b->n_slices * b->parts_max + 2);
       if ((rc = b->sbounds.alloc((size_t)total))) return rc;
       if ((rc = b->work_counter.alloc(2))) return rc;
       v3::SliceBoundsLaunch S;
       S.ix = ix->view(); S.clauses = b->clauses.p; S.queries = b->queries.p; S.nq = nq; S.n_slices = b->n_slices;
-      S.slice_gran = b->slice_docs / v2::kGran; S.n_gran = b->n_gran; S.sbounds = b->sbounds.p;
+      S.slice_gran = b->slice_docs / v2::kGran; S.n_gran = b->n_gran; S.parts_max = b->parts_max; S.sbounds = b->sbounds.p;
       v3::slice_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S);
       NRT_CUDA_TRY(cudaGetLastError());
     }
@@ -1012,7 +1048,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
         v3::ProbeLaunch P;
         P.ix = L.ix; P.clauses = L.clauses; P.queries = L.queries; P.sbounds = b->sbounds.p;
         P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr;
-        P.n_lists = b->n_lists; P.n_slices = b->n_slices; P.top_k = b->top_k; P.slice_docs = b->slice_docs; P.n_gran = b->n_gran;
+        { const char* e = getenv("NRTGPU_KNOCK"); P.knock = e ? atoi(e) : 0; }
+        P.n_lists = b->n_lists; P.parts_max = b->parts_max; P.n_slices = b->n_slices; P.top_k = b->top_k; P.slice_docs = b->slice_docs; P.n_gran = b->n_gran;
         P.threshold = b->threshold; P.pruned = b->pruned.p; P.theta = L.theta; P.total_hits = L.total_hits;
         P.slice_keys = L.slice_keys; P.slice_cnt = L.slice_cnt;
         P.deadline_ns = b->limits_active ? b->deadline_ns : 0; P.clock0 = b->clock0.p; P.timed_out = b->timed_out.p;
@@ -1050,20 +1087,22 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
           NRT_CUDA_TRY(cudaMemsetAsync(b->timed_out.p, 0, b->timed_out.bytes(), st));
         }
         if (debug) {
-          if (!b->probe_stats.p && (rc_dbg = b->probe_stats.alloc(16))) return rc_dbg;
-          NRT_CUDA_TRY(cudaMemsetAsync(b->probe_stats.p, 0, 16 * sizeof(unsigned long long), st));
+          if (!b->probe_stats.p && (rc_dbg = b->probe_stats.alloc(32))) return rc_dbg;
+          NRT_CUDA_TRY(cudaMemsetAsync(b->probe_stats.p, 0, 32 * sizeof(unsigned long long), st));
         }
         const int resident = v3::kCtasPerSm * b->ix->ctx->sm_count;
         if (b->n_probe_simple > 0) {
           P.work_query = L.work_query; P.work_slice = L.work_slice; P.n_work = b->n_probe_simple; P.work_counter = b->work_counter.p;
           P.stats = debug ? b->probe_stats.p : nullptr;
-          v3::posting_probe_kernel<true><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          if (debug) v3::posting_probe_kernel<true, true><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          else v3::posting_probe_kernel<true, false><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
         }
         if (b->n_probe_generic > 0) {
           P.work_query = L.work_query + b->n_probe_simple; P.work_slice = L.work_slice + b->n_probe_simple;
           P.n_work = b->n_probe_generic; P.work_counter = b->work_counter.p + 1;
-          P.stats = debug ? b->probe_stats.p + 8 : nullptr;
-          v3::posting_probe_kernel<false><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          P.stats = debug ? b->probe_stats.p + 16 : nullptr;
+          if (debug) v3::posting_probe_kernel<false, true><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          else v3::posting_probe_kernel<false, false><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
         }
         NRT_CUDA_TRY(cudaGetLastError());
       }
@@ -1107,11 +1146,13 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     if (h[5]) fprintf(stderr, "[nrtgpu modes] sparse items: set-up %.0f cyc, sweep %.0f, flush+output %.0f, %.2f runs/item\n", (double)h[9] / h[5], (double)h[10] / h[5], (double)h[11] / h[5], (double)h[12] / h[5]);
   }
   if (debug && b->probe_stats.p && b->use_probe) {
-    unsigned long long h[16];
+    unsigned long long h[32];
     NRT_CUDA_TRY(cudaMemcpyAsync(h, b->probe_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     NRT_CUDA_TRY(cudaStreamSynchronize(st));
     for (int k = 0; k < 2; ++k) {
-      const unsigned long long* x = h + 8 * k;
+      const unsigned long long* x = h + 16 * k;
+      if (x[0]) fprintf(stderr, "[nrtgpu probe %s] longest item %llu cyc; CTA busy: mean %.0f max %llu cyc; warm-up items %llu, %.0f cyc each; per item: flush %.0f cyc, TMA wait %.0f cyc\n", k == 0 ? "simple" : "generic",
+                        x[8], (double)x[9] / std::min<double>((double)x[0], (double)(v3::kCtasPerSm * b->ix->ctx->sm_count)), x[10], x[11], x[11] ? (double)x[12] / x[11] : 0.0, (double)x[13] / x[0], (double)x[14] / x[0]);
       if (x[0]) fprintf(stderr, "[nrtgpu probe %s] %llu items, %.0f cyc/item (set-up %.0f), %.2f runs/item (%.2f staged), %.1f rounds/item, %llu driver postings (%.0f/item), %.2f flushes/item\n",
                         k == 0 ? "simple" : "generic", x[0], (double)x[1] / x[0], (double)x[6] / x[0], (double)x[2] / x[0], (double)x[5] / x[0],
                         (double)x[7] / x[0], x[3], (double)x[3] / x[0], (double)x[4] / x[0]);

@@ -40,6 +40,12 @@ using v2::mbar_init;
 using v2::mbar_try_wait;
 using v2::smem_u32;
 
+// profiling builds only (-DNRT_PROBE_KNOCK): parts of the kernel can be disabled at run time through ProbeLaunch::knock
+#ifdef NRT_PROBE_KNOCK
+#define NRT_KNOCK(bit) ((L.knock & (bit)) != 0)
+#else
+#define NRT_KNOCK(bit) false
+#endif
 constexpr int kT = 4;
 #ifndef NRT_PROBE_CTAS
 #define NRT_PROBE_CTAS 3
@@ -76,12 +82,13 @@ struct ProbeLaunch {
   const DevClause* clauses;
   const DevQuery* queries;
   const int32_t* work_query;
-  const int32_t* work_slice;     // slice | flags << 24 (1: warm-up item = first kWarmGran granules of slice 0, 2: slice-0 item behind them)
-  const uint32_t* sbounds;       // [nq][kT][n_slices + 2]: postings of the slot's list below every slice boundary, then below the warm-up boundary
+  const int32_t* work_slice;     // slice | part << 16 | log2(parts) << 20 | flags << 24 (1: warm-up item = first kWarmGran granules of slice 0, 2: slice-0 item behind them)
+  const uint32_t* sbounds;       // [nq][kT][n_slices * parts_max + 2]: postings of the slot's list below every part boundary, the shard end, the warm-up boundary
   const uint8_t* field_min_norm;
   unsigned int* work_counter;    // queue head
   unsigned long long* stats;     // optional [8]: items, item cycles, runs, driver postings, flushes, staged postings, set-up cycles, rounds
   int32_t n_work, n_lists, n_slices, top_k;
+  int32_t parts_max;             // result lists / boundary entries per slice (a heavy (query, slice) is split into up to this many items)
   int32_t slice_docs;            // multiple of kGran, <= kMaxSliceGran * kGran
   int32_t n_gran;
   int64_t threshold;             // INT32_MAX: ScoreMode.COMPLETE (exact counts)
@@ -105,6 +112,7 @@ struct ProbeLaunch {
   const uint32_t* sort_codes;    // [n_docs] codes of the sort column (0 = doc without a value)
   const uint32_t* sort_missing_code;   // [1] code of the sort's missing value
   const AggLaunch* aggs;         // additional collectors (generic instantiation; device pointer, NULL: none)
+  int32_t knock;                 // profiling only (NRTGPU_KNOCK): 1 no plane gathers, 2 no searches, 4 no appends, 8 no sweep
 };
 
 struct alignas(128) ProbeSmem {
@@ -323,7 +331,8 @@ __device__ __noinline__ uint32_t probe_global(const int32_t* docs, const uint8_t
   return (l < end && __ldg(docs + l) == doc) ? (uint32_t)__ldg(f8 + l) : 0u;
 }
 
-template <bool kSimple>
+// kStats: the profiling instantiation (NRTGPU_DEBUG_MODES=1) keeps cycle counters; the production one has none of their registers
+template <bool kSimple, bool kStats>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(const __grid_constant__ ProbeLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>(smem_raw);
@@ -336,7 +345,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
   }
   uint32_t stage_parity = 0;   // phase of stage_bar the next staged run completes (tracked identically by every thread)
   const int gran_per_slice = L.slice_docs >> kLogGran;
-  const int sb_stride = L.n_slices + 2;
+  const int fine = (gran_per_slice + L.parts_max - 1) / L.parts_max;   // granules per finest part of a slice
+  const int sb_stride = L.n_slices * L.parts_max + 2;
+  const long long t_cta = kStats ? clock64() : 0ll;
 
   for (;;) {
     __syncthreads();   // the previous item is retired (also orders the mbarrier init before its first use)
@@ -360,10 +371,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     const int wi = sm.wi;
     if (wi >= L.n_work) break;
     if (sm.skip) continue;
-    const long long t_start = L.stats ? clock64() : 0ll;
+    const long long t_start = kStats ? clock64() : 0ll;
     const int qi = L.work_query[wi];
     const int slice_raw = L.work_slice[wi];
-    const int slice = slice_raw & 0xffffff;
+    const int slice = slice_raw & 0xffff;
+    const int part = (slice_raw >> 16) & 0xf, lparts = (slice_raw >> 20) & 0xf;   // part `part` of 2^lparts of the slice
     const int wflags = slice_raw >> 24;
     const int ncl = L.queries[qi].n_clauses, cbeg = L.queries[qi].clause_begin, n_term = L.queries[qi].n_term;
     if (tid == 0) {
@@ -379,8 +391,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
                                       sm.s_clause[s] = 0; sm.s_field[s] = 0; sm.s_sdelta[s] = 0; sm.s_pbm[s] = 0; sm.s_row[s] = -1; }
     const int g_first = slice * gran_per_slice;
     const int g_count = min(gran_per_slice, L.n_gran - g_first);
-    const int g_lo = (wflags & 2) ? min(g_count, kWarmGran) : 0;
-    const int g_hi = (wflags & 1) ? min(g_count, kWarmGran) : g_count;
+    // granule range of the item inside its slice, and the entries of the boundary table that hold its posting bounds
+    const int kfine = L.parts_max >> lparts;   // finest parts per part of this item
+    int g_lo = min(g_count, part * kfine * fine);
+    int g_hi = ((part + 1) * kfine >= L.parts_max) ? g_count : min(g_count, (part + 1) * kfine * fine);
+    const int e_lo = slice * L.parts_max + part * kfine;
+    int e_hi = slice * L.parts_max + (part + 1) * kfine;   // (part + 1) * kfine == parts_max: entry 0 of the next slice / the end entry
+    const int e_warm = L.n_slices * L.parts_max + 1;
+    if (wflags & 2) g_lo = max(g_lo, min(g_count, kWarmGran));
+    if (wflags & 1) { g_hi = min(g_count, kWarmGran); e_hi = e_warm; }
     __syncthreads();   // B1: query + clauses resident
     // terminateAfter (TerminateAfterWrapper.java:150-162): a query that has collected enough hits stops collecting
     if (L.terminate_after > 0 && (long long)sm.hits0 >= L.terminate_after) {
@@ -392,9 +411,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       const DevClause& c = sm.cl[tid];
       const int s = c.slot;
       const uint32_t* sb = L.sbounds + ((size_t)qi * kT + s) * sb_stride;
-      const uint32_t a = (wflags & 2) ? sb[L.n_slices + 1] : sb[slice];
-      const uint32_t b = (wflags & 1) ? sb[L.n_slices + 1] : sb[slice + 1];
-      sm.s_ia[s] = a; sm.s_ib[s] = b;
+      uint32_t a = sb[e_lo];
+      const uint32_t b = sb[e_hi];
+      if (wflags & 2) a = max(a, sb[e_warm]);
+      sm.s_ia[s] = a; sm.s_ib[s] = max(a, b);
       sm.s_gdocs[s] = L.ix.post_docs + c.post_base;
       sm.s_gf8[s] = L.ix.post_f8 + c.post_base;
       const bool has_plane = c.plane >= 0 && L.ix.dense_tf != nullptr && L.ix.dense_tf2 != nullptr;
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       const DevClause& c = sm.cl[i];
       if (c.kind != NRTGPU_TERM || c.gran_row < 0) continue;
       const uint32_t* row = L.ix.gran_tab + (size_t)c.gran_row * (size_t)(L.n_gran + 1) + g_first;
-      for (int g = tid; g <= g_count; g += kThreads) sm.gb[c.slot][g] = __ldg(row + g);
+      for (int g = g_lo + tid; g <= g_hi; g += kThreads) sm.gb[c.slot][g] = __ldg(row + g);
     }
     if (kSimple && tid >= 64 && tid < 64 + 4 * kT) {   // per-slot score bounds at tf = 1..4 (shortest field length present)
       const int s = (tid - 64) >> 2, c = ((tid - 64) & 3) + 1;
@@ -522,7 +542,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     const uint8_t* pl0 = sm.s_plane2[0]; const uint8_t* pl1 = sm.s_plane2[1]; const uint8_t* pl2 = sm.s_plane2[2]; const uint8_t* pl3 = sm.s_plane2[3];
     unsigned int my_hits = 0;
     unsigned long long dbg_post = 0; unsigned int dbg_runs = 0, dbg_rounds = 0, dbg_flush = 0, dbg_staged = 0;
-    const long long t_setup = L.stats ? clock64() : 0ll;
+    long long dbg_tflush = 0, dbg_twait = 0;
+    const long long t_setup = kStats ? clock64() : 0ll;
 
     const bool dense = !kSimple && sm.q.dense_driver != 0;
     const uint32_t* live = L.ix.live_bits;
@@ -623,8 +644,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       __syncthreads();   // R1: run plan visible
       const int g1 = sm.g1;
       if (sm.staged) {
+        const long long tw = kStats ? clock64() : 0ll;
         while (!mbar_try_wait(&sm.stage_bar, stage_parity)) {}
         stage_parity ^= 1u;
+        if (kStats) dbg_twait += clock64() - tw;
       }
       if (first_run && g1 < g_hi && short_mask) {   // multi-run item: narrow the (now resident) short lists to the first run's docs
         __syncthreads();
@@ -648,10 +671,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
         }
         __syncthreads();
       }
-      ++dbg_runs;
+      if (kStats) ++dbg_runs;
       // ---------------- rounds over the driver postings of the run
       const uint32_t n_total = sm.s_pre[kT];
-      if (L.stats && tid == 0) { dbg_post += n_total; dbg_staged += sm.staged ? 1u : 0u; }
+      if (kStats && tid == 0) { dbg_post += n_total; dbg_staged += sm.staged ? 1u : 0u; }
       // No barrier between rounds: every warp streams through its postings on its own. A thread whose candidate does
       // not fit the buffer parks it and stops; the CTA meets at the barrier below, flushes once, and the loop resumes.
       // Driver lists are swept one after the other, so everything that depends on the leading list (what to probe,
@@ -668,15 +691,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
             const int p = atomicAdd(&sm.cand_count, 1);
             if (p < kCand) { sm.cand[p] = park[j]; pmask &= ~(1u << j); } else full = true;
           }
-        const int ct_end = dense ? n_term + 1 : n_term;   // dense: one more "list" = every doc of the run
+        const int ct_end = NRT_KNOCK(8) ? 0 : (dense ? n_term + 1 : n_term);   // dense: one more "list" = every doc of the run
         while (!full && ct < ct_end) {
           const bool t_dense = ct == n_term;
           const uint32_t n_t = t_dense ? (uint32_t)(sm.run_d1 - sm.run_d0) : (((drv_mask >> ct) & 1u) ? sm.s_rb[ct] - sm.s_ra[ct] : 0u);
           if (cb >= n_t) { ++ct; cb = 0; continue; }
           const int t = t_dense ? 0 : ct;
           const uint32_t need = t_dense ? ((n_term >= 32) ? 0xffffffffu : ((1u << n_term) - 1u)) : sm.s_need[t];
-          const uint32_t need_plane = need & plane_mask, need_long = need & long_mask, need_short = need & short_mask,
-                         need_glob = need & global_mask;
+          const uint32_t need_plane = NRT_KNOCK(1) ? 0u : need & plane_mask, need_long = NRT_KNOCK(2) ? 0u : need & long_mask,
+                         need_short = NRT_KNOCK(2) ? 0u : need & short_mask, need_glob = need & global_mask;
           const bool t_staged = !t_dense && (((long_mask | short_mask) >> t) & 1u);
           const bool t_ess = (ess_mask >> t) & 1u;
           const uint32_t candbelow = t_dense ? 0u : sm.s_candbelow[t], cntbefore = t_dense ? 0u : sm.s_cntbefore[t];
@@ -785,18 +808,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
                 }
                 if (!(entry > theta) || (has_after && !(entry < after_key))) continue;
               }
+              if (NRT_KNOCK(4)) continue;
               const int p = atomicAdd(&sm.cand_count, 1);
               if (p < kCand) sm.cand[p] = entry;
               else { park[j] = entry; pmask |= 1u << j; full = true; }
             }
             cb += kR * kThreads;
-            if (tid == 0) ++dbg_rounds;
+            if (kStats && tid == 0) ++dbg_rounds;
           }
         }
         __syncthreads();
         if (sm.cand_count <= kCand) break;   // nobody is parked (the count passes kCand only through a failed append)
+        const long long tf = kStats ? clock64() : 0ll;
         flush_candidates<kSimple>(L, sm, norms0, n_term, has_after, after_key, L.top_k, &L.theta[qi]);
-        ++dbg_flush;
+        if (kStats) dbg_tflush += clock64() - tf;
+        if (kStats) ++dbg_flush;
       }
       g0 = g1;
       first_run = false;
@@ -806,17 +832,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     // ---------------- finish the work item (the slice merge sorts, so only a full buffer needs ordering here)
     __syncthreads();
     if (kSimple ? sm.cand_count > sm.n_keys : sm.cand_count > L.top_k) {
+      const long long tf = kStats ? clock64() : 0ll;
       flush_candidates<kSimple>(L, sm, norms0, n_term, has_after, after_key, L.top_k, &L.theta[qi]);
-      ++dbg_flush;
+      if (kStats) dbg_tflush += clock64() - tf;
+      if (kStats) ++dbg_flush;
     }
     const int keep = min(sm.cand_count, L.top_k);
-    const int out_list = (wflags & 1) ? L.n_lists - 1 : slice;
+    const int out_list = (wflags & 1) ? L.n_lists - 1 : slice * L.parts_max + part * kfine;
     uint64_t* out = L.slice_keys + ((size_t)qi * L.n_lists + out_list) * L.top_k;
     for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
     if (tid == 0) L.slice_cnt[(size_t)qi * L.n_lists + out_list] = keep;
     for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
     if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
-    if (L.stats && tid == 0) {
+    if (kStats && tid == 0) {
       atomicAdd(&L.stats[0], 1ull);
       atomicAdd(&L.stats[1], (unsigned long long)(clock64() - t_start));
       atomicAdd(&L.stats[2], (unsigned long long)dbg_runs);
@@ -825,26 +853,40 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
       atomicAdd(&L.stats[5], (unsigned long long)dbg_staged);
       atomicAdd(&L.stats[6], (unsigned long long)(t_setup - t_start));
       atomicAdd(&L.stats[7], (unsigned long long)dbg_rounds);
+      const unsigned long long cyc = (unsigned long long)(clock64() - t_start);
+      atomicMax(&L.stats[8], cyc);
+      if (wflags & 1) { atomicAdd(&L.stats[11], 1ull); atomicAdd(&L.stats[12], cyc); }
+      atomicAdd(&L.stats[13], (unsigned long long)dbg_tflush); atomicAdd(&L.stats[14], (unsigned long long)dbg_twait);
     }
+  }
+  if (kStats && tid == 0) {
+    const unsigned long long busy = (unsigned long long)(clock64() - t_cta);
+    atomicAdd(&L.stats[9], busy); atomicMax(&L.stats[10], busy);
   }
 }
 
-// postings of every (query, term slot) below each slice boundary and below the warm-up boundary of slice 0
+// postings of every (query, term slot) below each part boundary of every slice (parts_max equal granule ranges per
+// slice), below the end of the shard, and below the warm-up boundary of slice 0
 struct SliceBoundsLaunch {
   DevIndexView ix;
   const DevClause* clauses;
   const DevQuery* queries;
-  int32_t nq, n_slices, slice_gran, n_gran;
-  uint32_t* sbounds;   // [nq][kT][n_slices + 2]
+  int32_t nq, n_slices, slice_gran, n_gran, parts_max;
+  uint32_t* sbounds;   // [nq][kT][n_slices * parts_max + 2]
 };
 
 __global__ void slice_bounds_kernel(SliceBoundsLaunch B) {
-  const int per_slot = B.n_slices + 2;
+  const int n_b = B.n_slices * B.parts_max;
+  const int per_slot = n_b + 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B.nq * kT * per_slot) return;
   const int q = (int)(i / (kT * per_slot)), s = (int)((i / per_slot) % kT), e = (int)(i % per_slot);
   const DevQuery dq = B.queries[q];
-  int64_t gran = (e <= B.n_slices) ? (int64_t)e * B.slice_gran : (int64_t)min(kWarmGran, B.slice_gran);
+  const int fine = (B.slice_gran + B.parts_max - 1) / B.parts_max;
+  int64_t gran;
+  if (e < n_b) gran = (int64_t)(e / B.parts_max) * B.slice_gran + min(B.slice_gran, (e % B.parts_max) * fine);
+  else if (e == n_b) gran = B.n_gran;
+  else gran = min(kWarmGran, B.slice_gran);
   if (gran > B.n_gran) gran = B.n_gran;
   uint32_t out = 0;
   for (int c = 0; c < dq.n_clauses; ++c) {
