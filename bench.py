@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] legs of the default N=1 line")
     ap.add_argument("--workload", default="bm25", choices=["bm25", "conj", "knn", "hybrid"],
                     help="bm25 = configs[1] (the headline line); conj = configs[2]; knn = configs[3] (1..8 GPUs); hybrid = configs[4] shape")
+    ap.add_argument("--hybrid-docs-per-gpu", type=int, default=12_500_000, help="--workload hybrid: docs (text + one vector each) per GPU")
+    ap.add_argument("--hybrid-dims", type=int, default=128)
     ap.add_argument("--vectors", type=int, default=1_000_000)
     ap.add_argument("--dims", type=int, default=768)
     return ap.parse_args()
@@ -240,10 +242,24 @@ def conj_leg(args, searcher, sh, stream, steps, threads, n_sample):
     stats = batch.stats()
     kernel_ms, merge_ms, step_ms = time_batch(batch, stream, steps)
     batch.close()
+    # e2e: the one-shot C-ABI call with HOST query buffers (compiled once, as a serving adaptor would cache them) and host results
+    from nrtsearch_b200.search import compile_queries
+    from nrtsearch_b200 import _native
+    carr, ncl, qarr, _ = compile_queries(queries)
+    hd, hs = np.zeros((args.nq, args.topk), np.int32), np.zeros((args.nq, args.topk), np.float32)
+    hc, ht, hr = np.zeros(args.nq, np.int32), np.zeros(args.nq, np.int64), np.zeros(args.nq, np.uint8)
+    lib = _native.gpu_lib()
+
+    def e2e_call():
+        _native.check(lib.nrtgpu_search_bool(searcher.index.handle, carr, ncl, qarr, args.nq, args.topk, args.threshold, 0, ctypes.c_void_p(stream),
+                                             hd.ctypes.data, hs.ctypes.data, hc.ctypes.data, ht.ctypes.data, hr.ctypes.data))
+    for _ in range(2):
+        e2e_call()
     t0 = time.perf_counter()
     for _ in range(steps):
-        searcher.search_batch(queries, coll)
+        e2e_call()
     e2e = args.nq * steps / (time.perf_counter() - t0)
+    assert np.array_equal(hd[:len(ref[2])][:, :1], res.docs[:len(ref[2])][:, :1]), "bench (conj): the one-shot call disagrees with the prepared batch"
     pk, src = peaks()
     alg = float(stats["alg_postings"]) * 8.0 + float(inter.sum()) * (2 + 4) + args.nq * args.topk * 8
     ach = alg / (kernel_ms * 1e-3) / 1e9
@@ -357,7 +373,7 @@ def knn_leg(args, rank, world, local_rank, steps, warmup):
                 "gate": {"queries": ns, "ids_equal_oracle": ns - len(bad), "tie_band_only": len(bad), "scores_rtol": 1e-5},
                 "certificate": {"uncertified_queries": uncert, "of": nq,
                                 "rule": "every vector outside the k' = 4k candidate list proven below the k-th exact score with the bf16 error bound 2^-7 |q||d|; rejected queries re-run exactly"},
-                "roofline": {"bound": "tensor", "kernel": "knn_gemm_bf16_kernel (tcgen05 UMMA 128x256x16, TMEM accumulators, TMA operands, fused top-k' epilogue)",
+                "roofline": {"bound": "tensor", "kernel": "knn_gemm_bf16_db_kernel (tcgen05 UMMA, 256x128 tiles double-buffered in TMEM, TMA operand ring, 16 epilogue warps with the fused top-k' threshold filter)",
                              "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
                              "peak_source": src + " burst", "gemm_ms": gemm_ms, "select_ms": float(np.mean(sel)), "rescore_ms": float(np.mean(resc))},
                 "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": threads, "kind": "port",
@@ -367,48 +383,149 @@ def knn_leg(args, rank, world, local_rank, steps, warmup):
     return line
 
 
-def run_hybrid(args):
-    """configs[4] shape on one shard: text retriever (3-term disjunction, top-100) + kNN retriever (k = 100) ->
-    weighted RRF (rankConstant 60, boosts 1) -> top-100, every stage through the C ABI with host buffers."""
+def run_hybrid(args, rank, world, local_rank):
+    """configs[4]: docs sharded by doc range over the GPUs (12.5M docs x 128-d per GPU by default = 100M docs at 8 GPUs), every
+    shard runs the text retriever (3-term disjunction, top-100, index-wide statistics) and the kNN retriever (cosine,
+    k = 100); ONE all-gather moves both packed per-shard pages, every rank merges each retriever's pages (TopDocs.merge)
+    and blends them with weighted RRF (rankConstant 60, boosts 1; BlenderOperation.java:76-87). Everything goes through
+    the C ABI; the gate is a DISTRIBUTED oracle: each rank's host computes its shard's exact pages (oracle/oracle.c),
+    rank 0 merges and blends them on the CPU and compares the final page bit for bit."""
+    import torch
     import __graft_entry__ as g
     g.build_if_needed()
     import oracle
-    from nrtsearch_b200 import index as ix
+    from nrtsearch_b200 import _native, index as ix
     from nrtsearch_b200.search import GpuContext, GpuIndex, GpuIndexSearcher, RelevanceCollector, blend_rrf, compile_queries
-    n, dims, nq, k = args.docs, args.dims, args.nq, args.topk
-    sh = ix.synth_text_shard(n, args.vocab)
-    sh.term_df = np.diff(sh.term_off).astype(np.int64)
-    sh.vectors = ix.synth_vectors(n, dims)
+    from nrtsearch_b200.shards import PackedGather, shard_range, unpack_record
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; nrtsearch_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    per_gpu = args.hybrid_docs_per_gpu
+    args.docs = per_gpu * world          # weak scaling: the corpus grows with the GPUs (configs[4] = 100M docs at 8)
+    dims, nq, k = args.hybrid_dims, args.nq, args.topk
+    lo, hi = shard_range(args.docs, rank, world)
+    t_build = time.perf_counter()
+    sh = build_shard(args, rank, world, with_column=False)
+    sh.vectors = ix.synth_vectors(hi - lo, dims, row_begin=lo)
     sh.vec_similarity = ix.SIM_COSINE
     queries = make_queries(nq, args.vocab)
     qvec = ix.synth_vectors(nq, dims, seed=ix.SEED_VQUERIES)
-    ctx = GpuContext(0); gix = GpuIndex(ctx, sh); s = GpuIndexSearcher(gix)
+    ctx = GpuContext(local_rank); gix = GpuIndex(ctx, sh); s = GpuIndexSearcher(gix)
+    build_s = time.perf_counter() - t_build
+    lib = _native.gpu_lib()
     coll = RelevanceCollector(k, args.threshold)
+    batch = s.prepare(queries, coll)
+    words = int(lib.nrtgpu_packed_words(nq, k))
+    comb = torch.zeros(2 * words, dtype=torch.int32, device=dev)            # [text record | kNN record] of this shard
+    allrec = torch.zeros(world * 2 * words, dtype=torch.int32, device=dev)
+    text_all = torch.zeros(world * words, dtype=torch.int32, device=dev)
+    knn_all = torch.zeros(world * words, dtype=torch.int32, device=dev)
+    merged = torch.zeros(2 * words, dtype=torch.int32, device=dev)
+    host_rec = torch.zeros(words, dtype=torch.int32).pin_memory()
+    host_out = torch.zeros(2 * words, dtype=torch.int32).pin_memory()
+    batch.bind_packed(comb.data_ptr())
+    stream = torch.cuda.current_stream().cuda_stream
+    kd, ks, kc = np.zeros((nq, k), np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
 
     def step():
-        t = s.search_batch(queries, coll)
-        kd, ks, kc = s.knn(qvec, k)
-        return blend_rrf(ctx, np.stack([t.docs, kd]), np.stack([t.counts, kc]), [1.0, 1.0], 60, k), t, (kd, ks, kc)
-    for _ in range(args.warmup):
+        batch.run(stream)                                                   # text page of the shard -> comb[:words] (device)
+        _native.check(lib.nrtgpu_search_knn(gix.handle, qvec.ctypes.data, nq, k, None, None, ctypes.c_void_p(stream),
+                                            kd.ctypes.data, ks.ctypes.data, kc.ctypes.data))
+        r = host_rec.numpy()
+        r[:nq * k] = kd.reshape(-1); r[nq * k:2 * nq * k] = ks.reshape(-1).view(np.int32); r[2 * nq * k:2 * nq * k + nq] = kc
+        comb[words:].copy_(host_rec, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(allrec, comb)                       # the ONE collective of the step
+        else:
+            allrec.copy_(comb)
+        v = allrec.view(world, 2, words)
+        text_all.view(world, words).copy_(v[:, 0, :]); knn_all.view(world, words).copy_(v[:, 1, :])
+        _native.check(lib.nrtgpu_merge_topk_packed(ctx.handle, world, nq, k, text_all.data_ptr(), merged.data_ptr(), ctypes.c_void_p(stream)))
+        _native.check(lib.nrtgpu_merge_topk_packed(ctx.handle, world, nq, k, knn_all.data_ptr(), merged[words:].data_ptr(), ctypes.c_void_p(stream)))
+        host_out.copy_(merged, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = host_out.numpy()
+        td, ts, tc, _, _ = unpack_record(h[:words], nq, k)
+        nd, ns_, nc, _, _ = unpack_record(h[words:], nq, k)
+        return blend_rrf(ctx, np.stack([td, nd]), np.stack([tc, nc]), [1.0, 1.0], 60, k), (td, ts, tc), (nd, ns_, nc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- gate: distributed oracle on the first queries
+    ns = 0 if args.no_check else min(8, nq)
+    (bd, bs, bc, bt), _, _ = step()
+    barrier()
+    gate_info = None
+    if ns:
+        carr, ncl, qarr, _ = compile_queries(queries[:ns])
+        threads = max(1, (os.cpu_count() or 1) // world)
+        od, os_, oc, _, _ = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, ns, k, INT_MAX, 0, threads)
+        xd, xs, xc = oracle.knn_exact(sh.vectors, ix.SIM_COSINE, qvec[:ns], k, n_threads=threads)
+        xd = xd + lo                                                        # the oracle's kNN page is shard-local
+        mine = (od, os_, oc, xd, xs, xc)
+        if world > 1:
+            pages = [None] * world
+            dist.all_gather_object(pages, mine)
+        else:
+            pages = [mine]
+        if rank == 0:
+            same = 0
+            for q in range(ns):
+                def merge(di, si, ci):   # TopDocs.merge: score desc, doc asc
+                    d = np.concatenate([pg_[di][q, :pg_[ci][q]] for pg_ in pages]); sc = np.concatenate([pg_[si][q, :pg_[ci][q]] for pg_ in pages])
+                    o = np.lexsort((d, -sc.astype(np.float64)))[:k]
+                    return d[o], sc[o]
+                tdq, _ = merge(0, 1, 2)
+                ndq, _ = merge(3, 4, 5)
+                pad = lambda a: np.concatenate([a, np.zeros(k - len(a), a.dtype)])
+                wd, ws, wt = oracle.blend_rrf(np.stack([pad(tdq), pad(ndq)]), [len(tdq), len(ndq)], [1.0, 1.0], 60, k)
+                ok = np.array_equal(bd[q, :bc[q]], wd) and np.array_equal(bs[q, :bc[q]].view(np.uint32), np.asarray(ws, np.float32).view(np.uint32))
+                same += int(ok)
+            assert same == ns, f"bench gate (hybrid N={world}): {ns - same} of {ns} blended pages differ from the distributed CPU oracle"
+            gate_info = {"queries": ns, "bit_exact": True, "against": "per-shard oracle pages (text: exact BM25, kNN: fp64 brute force) merged and RRF-blended on the CPU"}
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
         step()
+    barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        (bd, bs, bc, bt), t, kn = step()
-    dt = (time.perf_counter() - t0) / args.steps
-    # parity of the whole pipeline on a sample
-    ns = min(16, nq)
-    carr, ncl, qarr, _ = compile_queries(queries[:ns])
-    od, os_, oc, _, _ = oracle.search_compiled(oracle.OracleIndex(sh), carr, ncl, qarr, ns, k)
-    kd, ks, kc = oracle.knn_exact(sh.vectors, ix.SIM_COSINE, qvec[:ns], k, n_threads=os.cpu_count() or 1)
-    same = 0
-    for q in range(ns):
-        wd, ws, wt = oracle.blend_rrf(np.stack([od[q], kd[q]]), [oc[q], kc[q]], [1.0, 1.0], 60, k)
-        same += int(np.array_equal(bd[q, :bc[q]], wd) and np.allclose(bs[q, :bc[q]], ws, rtol=1e-6))
-    print(json.dumps({"metric": "hybrid BM25 + kNN + weighted-RRF queries/sec (batch 1024, one shard)", "value": nq / dt, "unit": "queries/s",
-                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-                      "data": "synthetic", "config": {"workload": "configs[4] shape, single shard", "docs": n, "dims": dims, "batch": nq, "top_k": k},
-                      "parity_sample": {"queries": ns, "identical_to_oracle_pipeline": same}}))
-    gix.close(); ctx.close()
+        step()
+    barrier()
+    wall = (time.perf_counter() - t0) / args.steps
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+    if rank == 0:
+        stats = batch.stats()
+        print(json.dumps({
+            "metric": "hybrid BM25 + kNN + weighted-RRF queries/sec (batch 1024, doc-sharded)", "value": nq / wall, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 BM25; bf16 candidates + f64 exact re-score (kNN)", "data": "synthetic",
+            "config": {"workload": "configs[4]: hybrid BM25 + kNN rescorer/blender, doc-range shards, one all-gather of the packed per-shard pages",
+                       "docs": args.docs, "docs_per_gpu": per_gpu, "dims": dims, "vocab": args.vocab, "batch": nq, "top_k": k,
+                       "sharding": f"doc-range x{world}", "blend": "weighted RRF, rankConstant 60"},
+            "e2e": {"value": nq / wall, "unit": "queries/s", "h2d_bytes_per_step": nq * 3 * 24 + nq * dims * 4 + words * 4,
+                    "d2h_bytes_per_step": 2 * words * 4 + nq * k * 8},
+            "timing": "host wall clock per step (the step is host-driven: C-ABI calls with host buffers), barrier + synchronize on both sides, max over ranks",
+            "gpu_launches": int(stats["launches_per_run"]) + 8, "gate": gate_info, "clocks": clocks,
+            "index": {"postings_rank0": int(sh.term_off[-1]), "device_bytes_rank0": gix.device_bytes, "build_s": build_s}}))
+    batch.close(); gix.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
@@ -461,7 +578,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if args.workload == "hybrid":
-        return run_hybrid(args) if rank == 0 else None
+        return run_hybrid(args, rank, world, local_rank)
 
     import torch
     import __graft_entry__ as g

@@ -423,6 +423,8 @@ struct MergeLaunch {
   const unsigned long long* total_hits; const int32_t* pruned; int32_t* terminated;
   long long terminate_after;                  // > 0: a query with more hits than this terminated early (TerminateAfterWrapper.java:150-158)
   long long* out_total; int32_t* out_flags;   // flags: bit 0 relation GREATER_THAN_OR_EQUAL_TO, bit 1 terminated early
+  const uint64_t* theta = nullptr;            // optional [nq]: the k-th best key some work item published (>= top_k keys are >= it):
+                                              // smaller keys cannot be in the merged page and are dropped before the sort
 };
 
 constexpr int kMergeThreads = 256;
@@ -433,8 +435,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
   __shared__ int32_t s_cnt[kMergeThreads];
   __shared__ int32_t s_nz[kMergeThreads];   // the non-empty lists of a chunk of list counts
   __shared__ int32_t s_nnz;
+  __shared__ int32_t s_fill;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
+  const uint64_t floor_key = M.theta ? M.theta[q] : 0ull;
   int have = 0;        // keys[0..have) hold the best so far
   bool dirty = false;  // ... unsorted / not yet cut to top_k
   auto sort_and_cut = [&]() {
@@ -458,12 +462,34 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
     if (c > 0) { const int p = atomicAdd(&s_nnz, 1); s_nz[p] = l; s_cnt[p] = c; }
     __syncthreads();
     const int nnz = s_nnz;
-    for (int i0 = 0; i0 < nnz; ++i0) {
-      const int cnt = s_cnt[i0];
-      if (have + cnt > kMergeCap) sort_and_cut();
-      const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
-      for (int i = tid; i < cnt; i += kMergeThreads) keys[have + i] = src[i];
-      have += cnt; dirty = true;
+    int total = 0;
+    for (int i = 0; i < nnz; ++i) total += s_cnt[i];
+    if (have + total > kMergeCap && dirty) sort_and_cut();
+    if (have + total <= kMergeCap) {
+      // every list of the chunk fits: one warp per list, no barrier between lists; keys below the floor are dropped
+      __syncthreads();
+      if (tid == 0) s_fill = have;
+      __syncthreads();
+      for (int i0 = tid >> 5; i0 < nnz; i0 += kMergeThreads / 32) {
+        const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
+        for (int i = tid & 31; i < s_cnt[i0]; i += 32) { const uint64_t k = src[i]; if (k >= floor_key) keys[atomicAdd(&s_fill, 1)] = k; }
+      }
+      __syncthreads();
+      if (s_fill > have) dirty = true;
+      have = s_fill;
+    } else {
+      for (int i0 = 0; i0 < nnz; ++i0) {
+        const int cnt = s_cnt[i0];
+        if (have + cnt > kMergeCap) sort_and_cut();
+        const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
+        __syncthreads();
+        if (tid == 0) s_fill = have;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += kMergeThreads) { const uint64_t k = src[i]; if (k >= floor_key) keys[atomicAdd(&s_fill, 1)] = k; }
+        __syncthreads();
+        have = s_fill;
+        dirty = true;
+      }
     }
   }
   if (dirty) sort_and_cut();

@@ -138,11 +138,16 @@ struct nrtgpu_ctx {
   std::mutex hyb_mu;             // O(k) hybrid stages share one pooled device scratch (no cudaMalloc per call)
   DevBuf<int32_t> hyb_scratch;
   int64_t item_postings = 32768; // NRTGPU_ITEM_POSTINGS: floor of the postings a (query, slice) may hold before it is split into 2..16 parts
+  int64_t item_share_full = 32;  // NRTGPU_ITEM_SHARE_FULL: the same for launches that visit every posting (ScoreMode.COMPLETE, generic clause evaluation)
   int64_t item_share = 12;       // NRTGPU_ITEM_SHARE: ... and it is split when it exceeds 1/share of the postings per resident CTA
+  int probe_cfg = 0;             // NRTGPU_PROBE_CFG: 0 auto, 1 always A (3 CTAs / SM), 2 always B (4 CTAs / SM)
   bool order_lpt = false;        // NRTGPU_ORDER=lpt: query-major work order, longest query first
   bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
   bool debug_modes = false;     // NRTGPU_DEBUG_MODES=1: per-launch kernel statistics on stderr (adds a stream synchronisation)
 };
+
+// which launch configuration of the probe kernel a launch takes (see probe_kernel.cuh kCtasA / kCtasB)
+static inline bool ix_ctx_probe_cfg(const nrtgpu_ctx* c, bool visits_everything) { return c->probe_cfg == 2 || (c->probe_cfg == 0 && visits_everything); }
 
 struct nrtgpu_index {
   nrtgpu_ctx* ctx = nullptr;
@@ -351,8 +356,10 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
+  { const char* e = getenv("NRTGPU_PROBE_CFG"); c->probe_cfg = e ? atoi(e) : 0; }
   { const char* e = getenv("NRTGPU_ITEM_POSTINGS"); if (e && atoll(e) > 0) c->item_postings = atoll(e); }
   { const char* e = getenv("NRTGPU_ITEM_SHARE"); if (e && atoll(e) > 0) c->item_share = atoll(e); }
+  { const char* e = getenv("NRTGPU_ITEM_SHARE_FULL"); if (e && atoll(e) > 0) c->item_share_full = atoll(e); }
   { const char* e = getenv("NRTGPU_ORDER"); c->order_by_cost = e && (std::strcmp(e, "cost") == 0 || std::strcmp(e, "lpt") == 0); c->order_lpt = e && std::strcmp(e, "lpt") == 0; }
   NRT_CUDA_TRY(cudaFuncSetAttribute(bool_window_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(BoolSmem<uint32_t>)));
@@ -362,10 +369,11 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
                                     (int)sizeof(v2::StreamSmem)));
   NRT_CUDA_TRY(cudaFuncSetAttribute(v2::posting_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(v2::StreamSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
-  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmem)));
+#define NRT_PROBE_ATTR(S, D) \
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<S, D, v3::kCtasA, v3::kStageA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmemT<v3::kStageA>))); \
+  NRT_CUDA_TRY(cudaFuncSetAttribute(v3::posting_probe_kernel<S, D, v3::kCtasB, v3::kStageB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v3::ProbeSmemT<v3::kStageB>)));
+  NRT_PROBE_ATTR(true, false) NRT_PROBE_ATTR(false, false) NRT_PROBE_ATTR(true, true) NRT_PROBE_ATTR(false, true)
+#undef NRT_PROBE_ATTR
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemmSmem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm3Smem));
   NRT_CUDA_TRY(cudaFuncSetAttribute(tc::knn_gemm_bf16_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kGemm2Smem));
@@ -899,8 +907,13 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if (b->use_probe) {
     int64_t total_cost = 0;
     for (int qi : order) total_cost += cost[qi];
-    const int64_t item_max = std::max<int64_t>(ix->ctx->item_postings, total_cost / ((int64_t)v3::kCtasPerSm * ix->ctx->sm_count * ix->ctx->item_share));
+    const int64_t per_cta = total_cost / ((int64_t)v3::kCtasA * ix->ctx->sm_count);
+    const int64_t item_max_top = std::max<int64_t>(ix->ctx->item_postings, per_cta / ix->ctx->item_share);
+    const int64_t item_max_full = std::max<int64_t>(ix->ctx->item_postings, per_cta / ix->ctx->item_share_full);
     for (int qi : order) {
+      // pruned sweeps (TOP_SCORES pure disjunctions) skip most of a heavy item's postings; launches that visit every
+      // posting are split finer (their longest item is the tail of the launch)
+      const int64_t item_max = (is_simple(qi) && b->threshold < (int64_t)INT32_MAX) ? item_max_top : item_max_full;
       const int64_t per_slice = cost[qi] / std::max(1, (int)b->n_slices);
       int lp = 0;
       while (lp < 4 && (per_slice >> lp) > item_max && (gran_per_slice >> (lp + 1)) >= 8) ++lp;
@@ -1090,19 +1103,31 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
           if (!b->probe_stats.p && (rc_dbg = b->probe_stats.alloc(32))) return rc_dbg;
           NRT_CUDA_TRY(cudaMemsetAsync(b->probe_stats.p, 0, 32 * sizeof(unsigned long long), st));
         }
-        const int resident = v3::kCtasPerSm * b->ix->ctx->sm_count;
+        // configuration A (3 CTAs / SM) for the pruned sweeps of TOP_SCORES, B (4 CTAs / SM) where every posting is visited
+        const bool cfg_b_simple = ix_ctx_probe_cfg(b->ix->ctx, P.threshold >= (int64_t)INT32_MAX);
+        const bool cfg_b_generic = ix_ctx_probe_cfg(b->ix->ctx, true);
+        auto launch = [&](auto simple_tag, bool cfg_b, int n_items) {
+          constexpr bool S = decltype(simple_tag)::value;
+          if (cfg_b) {
+            const int grid = std::min(v3::kCtasB * b->ix->ctx->sm_count, n_items);
+            if (debug) v3::posting_probe_kernel<S, true, v3::kCtasB, v3::kStageB><<<grid, v3::kThreads, sizeof(v3::ProbeSmemT<v3::kStageB>), st>>>(P);
+            else v3::posting_probe_kernel<S, false, v3::kCtasB, v3::kStageB><<<grid, v3::kThreads, sizeof(v3::ProbeSmemT<v3::kStageB>), st>>>(P);
+          } else {
+            const int grid = std::min(v3::kCtasA * b->ix->ctx->sm_count, n_items);
+            if (debug) v3::posting_probe_kernel<S, true, v3::kCtasA, v3::kStageA><<<grid, v3::kThreads, sizeof(v3::ProbeSmemT<v3::kStageA>), st>>>(P);
+            else v3::posting_probe_kernel<S, false, v3::kCtasA, v3::kStageA><<<grid, v3::kThreads, sizeof(v3::ProbeSmemT<v3::kStageA>), st>>>(P);
+          }
+        };
         if (b->n_probe_simple > 0) {
           P.work_query = L.work_query; P.work_slice = L.work_slice; P.n_work = b->n_probe_simple; P.work_counter = b->work_counter.p;
           P.stats = debug ? b->probe_stats.p : nullptr;
-          if (debug) v3::posting_probe_kernel<true, true><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
-          else v3::posting_probe_kernel<true, false><<<std::min(resident, b->n_probe_simple), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          launch(std::true_type{}, cfg_b_simple, b->n_probe_simple);
         }
         if (b->n_probe_generic > 0) {
           P.work_query = L.work_query + b->n_probe_simple; P.work_slice = L.work_slice + b->n_probe_simple;
           P.n_work = b->n_probe_generic; P.work_counter = b->work_counter.p + 1;
           P.stats = debug ? b->probe_stats.p + 16 : nullptr;
-          if (debug) v3::posting_probe_kernel<false, true><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
-          else v3::posting_probe_kernel<false, false><<<std::min(resident, b->n_probe_generic), v3::kThreads, sizeof(v3::ProbeSmem), st>>>(P);
+          launch(std::false_type{}, cfg_b_generic, b->n_probe_generic);
         }
         NRT_CUDA_TRY(cudaGetLastError());
       }
@@ -1151,8 +1176,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
     NRT_CUDA_TRY(cudaStreamSynchronize(st));
     for (int k = 0; k < 2; ++k) {
       const unsigned long long* x = h + 16 * k;
-      if (x[0]) fprintf(stderr, "[nrtgpu probe %s] longest item %llu cyc; CTA busy: mean %.0f max %llu cyc; warm-up items %llu, %.0f cyc each; per item: flush %.0f cyc, TMA wait %.0f cyc\n", k == 0 ? "simple" : "generic",
-                        x[8], (double)x[9] / std::min<double>((double)x[0], (double)(v3::kCtasPerSm * b->ix->ctx->sm_count)), x[10], x[11], x[11] ? (double)x[12] / x[11] : 0.0, (double)x[13] / x[0], (double)x[14] / x[0]);
+      if (x[0]) fprintf(stderr, "[nrtgpu probe %s] longest item %llu cyc; CTA busy: mean %.0f max %llu cyc; warm-up items %llu, %.0f cyc each; per item: flush %.0f cyc (sort %.0f), TMA wait %.0f cyc\n", k == 0 ? "simple" : "generic",
+                        x[8], (double)x[9] / std::min<double>((double)x[0], (double)(v3::kCtasA * b->ix->ctx->sm_count)), x[10], x[11], x[11] ? (double)x[12] / x[11] : 0.0, (double)x[13] / x[0], (double)x[15] / x[0], (double)x[14] / x[0]);
       if (x[0]) fprintf(stderr, "[nrtgpu probe %s] %llu items, %.0f cyc/item (set-up %.0f), %.2f runs/item (%.2f staged), %.1f rounds/item, %llu driver postings (%.0f/item), %.2f flushes/item\n",
                         k == 0 ? "simple" : "generic", x[0], (double)x[1] / x[0], (double)x[6] / x[0], (double)x[2] / x[0], (double)x[5] / x[0],
                         (double)x[7] / x[0], x[3], (double)x[3] / x[0], (double)x[4] / x[0]);
@@ -1164,6 +1189,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   M.out_docs = b->o_docs(); M.out_scores = b->o_scores(); M.out_counts = b->o_counts();
   M.total_hits = b->total_hits.p; M.pruned = b->pruned.p; M.terminated = b->terminated.p; M.terminate_after = b->ta_scalar;
   M.out_total = b->bound_total; M.out_flags = b->bound_flags;
+  M.theta = b->use_probe ? b->theta.p : nullptr;
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
   if (b->sort_kind != NRTGPU_SORT_RELEVANCE) {   // FieldDoc values of the final hits; scores become NaN

@@ -47,22 +47,18 @@ using v2::smem_u32;
 #define NRT_KNOCK(bit) false
 #endif
 constexpr int kT = 4;
-#ifndef NRT_PROBE_CTAS
-#define NRT_PROBE_CTAS 3
-#endif
-constexpr int kCtasPerSm = NRT_PROBE_CTAS;
+// Two launch configurations of the same kernel: 3 CTAs / SM with an 8192-posting stage (80 registers; best for the
+// MAXSCORE-pruned sweeps of TOP_SCORES, whose sparse leading lists want the larger stage) and 4 CTAs / SM with a
+// 6656-posting stage (64 registers; best where every posting is visited: ScoreMode.COMPLETE and the generic clause
+// evaluation, both latency bound on their gathers: 32 resident warps hide more of it than 24).
+constexpr int kCtasA = 3, kStageA = 8192;
+constexpr int kCtasB = 4, kStageB = 6656;
 constexpr int kThreads = 256;
 constexpr int kLogGran = v2::kLogGran;       // 1024-doc granules: the granularity of the index-time skip data (gran_tab)
 constexpr int kGran = 1 << kLogGran;
 constexpr int kMaxSliceGran = 512;           // a slice spans at most 512K docs (its granule offsets live in shared memory)
-#ifndef NRT_PROBE_STAGE
-#define NRT_PROBE_STAGE 8192
-#endif
-constexpr int kStage = NRT_PROBE_STAGE;      // postings of the searched lists resident in shared memory (5 B each)
 constexpr int kAlign = 16;                   // staged segments start on 16-posting boundaries (TMA: 16-byte aligned tf bytes)
 constexpr int kLongReserve = kT * (kGran + 2 * kAlign);   // one granule of every long list always fits
-constexpr int kShortMax = kStage - kLongReserve;          // lists without skip data are staged whole, up to this many postings
-static_assert(kShortMax >= 1024, "stage too small");
 #ifndef NRT_PROBE_R
 #define NRT_PROBE_R 2
 #endif
@@ -115,9 +111,13 @@ struct ProbeLaunch {
   int32_t knock;                 // profiling only (NRTGPU_KNOCK): 1 no plane gathers, 2 no searches, 4 no appends, 8 no sweep
 };
 
-struct alignas(128) ProbeSmem {
-  int32_t sdocs[kStage];
-  uint8_t sf8[kStage];
+template <int kStageT>
+struct alignas(128) ProbeSmemT {
+  static constexpr int kStage = kStageT;             // postings of the searched lists resident in shared memory (5 B each)
+  static constexpr int kShortMax = kStageT - kLongReserve;   // lists without skip data are staged whole, up to this many postings
+  static_assert(kShortMax >= 1024, "stage too small");
+  int32_t sdocs[kStageT];
+  uint8_t sf8[kStageT];
   uint32_t gb[kT][kMaxSliceGran + 4];   // granule offsets of the slice for lists with skip data (relative to the list's first posting)
   uint64_t cand[kCand];
   float ubt[kUbt];
@@ -156,7 +156,7 @@ struct alignas(128) ProbeSmem {
   unsigned long long hits0;
   unsigned long long theta;
 };
-static_assert(sizeof(ProbeSmem) <= 232448 / kCtasPerSm - 1024, "ProbeSmem exceeds the per-CTA shared memory budget");
+static_assert(sizeof(ProbeSmemT<kStageA>) <= 232448 / kCtasA - 1024 && sizeof(ProbeSmemT<kStageB>) <= 232448 / kCtasB - 1024, "ProbeSmem exceeds the per-CTA shared memory budget");
 
 // A staged segment [a, b) of a list (postings relative to the list's first) is copied from the enclosing 16-posting
 // aligned range of the GLOBAL posting arrays (TMA needs 16-byte aligned tf bytes): with pbm = post_base mod 16 the
@@ -169,12 +169,24 @@ __device__ __forceinline__ uint32_t seg_n(uint32_t a, uint32_t b, uint32_t pbm) 
 
 // Universal clause evaluation of one doc given the tf word of its term slots (Lucene BooleanScorerSupplier semantics,
 // as v2::evaluate_doc_generic: conjunction / disjunction sums in double, ReqOptSumScorer float add when msm == 0).
-__device__ __noinline__ bool evaluate_doc(const ProbeLaunch& L, const ProbeSmem& sm, int32_t doc, uint32_t word, float* out_score) {
+template <typename SM>
+__device__ __noinline__ bool evaluate_doc(const ProbeLaunch& L, const SM& sm, int32_t doc, uint32_t word, float* out_score) {
   const DevQuery& q = sm.q;
   const uint32_t m = v2::presence4(word);
   if ((m & q.req_term_mask) != q.req_term_mask) return false;
   if (m & q.not_term_mask) return false;
   if (L.ix.live_bits && !((L.ix.live_bits[doc >> 5] >> (doc & 31)) & 1u)) return false;
+  // doc-value clauses first: a doc that fails a required range (or hits an excluded one) is dropped before any norm is
+  // gathered or score computed (what ConjunctionDISI does by advancing the cheapest iterators first)
+  uint32_t range_present = 0;
+  if (q.has_nonterm)
+    for (int i = 0; i < q.n_clauses; ++i) {
+      const DevClause& c = sm.cl[i];
+      if (c.kind != NRTGPU_RANGE_I64) continue;
+      const bool p = range_matches(L.ix, c.col, doc, c.lo, c.hi);
+      if (p) { if (c.occur == NRTGPU_MUST_NOT) return false; range_present |= 1u << i; }
+      else if (c.occur == NRTGPU_MUST || c.occur == NRTGPU_FILTER) return false;
+    }
   double must_sum = 0.0, should_sum = 0.0;
   int n_should = 0;
   int cur_field = -1;
@@ -197,7 +209,7 @@ __device__ __noinline__ bool evaluate_doc(const ProbeLaunch& L, const ProbeSmem&
         s = bm25_score(c.weight, f, __ldg(&L.ix.caches[c.field * 256 + nb]));
       }
     } else if (c.kind == NRTGPU_RANGE_I64) {
-      present = range_matches(L.ix, c.col, doc, c.lo, c.hi);
+      present = (range_present >> i) & 1u;
       s = c.weight;
     } else {
       present = true;
@@ -231,7 +243,8 @@ __device__ __noinline__ bool evaluate_doc(const ProbeLaunch& L, const ProbeSmem&
 
 // exact score of a doc of a pure single-field disjunction: double sum, in slot (= clause) order, of Lucene's BM25 float
 // expression for the slots present (BM25Scorer.score; DisjunctionSumScorer / MaxScoreBulkScorer sum in double)
-__device__ __forceinline__ float score_disjunction(const ProbeLaunch& L, const ProbeSmem& sm, const uint8_t* norms0, int n_term,
+template <typename SM>
+__device__ __forceinline__ float score_disjunction(const ProbeLaunch& L, const SM& sm, const uint8_t* norms0, int n_term,
                                                    int32_t doc, uint32_t word) {
   const uint32_t nb = norms0 ? (uint32_t)__ldg(norms0 + doc) : 1u;
   double sum = 0.0;
@@ -250,8 +263,8 @@ __device__ __forceinline__ float score_disjunction(const ProbeLaunch& L, const P
 // Candidate buffer flush (all threads). Entries [0, n_keys) are keys kept by the previous flush; the rest are keys
 // (generic) or unscored (tf word << 32 | doc) pairs (pure disjunctions) which are scored here, one per thread, so the norm
 // loads of the whole buffer overlap. Keeps the best top_k, publishes the k-th key as the query's threshold.
-template <bool kSimple>
-__device__ __noinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& sm, const uint8_t* norms0, int n_term,
+template <bool kSimple, typename SM>
+__device__ __noinline__ void flush_candidates(const ProbeLaunch& L, SM& sm, const uint8_t* norms0, int n_term,
                                                  bool has_after, uint64_t after_key, int top_k, uint64_t* g_theta) {
   __syncthreads();
   int n = sm.cand_count;
@@ -261,14 +274,36 @@ __device__ __noinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& s
     const int n_keys = sm.n_keys;
     constexpr int kPer = kCand / kThreads;
     uint64_t mine[kPer];
+    // every gather of the thread's candidates is issued before the first score is computed: the norm byte, and the
+    // exact tf byte of every slot whose 2-bit plane code saturated
+    uint32_t nbv[kPer], wv[kPer];
 #pragma unroll
     for (int j = 0; j < kPer; ++j) {
       const int i = n_keys + (int)threadIdx.x + j * kThreads;
+      mine[j] = (i < n) ? sm.cand[i] : 0ull;
+      const int32_t doc = (int32_t)(uint32_t)mine[j];
+      nbv[j] = (mine[j] && norms0) ? (uint32_t)__ldg(norms0 + doc) : 1u;
+      uint32_t w = (uint32_t)(mine[j] >> 32);
+#pragma unroll
+      for (int s2 = 0; s2 < kT; ++s2)
+        if (((w >> (8 * s2)) & 0xffu) == kTfInexact && sm.s_plane[s2])
+          w = (w & ~(0xffu << (8 * s2))) | ((uint32_t)__ldg(sm.s_plane[s2] + doc) << (8 * s2));
+      wv[j] = w;
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
       uint64_t key = 0ull;
-      if (i < n) {
-        const uint64_t e = sm.cand[i];
-        const int32_t doc = (int32_t)(uint32_t)e;
-        key = make_key(score_disjunction(L, sm, norms0, n_term, doc, (uint32_t)(e >> 32)), doc);
+      if (mine[j]) {
+        const int32_t doc = (int32_t)(uint32_t)mine[j];
+        double sum = 0.0;   // BM25Scorer.score per slot (float), DisjunctionSumScorer / MaxScoreBulkScorer sum in double, slot order
+#pragma unroll
+        for (int s2 = 0; s2 < kT; ++s2) {
+          const uint32_t b = (wv[j] >> (8 * s2)) & 0xffu;
+          if (s2 >= n_term || b == 0u) continue;
+          const float f = (b == 255u) ? exact_freq_slow<uint32_t>(L.ix, sm.cl[sm.s_clause[s2]], doc) : (float)b;
+          sum += (double)bm25_score(sm.s_weight[s2], f, __ldg(&L.ix.caches[sm.s_field[s2] * 256 + nbv[j]]));
+        }
+        key = make_key((float)sum, doc);
         if (!(key > theta) || (has_after && !(key < after_key))) key = 0ull;   // a real key is never 0
       }
       mine[j] = key;
@@ -293,9 +328,11 @@ __device__ __noinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& s
     }
   }
   const int m = next_pow2(n < 2 ? 2 : n);
+  const long long ts = L.stats ? clock64() : 0ll;
   for (int i = n + threadIdx.x; i < m; i += kThreads) sm.cand[i] = 0ull;
   __syncthreads();
   block_bitonic_sort_desc(sm.cand, m);
+  if (L.stats && threadIdx.x == 0) atomicAdd(&L.stats[15], (unsigned long long)(clock64() - ts));
   if (threadIdx.x == 0) {
     const int keep = n < top_k ? n : top_k;
     sm.cand_count = keep;
@@ -314,7 +351,8 @@ __device__ __noinline__ void flush_candidates(const ProbeLaunch& L, ProbeSmem& s
 }
 
 // binary search of doc in the sorted smem range [l, h); returns the tf byte (0 = absent)
-__device__ __forceinline__ uint32_t probe_smem(const ProbeSmem& sm, int l, int h, int32_t doc) {
+template <typename SM>
+__device__ __forceinline__ uint32_t probe_smem(const SM& sm, int l, int h, int32_t doc) {
   const int end = h;
   while (l < h) {
     const int mid = (l + h) >> 1;
@@ -332,9 +370,11 @@ __device__ __noinline__ uint32_t probe_global(const int32_t* docs, const uint8_t
 }
 
 // kStats: the profiling instantiation (NRTGPU_DEBUG_MODES=1) keeps cycle counters; the production one has none of their registers
-template <bool kSimple, bool kStats>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(const __grid_constant__ ProbeLaunch L) {
+template <bool kSimple, bool kStats, int kCtas, int kStageT>
+__global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __grid_constant__ ProbeLaunch L) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  using ProbeSmem = ProbeSmemT<kStageT>;
+  constexpr int kStage = kStageT, kShortMax = ProbeSmem::kShortMax;
   ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -444,7 +484,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) posting_probe_kernel(con
     if (kSimple) {
       // ubt[sum min(tf_s, 5) * 6^s]: the double clause sum with every term at the shortest field length present
       // (tf >= 5 bounded by the clause weight, the limit tf -> inf) -- an upper bound of the doc's score
-      for (int i = tid; i < kUbt; i += kThreads) {
+      const int n_ubt = n_term >= 4 ? kUbt : (n_term == 3 ? 216 : (n_term == 2 ? 36 : 6));   // patterns of the slots that exist
+      for (int i = tid; i < n_ubt; i += kThreads) {
         const int c[kT] = {i % 6, (i / 6) % 6, (i / 36) % 6, i / 216};
         double sum = 0.0;
 #pragma unroll

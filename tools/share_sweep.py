@@ -18,7 +18,7 @@ sh.columns = [ix.synth_int_column(docs)]; sh.column_has = [None]
 disj = bench.make_queries(1024, 1_000_000); conj = bench.make_conj_queries(1024, 1_000_000)
 for cfg in sys.argv[2].split(","):
     share, post = cfg.split(":")
-    os.environ["NRTGPU_ITEM_SHARE"] = share; os.environ["NRTGPU_ITEM_POSTINGS"] = post
+    os.environ["NRTGPU_ITEM_SHARE_FULL"] = share; os.environ["NRTGPU_ITEM_POSTINGS"] = post
     ctx = GpuContext(0); gix = GpuIndex(ctx, sh); s = GpuIndexSearcher(gix)
     out = {}
     for leg, (qs, thr) in {"top": (disj, 1000), "complete": (disj, 2**31 - 1), "conj": (conj, 1000)}.items():
