@@ -140,6 +140,8 @@ struct nrtgpu_ctx {
   int64_t item_postings = 32768; // NRTGPU_ITEM_POSTINGS: floor of the postings a (query, slice) may hold before it is split into 2..16 parts
   int64_t item_share_full = 32;  // NRTGPU_ITEM_SHARE_FULL: the same for launches that visit every posting (ScoreMode.COMPLETE, generic clause evaluation)
   int64_t item_share = 12;       // NRTGPU_ITEM_SHARE: ... and it is split when it exceeds 1/share of the postings per resident CTA
+  int64_t warm_min_docs = 8ll * v2::kWarmGran * v2::kGran;   // NRTGPU_WARM_MIN_DOCS: shards below this size run without warm-up items
+  int slice_gran = 512;          // NRTGPU_SLICE_GRAN: granules (1024 docs) per slice of the probe kernel, <= v3::kMaxSliceGran
   int probe_cfg = 0;             // NRTGPU_PROBE_CFG: 0 auto, 1 always A (3 CTAs / SM), 2 always B (4 CTAs / SM)
   bool order_lpt = false;        // NRTGPU_ORDER=lpt: query-major work order, longest query first
   bool order_by_cost = false;   // NRTGPU_ORDER=cost: round-1 work order (longest query first) instead of plane clusters
@@ -357,6 +359,8 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   { const char* e = getenv("NRTGPU_ENGINE"); c->engine_stream = e && std::strcmp(e, "stream") == 0; }
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
   { const char* e = getenv("NRTGPU_PROBE_CFG"); c->probe_cfg = e ? atoi(e) : 0; }
+  { const char* e = getenv("NRTGPU_WARM_MIN_DOCS"); if (e && atoll(e) > 0) c->warm_min_docs = atoll(e); }
+  { const char* e = getenv("NRTGPU_SLICE_GRAN"); if (e && atoi(e) >= 64) c->slice_gran = std::min(atoi(e), (int)v3::kMaxSliceGran); }
   { const char* e = getenv("NRTGPU_ITEM_POSTINGS"); if (e && atoll(e) > 0) c->item_postings = atoll(e); }
   { const char* e = getenv("NRTGPU_ITEM_SHARE"); if (e && atoll(e) > 0) c->item_share = atoll(e); }
   { const char* e = getenv("NRTGPU_ITEM_SHARE_FULL"); if (e && atoll(e) > 0) c->item_share_full = atoll(e); }
@@ -831,7 +835,11 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if (sorted && b->wide_slots) NRT_FAIL(NRTGPU_ERR_UNSUPPORTED, "sorted search: more than 4 term clauses or top_k > 512 is not on the GPU path");
   if (!b->wide_slots) {
     // slices of equal size, a multiple of the 1024-doc granule, at most 512K docs: a 1.25M-doc shard is 3 x 417K, not 2.38 -> 3 x 512K
-    const int64_t n_sl = std::max<int64_t>(1, ((int64_t)ix->n_docs + v2::kSliceDocs - 1) / v2::kSliceDocs);
+    // (probe kernel: slices of up to slice_gran granules -- NRTGPU_SLICE_GRAN, default and maximum 512: the MAXSCORE roles of an
+    //  item are fixed when it starts, so larger slices prune with staler thresholds -- measured slower -- and smaller ones pay
+    //  the per-item set-up more often)
+    const int64_t max_slice_docs = (!ix->ctx->engine_stream) ? (int64_t)ix->ctx->slice_gran * v2::kGran : (int64_t)v2::kSliceDocs;
+    const int64_t n_sl = std::max<int64_t>(1, ((int64_t)ix->n_docs + max_slice_docs - 1) / max_slice_docs);
     slice_docs = (((int64_t)ix->n_docs + n_sl - 1) / n_sl + v2::kGran - 1) / v2::kGran * v2::kGran;
     if (slice_docs < v2::kGran) slice_docs = v2::kGran;
   }
@@ -882,7 +890,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   // prune from the first slice on). Window kernel: TOP_SCORES mode, queries with a dense list; probe kernel: both score
   // modes, every query whose lists are expected to hold 2 * top_k hits in those granules.
   const bool warm_ok = !b->wide_slots && (b->use_probe || b->threshold < (int64_t)INT32_MAX) &&
-                       (int64_t)ix->n_docs >= 8ll * v2::kWarmGran * v2::kGran;
+                       (int64_t)ix->n_docs >= (int64_t)ix->ctx->warm_min_docs;
   std::vector<uint8_t> has_warm((size_t)nq, 0);
   if (warm_ok) {
     for (int qi : order) {
