@@ -724,6 +724,40 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       uint32_t cb = 0;      // first posting (of the slot's run segment) of the thread's next round
       uint64_t park[kR];
       uint32_t pmask = 0;   // parked candidates of this thread
+      // generic queries: per-warp queue of (doc, tf word) pairs awaiting clause evaluation (lives in the bound table's
+      // shared memory, which only pure disjunctions use); qn is warp-uniform
+      uint2* const wq = reinterpret_cast<uint2*>(sm.ubt) + (tid >> 5) * 64;
+      static_assert(kUbt * sizeof(float) >= (kThreads / 32) * 64 * sizeof(uint2), "warp queues do not fit the bound table");
+      int qn = 0;
+      const uint32_t q_req = sm.q.req_term_mask, q_not = sm.q.not_term_mask;
+      auto drain = [&](int n_take) -> bool {   // evaluates the last n_take (<= 32) queued pairs; true: a lane had to park its hit
+        __syncwarp();
+        bool parked = false;
+        const bool have = lane < n_take;
+        const uint2 e = have ? wq[qn - n_take + lane] : make_uint2(0u, 0u);
+        qn -= n_take;
+        float score;
+        if (have && evaluate_doc(L, sm, (int32_t)e.x, e.y, &score)) {
+          const int32_t d = (int32_t)e.x;
+          ++my_hits;
+          if (L.aggs) agg_collect(*L.aggs, L.ix, qi, d);   // additional collectors see every matching doc
+          uint64_t entry;
+          if (L.sort_kind == NRTGPU_SORT_RELEVANCE) entry = make_key(score, d);
+          else {   // TopFieldCollector: the key is the doc's sort value (order-preserving code), ties by doc id
+            uint32_t code = 0;
+            if (L.sort_kind == NRTGPU_SORT_COLUMN) { code = __ldg(L.sort_codes + d); if (code == 0u) code = sort_missing; }
+            entry = ((uint64_t)sort_hi(L.sort_kind, L.sort_reverse, code, d) << 32) | (uint32_t)(~(uint32_t)d);
+          }
+          const unsigned long long th = sm.theta;
+          if (entry > th && !(has_after && !(entry < after_key)) && !NRT_KNOCK(4)) {
+            const int p = atomicAdd(&sm.cand_count, 1);
+            if (p < kCand) sm.cand[p] = entry;
+            else { park[0] = entry; pmask |= 1u; parked = true; }
+          }
+        }
+        __syncwarp();
+        return parked;
+      };
       for (;;) {
         bool full = false;
 #pragma unroll
@@ -732,6 +766,10 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
             const int p = atomicAdd(&sm.cand_count, 1);
             if (p < kCand) { sm.cand[p] = park[j]; pmask &= ~(1u << j); } else full = true;
           }
+        if (!kSimple) {   // the warp moves together (its queue operations are collective); a queue left >= 32 by a full buffer is
+          full = __any_sync(0xffffffffu, full);   // brought below 32 before the sweep pushes again (capacity 64)
+          while (!full && qn >= 32) full = __any_sync(0xffffffffu, drain(32));
+        }
         const int ct_end = NRT_KNOCK(8) ? 0 : (dense ? n_term + 1 : n_term);   // dense: one more "list" = every doc of the run
         while (!full && ct < ct_end) {
           const bool t_dense = ct == n_term;
@@ -814,9 +852,9 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
                 }
               }
             }
-            // ownership, hit count, bound test / clause evaluation, append
+            // ownership, hit count, bound test, append (pure disjunctions; the generic path follows)
 #pragma unroll
-            for (int j = 0; j < kR; ++j) {
+            for (int j = 0; kSimple && j < kR; ++j) {
               if (doc[j] < 0) continue;
               uint32_t v = word[j];
               if (need_plane) {
@@ -836,27 +874,41 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
                 if (sm.ubt[__dp4a(__vminu4(v, 0x05050505u), 0xD8240601u, 0u)] < theta_s) continue;   // cannot reach the top-k
                 entry = ((uint64_t)v << 32) | (uint32_t)doc[j];   // scored at the next flush
               } else {
-                if ((v & candbelow) != 0u) continue;   // a lower driver list owns this doc
-                float score;
-                if (!evaluate_doc(L, sm, doc[j], v, &score)) continue;
-                ++my_hits;
-                if (L.aggs) agg_collect(*L.aggs, L.ix, qi, doc[j]);   // additional collectors see every matching doc
-                if (L.sort_kind == NRTGPU_SORT_RELEVANCE) entry = make_key(score, doc[j]);
-                else {   // TopFieldCollector: the key is the doc's sort value (order-preserving code), ties by doc id
-                  uint32_t code = 0;
-                  if (L.sort_kind == NRTGPU_SORT_COLUMN) { code = __ldg(L.sort_codes + doc[j]); if (code == 0u) code = sort_missing; }
-                  entry = ((uint64_t)sort_hi(L.sort_kind, L.sort_reverse, code, doc[j]) << 32) | (uint32_t)(~(uint32_t)doc[j]);
-                }
-                if (!(entry > theta) || (has_after && !(entry < after_key))) continue;
+                continue;   // (generic queries: the survivors of the round are queued below and evaluated a full warp at a time)
               }
               if (NRT_KNOCK(4)) continue;
               const int p = atomicAdd(&sm.cand_count, 1);
               if (p < kCand) sm.cand[p] = entry;
               else { park[j] = entry; pmask |= 1u << j; full = true; }
             }
+            if (!kSimple) {
+              // Generic queries: most driver postings fail the other required lists, so the clause evaluation (norm and
+              // doc-value gathers, BM25) would run with a handful of lanes. The survivors of the cheap tests -- not owned by
+              // a lower list, every required term present, no excluded term -- go to a per-warp queue and are evaluated
+              // 32 at a time.
+#pragma unroll
+              for (int j = 0; j < kR; ++j) {
+                uint32_t v = word[j];
+                if (need_plane) {
+                  const uint32_t raw = pbyte[j][0] | (pbyte[j][1] << 8) | (pbyte[j][2] << 16) | (pbyte[j][3] << 24);
+                  const uint32_t codes = (raw >> (((uint32_t)max(doc[j], 0) & 3u) * 2u)) & 0x03030303u;
+                  const uint32_t sat = __vcmpeq4(codes, 0x03030303u);
+                  v |= (codes & ~sat) | (sat & (kTfInexact * 0x01010101u));
+                }
+                const uint32_t pres = v2::presence4(v);
+                const bool surv = doc[j] >= 0 && (v & candbelow) == 0u && (pres & q_req) == q_req && (pres & q_not) == 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, surv);
+                if (surv) wq[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint2((uint32_t)doc[j], v);
+                qn += __popc(bal);
+                while (!full && qn >= 32) full = __any_sync(0xffffffffu, drain(32));   // (a parked hit stops the warp: park[0] is free whenever drain runs)
+              }
+            }
             cb += kR * kThreads;
             if (kStats && tid == 0) ++dbg_rounds;
           }
+        }
+        if (!kSimple) {   // the rest of the warp's queue (a partial warp), unless the buffer is full: then after the flush
+          while (!full && qn > 0) full = __any_sync(0xffffffffu, drain(min(qn, 32)));
         }
         __syncthreads();
         if (sm.cand_count <= kCand) break;   // nobody is parked (the count passes kCand only through a failed append)
