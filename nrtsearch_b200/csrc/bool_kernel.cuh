@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
   __shared__ uint64_t keys[kMergeCap];
   __shared__ int32_t s_cnt[kMergeThreads];
   __shared__ int32_t s_nz[kMergeThreads];   // the non-empty lists of a chunk of list counts
+  __shared__ int32_t s_off[kMergeThreads];
   __shared__ int32_t s_nnz;
   __shared__ int32_t s_fill;
   const int q = blockIdx.x;
@@ -462,34 +463,48 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
     if (c > 0) { const int p = atomicAdd(&s_nnz, 1); s_nz[p] = l; s_cnt[p] = c; }
     __syncthreads();
     const int nnz = s_nnz;
-    int total = 0;
-    for (int i = 0; i < nnz; ++i) total += s_cnt[i];
-    if (have + total > kMergeCap && dirty) sort_and_cut();
-    if (have + total <= kMergeCap) {
-      // every list of the chunk fits: one warp per list, no barrier between lists; keys below the floor are dropped
+    // exclusive prefix of the non-empty lists' counts (block-wide Hillis-Steele scan): the keys of the chunk become one flat
+    // range that the 256 threads read with independent loads, instead of list after list
+    s_off[tid] = tid < nnz ? s_cnt[tid] : 0;
+    __syncthreads();
+    for (int d = 1; d < kMergeThreads; d <<= 1) {
+      const int v = tid >= d ? s_off[tid - d] : 0;
+      __syncthreads();
+      s_off[tid] += v;
+      __syncthreads();
+    }
+    // (inclusive scan: s_off[i] = keys of lists 0..i of the chunk)
+    int i0 = 0;
+    while (i0 < nnz) {
+      // the longest run of lists [i0, i1) that fits behind the keys kept so far (worst case: no key below the floor)
+      const int base = i0 ? s_off[i0 - 1] : 0;
+      if (have + (s_off[i0] - base) > kMergeCap) sort_and_cut();   // room for list i0 at least (after the cut: <= top_k + top_k keys)
+      int i1 = i0 + 1;
+      while (i1 < nnz && have + (s_off[i1] - base) <= kMergeCap) ++i1;
+      const int n_flat = s_off[i1 - 1] - base;
       __syncthreads();
       if (tid == 0) s_fill = have;
       __syncthreads();
-      for (int i0 = tid >> 5; i0 < nnz; i0 += kMergeThreads / 32) {
-        const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
-        for (int i = tid & 31; i < s_cnt[i0]; i += 32) { const uint64_t k = src[i]; if (k >= floor_key) keys[atomicAdd(&s_fill, 1)] = k; }
+      for (int e0 = tid; e0 < n_flat; e0 += 4 * kMergeThreads) {   // four independent loads in flight per thread
+        uint64_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kMergeThreads;
+          kk[u] = 0ull;
+          if (e < n_flat) {
+            int lo = i0, hi = i1;   // list of flat element e: the first i in [i0, i1) with s_off[i] - base > e
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_off[mid] - base > e) hi = mid; else lo = mid + 1; }
+            kk[u] = M.slice_keys[((size_t)q * M.n_lists + s_nz[lo]) * M.top_k + (e - (lo > i0 ? s_off[lo - 1] - base : 0))];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (kk[u] != 0ull && kk[u] >= floor_key) keys[atomicAdd(&s_fill, 1)] = kk[u];   // (a real key is never 0)
       }
       __syncthreads();
       if (s_fill > have) dirty = true;
       have = s_fill;
-    } else {
-      for (int i0 = 0; i0 < nnz; ++i0) {
-        const int cnt = s_cnt[i0];
-        if (have + cnt > kMergeCap) sort_and_cut();
-        const uint64_t* src = M.slice_keys + ((size_t)q * M.n_lists + s_nz[i0]) * M.top_k;
-        __syncthreads();
-        if (tid == 0) s_fill = have;
-        __syncthreads();
-        for (int i = tid; i < cnt; i += kMergeThreads) { const uint64_t k = src[i]; if (k >= floor_key) keys[atomicAdd(&s_fill, 1)] = k; }
-        __syncthreads();
-        have = s_fill;
-        dirty = true;
-      }
+      i0 = i1;
     }
   }
   if (dirty) sort_and_cut();
