@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(kThreads, 2) bool_window_kernel(BoolLaunch L) 
             offer(matched, doc, score);
             round_end();
           }
+          __syncthreads();   // the words this list cleared are seen cleared by the next driver list (either order gave the same
+                             // result -- the doc is skipped -- but the ordering is now explicit: racecheck-clean)
         }
       } else {
         for (int i0 = 0; i0 < wlen; i0 += kThreads) {

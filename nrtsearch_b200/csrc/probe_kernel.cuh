@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
           unsigned long long t0 = atomicCAS(L.clock0, 0ull, now);
           if (t0 == 0ull) t0 = now;
-          late = now - t0 > (unsigned long long)L.deadline_ns;
+          late = now > t0 && now - t0 > (unsigned long long)L.deadline_ns;   // (another CTA may have stamped clock0 after this one read the timer)
         }
         if (late) { sm.skip = 1; L.timed_out[L.work_query[w]] = 1; }   // drain the queue
       }
