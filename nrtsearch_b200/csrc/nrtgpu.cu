@@ -762,7 +762,9 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
     for (int ci = q.clause_begin; ci < q.clause_end; ++ci) {
       const nrtgpu_clause& c = clauses[ci];
       if (c.occur < NRTGPU_SHOULD || c.occur > NRTGPU_MUST_NOT) NRT_FAIL(NRTGPU_ERR_INVALID, "bad occur");
-      if (c.boost < 0.0f) NRT_FAIL(NRTGPU_ERR_INVALID, "Boost must be a positive number");  // QueryNodeMapper.java:127
+      // QueryNodeMapper.java:127-133: the reference rejects boost < 0 with exactly this message and treats the proto default 0 as
+      // "no boost"; the adaptor folds that rule before it fills the clause, so 0 here is a weight of 0, not an error
+      if (c.boost < 0.0f) NRT_FAIL(NRTGPU_ERR_INVALID, "Boost must be a positive number");
       DevClause x; std::memset(&x, 0, sizeof(x));
       x.occur = c.occur; x.kind = c.kind; x.slot = -1; x.plane = -1; x.gran_row = -1; x.lo = c.lo; x.hi = c.hi;
       x.scoring = (c.occur == NRTGPU_MUST || c.occur == NRTGPU_SHOULD) ? 1 : 0;
@@ -1069,7 +1071,11 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
         v3::ProbeLaunch P;
         P.ix = L.ix; P.clauses = L.clauses; P.queries = L.queries; P.sbounds = b->sbounds.p;
         P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr;
-        { const char* e = getenv("NRTGPU_KNOCK"); P.knock = e ? atoi(e) : 0; }
+#ifdef NRT_PROBE_KNOCK
+        { const char* e = getenv("NRTGPU_KNOCK"); P.knock = e ? atoi(e) : 0; }   // profiling builds only (tools/knock.py)
+#else
+        P.knock = 0;
+#endif
         P.n_lists = b->n_lists; P.parts_max = b->parts_max; P.n_slices = b->n_slices; P.top_k = b->top_k; P.slice_docs = b->slice_docs; P.n_gran = b->n_gran;
         P.threshold = b->threshold; P.pruned = b->pruned.p; P.theta = L.theta; P.total_hits = L.total_hits;
         P.slice_keys = L.slice_keys; P.slice_cnt = L.slice_cnt;

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Knock-out timing of the posting kernel (profiling aid): one index build, then the TOP_SCORES / COMPLETE / conj batches
-timed with parts of the kernel disabled through NRTGPU_KNOCK (results are wrong by construction; only times matter)."""
+timed with parts of the kernel disabled through NRTGPU_KNOCK (results are wrong by construction; only times matter).
+Needs a library built with -DNRT_PROBE_KNOCK (make EXTRA=-DNRT_PROBE_KNOCK in nrtsearch_b200/csrc, or a variant under
+gpurun_variants/ loaded through NRTGPU_LIB_PATH): the production build compiles the switches out."""
 import json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
