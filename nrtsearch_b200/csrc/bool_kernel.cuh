@@ -425,6 +425,7 @@ struct MergeLaunch {
   const unsigned long long* total_hits; const int32_t* pruned; int32_t* terminated;
   long long terminate_after;                  // > 0: a query with more hits than this terminated early (TerminateAfterWrapper.java:150-158)
   long long* out_total; int32_t* out_flags;   // flags: bit 0 relation GREATER_THAN_OR_EQUAL_TO, bit 1 terminated early
+  const unsigned long long* known_hits = nullptr;   // optional [nq]: docs known to match (reported totalHits = max(counted, known))
   const uint64_t* theta = nullptr;            // optional [nq]: the k-th best key some work item published (>= top_k keys are >= it):
                                               // smaller keys cannot be in the merged page and are dropped before the sort
 };
@@ -521,7 +522,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_slices_kernel(MergeLaunch
     M.out_counts[q] = have;
     if (M.terminate_after > 0 && M.terminated && M.total_hits && (long long)M.total_hits[q] > M.terminate_after) M.terminated[q] = 1;
     const bool term = M.terminated && M.terminated[q];
-    if (M.out_total) M.out_total[q] = M.total_hits ? (long long)M.total_hits[q] : 0ll;
+    if (M.out_total) {
+      long long t = M.total_hits ? (long long)M.total_hits[q] : 0ll;
+      if (M.known_hits && M.pruned && M.pruned[q] && (long long)M.known_hits[q] > t) t = (long long)M.known_hits[q];   // a lower bound either way
+      M.out_total[q] = t;
+    }
     if (M.out_flags) M.out_flags[q] = ((M.pruned && M.pruned[q]) || term ? 1 : 0) | (term ? 2 : 0);
   }
 }

@@ -141,6 +141,7 @@ struct nrtgpu_ctx {
   int64_t item_share_full = 32;  // NRTGPU_ITEM_SHARE_FULL: the same for launches that visit every posting (ScoreMode.COMPLETE, generic clause evaluation)
   int64_t item_share = 12;       // NRTGPU_ITEM_SHARE: ... and it is split when it exceeds 1/share of the postings per resident CTA
   int64_t warm_min_docs = 8ll * v2::kWarmGran * v2::kGran;   // NRTGPU_WARM_MIN_DOCS: shards below this size run without warm-up items
+  bool warm_sweep = true;        // NRTGPU_WARM=docs: warm-up items sweep the first 32K docs (round-2 first style) instead of the rarest list
   int slice_gran = 512;          // NRTGPU_SLICE_GRAN: granules (1024 docs) per slice of the probe kernel, <= v3::kMaxSliceGran
   int probe_cfg = 0;             // NRTGPU_PROBE_CFG: 0 auto, 1 always A (3 CTAs / SM), 2 always B (4 CTAs / SM)
   bool order_lpt = false;        // NRTGPU_ORDER=lpt: query-major work order, longest query first
@@ -278,6 +279,8 @@ struct nrtgpu_batch {
   int64_t terminate_after_max_recall = 0;
   std::vector<DevClause> h_dc; std::vector<DevQuery> h_dq; std::vector<int32_t> h_wq, h_ws;   // host copies the async uploads read
   int32_t slice_docs = 0;
+  DevBuf<unsigned long long> known_hits;        // probe kernel: docs known to match per query (0: unknown)
+  std::vector<unsigned long long> h_known;
   int32_t parts_max = 1;       // probe kernel: parts a (query, slice) work item may be split into (power of two)
   int64_t threshold = INT32_MAX;
   int32_t n_gran = 0;
@@ -360,6 +363,7 @@ int nrtgpu_init(int device_id, nrtgpu_ctx** out) {
   c->debug_modes = getenv("NRTGPU_DEBUG_MODES") != nullptr;
   { const char* e = getenv("NRTGPU_PROBE_CFG"); c->probe_cfg = e ? atoi(e) : 0; }
   { const char* e = getenv("NRTGPU_WARM_MIN_DOCS"); if (e && atoll(e) > 0) c->warm_min_docs = atoll(e); }
+  { const char* e = getenv("NRTGPU_WARM"); c->warm_sweep = !(e && std::strcmp(e, "docs") == 0); }
   { const char* e = getenv("NRTGPU_SLICE_GRAN"); if (e && atoi(e) >= 64) c->slice_gran = std::min(atoi(e), (int)v3::kMaxSliceGran); }
   { const char* e = getenv("NRTGPU_ITEM_POSTINGS"); if (e && atoll(e) > 0) c->item_postings = atoll(e); }
   { const char* e = getenv("NRTGPU_ITEM_SHARE"); if (e && atoll(e) > 0) c->item_share = atoll(e); }
@@ -894,9 +898,35 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   const bool warm_ok = !b->wide_slots && (b->use_probe || b->threshold < (int64_t)INT32_MAX) &&
                        (int64_t)ix->n_docs >= (int64_t)ix->ctx->warm_min_docs;
   std::vector<uint8_t> has_warm((size_t)nq, 0);
+  // probe kernel, pure disjunctions on a shard without deletes: the longest list is a lower bound of the matching docs
+  // (pruning may start as soon as that exceeds totalHitsThreshold), and the warm-up SWEEPS the first 32K postings of the
+  // highest-bound (rarest) list over the whole shard instead of the first 32K docs (flags 4; NRTGPU_WARM=docs: old style)
+  b->h_known.assign((size_t)nq, 0ull);
+  const bool limits_may_apply = true;   // (terminateAfter counts collected hits only: the kernel never uses known_hits for it)
+  (void)limits_may_apply;
+  if (b->use_probe && !ix->live_bits.p && !sorted && n_aggs == 0)
+    for (int qi : order) {
+      if (!is_simple(qi)) continue;
+      int64_t mx = 0;
+      for (int c = 0; c < dq[qi].n_clauses; ++c) mx = std::max<int64_t>(mx, dc[(size_t)dq[qi].clause_begin + c].n_post);
+      b->h_known[(size_t)qi] = (unsigned long long)mx;
+    }
   if (warm_ok) {
     for (int qi : order) {
       if (!is_simple(qi)) continue;
+      // (not with searchAfter: a doc whose LOWER-BOUND key passes the after filter may in truth lie on an earlier page, and
+      //  would be counted towards the k keys that justify the threshold)
+      if (b->use_probe && ix->ctx->warm_sweep && !dq[qi].has_after) {
+        int best = -1; float best_ub = -1.0f;
+        for (int c = 0; c < dq[qi].n_clauses; ++c) {
+          const DevClause& x = dc[(size_t)dq[qi].clause_begin + c];
+          if (x.kind == NRTGPU_TERM && x.ub > best_ub) { best_ub = x.ub; best = c; }
+        }
+        if (best >= 0 && dc[(size_t)dq[qi].clause_begin + best].n_post >= 2 * (int64_t)top_k) {
+          wq.push_back(qi); ws.push_back(0 | (dc[(size_t)dq[qi].clause_begin + best].slot << 16) | (4 << 24));
+          continue;   // (has_warm stays 0: the query's slice-0 items cover the whole slice)
+        }
+      }
       if (b->use_probe) {
         if (cost[qi] * (int64_t)(v2::kWarmGran * v2::kGran) >= 2ll * top_k * (int64_t)ix->n_docs) has_warm[(size_t)qi] = 1;
       } else {
@@ -966,6 +996,7 @@ static int batch_build(nrtgpu_batch* b, nrtgpu_index* ix, const nrtgpu_clause* c
   if ((rc = b->queries.upload_async(b->h_dq.data(), b->h_dq.size(), st))) return rc;
   if ((rc = b->work_query.upload_async(wq.data(), wq.size(), st))) return rc;
   if ((rc = b->work_slice.upload_async(ws.data(), ws.size(), st))) return rc;
+  if ((rc = b->known_hits.upload_async(b->h_known.data(), b->h_known.size(), st))) return rc;
   if (sorted) {
     bool any_after = false;
     b->h_after_docs.assign((size_t)nq, 0);
@@ -1048,8 +1079,11 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   int rc_dbg = 0;
   NRT_CUDA_TRY(cudaSetDevice(b->ix->ctx->device));
-  NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
-  NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
+  static const bool keep_theta = getenv("NRTGPU_EXPERIMENT_KEEP_THETA") != nullptr;   // timing experiment only: a run starts with the previous run's thresholds
+  if (!keep_theta || !b->ran) {
+    NRT_CUDA_TRY(cudaMemsetAsync(b->theta.p, 0, b->theta.bytes(), st));
+    NRT_CUDA_TRY(cudaMemsetAsync(b->total_hits.p, 0, b->total_hits.bytes(), st));
+  }
   NRT_CUDA_TRY(cudaMemsetAsync(b->slice_cnt.p, 0, b->slice_cnt.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->pruned.p, 0, b->pruned.bytes(), st));
   NRT_CUDA_TRY(cudaMemsetAsync(b->terminated.p, 0, b->terminated.bytes(), st));
@@ -1070,7 +1104,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       if (n_probe > 0) {
         v3::ProbeLaunch P;
         P.ix = L.ix; P.clauses = L.clauses; P.queries = L.queries; P.sbounds = b->sbounds.p;
-        P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr;
+        P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr; P.known_hits = b->known_hits.p;
 #ifdef NRT_PROBE_KNOCK
         { const char* e = getenv("NRTGPU_KNOCK"); P.knock = e ? atoi(e) : 0; }   // profiling builds only (tools/knock.py)
 #else
@@ -1204,6 +1238,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   M.total_hits = b->total_hits.p; M.pruned = b->pruned.p; M.terminated = b->terminated.p; M.terminate_after = b->ta_scalar;
   M.out_total = b->bound_total; M.out_flags = b->bound_flags;
   M.theta = b->use_probe ? b->theta.p : nullptr;
+  M.known_hits = b->use_probe ? b->known_hits.p : nullptr;
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
   if (b->sort_kind != NRTGPU_SORT_RELEVANCE) {   // FieldDoc values of the final hits; scores become NaN
@@ -1248,6 +1283,8 @@ static int batch_fetch_impl(nrtgpu_batch* b, void* stream_, int32_t* out_docs, f
     if (out_relation) out_relation[i] = (pr[(size_t)i] || term || to) ? 1 : 0;
     if (out_terminated_early) out_terminated_early[i] = term ? 1 : 0;
     if (out_hit_timeout) out_hit_timeout[i] = to ? 1 : 0;
+    if (out_total_hits && pr[(size_t)i] && !term && !to && (size_t)i < b->h_known.size() && (int64_t)b->h_known[(size_t)i] > out_total_hits[i])
+      out_total_hits[i] = (int64_t)b->h_known[(size_t)i];   // pruned search: the count is a lower bound; so is the longest list
     if (term && out_total_hits && b->terminate_after_max_recall > 0 && out_total_hits[i] > b->terminate_after_max_recall)
       out_total_hits[i] = b->terminate_after_max_recall;
   }

@@ -78,7 +78,7 @@ struct ProbeLaunch {
   const DevClause* clauses;
   const DevQuery* queries;
   const int32_t* work_query;
-  const int32_t* work_slice;     // slice | part << 16 | log2(parts) << 20 | flags << 24 (1: warm-up item = first kWarmGran granules of slice 0, 2: slice-0 item behind them)
+  const int32_t* work_slice;     // slice | part << 16 | log2(parts) << 20 | flags << 24 (4: sweep warm-up item, see the kernel; 1: warm-up item = first kWarmGran granules of slice 0, 2: slice-0 item behind them)
   const uint32_t* sbounds;       // [nq][kT][n_slices * parts_max + 2]: postings of the slot's list below every part boundary, the shard end, the warm-up boundary
   const uint8_t* field_min_norm;
   unsigned int* work_counter;    // queue head
@@ -108,6 +108,8 @@ struct ProbeLaunch {
   const uint32_t* sort_codes;    // [n_docs] codes of the sort column (0 = doc without a value)
   const uint32_t* sort_missing_code;   // [1] code of the sort's missing value
   const AggLaunch* aggs;         // additional collectors (generic instantiation; device pointer, NULL: none)
+  const unsigned long long* known_hits;   // optional [nq]: docs KNOWN to match (the longest list of a pure disjunction on a shard without
+                                          // deletes): lets pruning start before that many hits were collected (totalHits > threshold is a fact)
   int32_t knock;                 // profiling only (NRTGPU_KNOCK): 1 no plane gathers, 2 no searches, 4 no appends, 8 no sweep
 };
 
@@ -154,6 +156,8 @@ struct alignas(128) ProbeSmemT {
   int cand_count;
   int n_keys;
   unsigned long long hits0;
+  unsigned long long hits_known;   // max(hits0, docs known to match)
+  int theta_dec;                   // 1: the item publishes (k-th key - 1) as threshold (sweep warm-up: its candidates are not output)
   unsigned long long theta;
 };
 static_assert(sizeof(ProbeSmemT<kStageA>) <= 232448 / kCtasA - 1024 && sizeof(ProbeSmemT<kStageB>) <= 232448 / kCtasB - 1024, "ProbeSmem exceeds the per-CTA shared memory budget");
@@ -338,7 +342,7 @@ __device__ __noinline__ void flush_candidates(const ProbeLaunch& L, SM& sm, cons
     sm.cand_count = keep;
     sm.n_keys = keep;
     if (keep == top_k) {
-      const unsigned long long kth = sm.cand[top_k - 1];
+      const unsigned long long kth = sm.cand[top_k - 1] - (unsigned long long)sm.theta_dec;
       const unsigned long long old = atomicMax((unsigned long long*)g_theta, kth);
       const unsigned long long t = old > kth ? old : kth;
       if (t > sm.theta) sm.theta = t;
@@ -415,8 +419,14 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
     const int qi = L.work_query[wi];
     const int slice_raw = L.work_slice[wi];
     const int slice = slice_raw & 0xffff;
-    const int part = (slice_raw >> 16) & 0xf, lparts = (slice_raw >> 20) & 0xf;   // part `part` of 2^lparts of the slice
     const int wflags = slice_raw >> 24;
+    // Sweep warm-up item (flags 4): the first 32K postings of the query's highest-bound list, over the WHOLE shard, probing
+    // only the lists with tf planes (the other lists count as absent: scores are lower bounds). Nothing is output; the
+    // k-th best lower-bound key minus one becomes the query's threshold before any other item of the query runs --
+    // the docs that hold the query's rarest term are where its top-k is, a far better sample than the first 32K docs.
+    const bool sweep_warm = (wflags & 4) != 0;
+    const int warm_slot = (slice_raw >> 16) & 0xf;
+    const int part = sweep_warm ? 0 : ((slice_raw >> 16) & 0xf), lparts = (slice_raw >> 20) & 0xf;   // part `part` of 2^lparts of the slice
     const int ncl = L.queries[qi].n_clauses, cbeg = L.queries[qi].clause_begin, n_term = L.queries[qi].n_term;
     if (tid == 0) {
       sm.q = L.queries[qi];
@@ -424,6 +434,8 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       sm.n_keys = 0;
       sm.theta = *(volatile unsigned long long*)&L.theta[qi];
       sm.hits0 = *(volatile unsigned long long*)&L.total_hits[qi];
+      { const unsigned long long kn = L.known_hits ? L.known_hits[qi] : 0ull; sm.hits_known = kn > sm.hits0 ? kn : sm.hits0; }
+      sm.theta_dec = sweep_warm ? 1 : 0;
     }
     if (tid < ncl) sm.cl[tid] = L.clauses[cbeg + tid];
     if (tid >= 32 && tid < 32 + kT) { const int s = tid - 32; sm.s_kind[s] = kAbsent; sm.s_ia[s] = 0; sm.s_ib[s] = 0; sm.s_ra[s] = 0; sm.s_rb[s] = 0;
@@ -440,6 +452,8 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
     const int e_warm = L.n_slices * L.parts_max + 1;
     if (wflags & 2) g_lo = max(g_lo, min(g_count, kWarmGran));
     if (wflags & 1) { g_hi = min(g_count, kWarmGran); e_hi = e_warm; }
+    const int e_lo2 = sweep_warm ? 0 : e_lo;                              // whole-shard bounds of every list; one dummy run of one granule
+    if (sweep_warm) { g_lo = 0; g_hi = 1; e_hi = L.n_slices * L.parts_max; }
     __syncthreads();   // B1: query + clauses resident
     // terminateAfter (TerminateAfterWrapper.java:150-162): a query that has collected enough hits stops collecting
     if (L.terminate_after > 0 && (long long)sm.hits0 >= L.terminate_after) {
@@ -451,9 +465,10 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       const DevClause& c = sm.cl[tid];
       const int s = c.slot;
       const uint32_t* sb = L.sbounds + ((size_t)qi * kT + s) * sb_stride;
-      uint32_t a = sb[e_lo];
-      const uint32_t b = sb[e_hi];
+      uint32_t a = sb[e_lo2];
+      uint32_t b = sb[e_hi];
       if (wflags & 2) a = max(a, sb[e_warm]);
+      if (sweep_warm && s == warm_slot) b = min(b, a + 32768u);
       sm.s_ia[s] = a; sm.s_ib[s] = max(a, b);
       sm.s_gdocs[s] = L.ix.post_docs + c.post_base;
       sm.s_gf8[s] = L.ix.post_f8 + c.post_base;
@@ -461,12 +476,13 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       sm.s_plane[s] = has_plane ? L.ix.dense_tf + (size_t)c.plane * (size_t)L.ix.dense_stride : nullptr;
       sm.s_plane2[s] = has_plane ? L.ix.dense_tf2 + (size_t)c.plane * (size_t)(L.ix.dense_stride >> 2) : nullptr;
       sm.s_kind[s] = has_plane ? kPlane : (c.gran_row >= 0 ? kLong : kShort);   // kShort may become kGlobal below
+      if (sweep_warm && !has_plane && s != warm_slot) sm.s_kind[s] = kAbsent;   // not probed by the sweep warm-up: counts as absent
       sm.s_weight[s] = c.weight; sm.s_ub[s] = c.ub; sm.s_clause[s] = tid; sm.s_field[s] = c.field;
-      sm.s_pbm[s] = (uint32_t)(c.post_base & (int64_t)(kAlign - 1)); sm.s_row[s] = c.gran_row;
+      sm.s_pbm[s] = (uint32_t)(c.post_base & (int64_t)(kAlign - 1)); sm.s_row[s] = sweep_warm ? -1 : c.gran_row;
     }
     for (int i = 0; i < ncl; ++i) {
       const DevClause& c = sm.cl[i];
-      if (c.kind != NRTGPU_TERM || c.gran_row < 0) continue;
+      if (c.kind != NRTGPU_TERM || c.gran_row < 0 || sweep_warm) continue;
       const uint32_t* row = L.ix.gran_tab + (size_t)c.gran_row * (size_t)(L.n_gran + 1) + g_first;
       for (int g = g_lo + tid; g <= g_hi; g += kThreads) sm.gb[c.slot][g] = __ldg(row + g);
     }
@@ -503,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       const uint32_t all = (n_term >= 32) ? 0xffffffffu : ((1u << n_term) - 1u);
       uint32_t ne = 0;
       const bool complete = L.threshold >= (int64_t)INT32_MAX;
-      if (kSimple && sm.theta != 0ull && (complete || (int64_t)sm.hits0 > L.threshold)) {
+      if (kSimple && !sweep_warm && sm.theta != 0ull && (complete || (int64_t)sm.hits_known > L.threshold)) {
         const float theta_s = key_score(sm.theta);
         int ord[kT]; int n = 0;
         for (int s = 0; s < n_term; ++s) ord[n++] = s;
@@ -530,10 +546,14 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
           else { sm.s_kind[s] = kGlobal; gm |= 1u << s; }
         }
       }
+      if (sweep_warm) { st = 0; lm = 0; shm = 0; gm = 0; }   // the leading list is read in place, nothing is staged or searched
       sm.short_total = st;
       sm.plane_mask = pm; sm.long_mask = lm; sm.short_mask = shm; sm.global_mask = gm;
       uint32_t drv, ess;
-      if (kSimple) {
+      if (kSimple && sweep_warm) {
+        drv = ess = 1u << warm_slot;
+        for (int t = 0; t < n_term; ++t) { sm.s_candbelow[t] = 0u; sm.s_cntbefore[t] = 0xffffffffu; sm.s_need[t] = pm & ~(1u << t); }   // (cntbefore: nothing is counted)
+      } else if (kSimple) {
         ess = all & ~ne;
         int cnt_first = -1;
         if (complete && ne && !L.ix.live_bits) {   // the densest non-essential list with a plane contributes its posting count unread
@@ -930,13 +950,13 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       if (kStats) dbg_tflush += clock64() - tf;
       if (kStats) ++dbg_flush;
     }
-    const int keep = min(sm.cand_count, L.top_k);
-    const int out_list = (wflags & 1) ? L.n_lists - 1 : slice * L.parts_max + part * kfine;
+    const int keep = sweep_warm ? 0 : min(sm.cand_count, L.top_k);
+    const int out_list = (wflags & 5) ? L.n_lists - 1 : slice * L.parts_max + part * kfine;
     uint64_t* out = L.slice_keys + ((size_t)qi * L.n_lists + out_list) * L.top_k;
     for (int i = tid; i < keep; i += kThreads) out[i] = sm.cand[i];
     if (tid == 0) L.slice_cnt[(size_t)qi * L.n_lists + out_list] = keep;
     for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, o);
-    if (lane == 0 && my_hits) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
+    if (lane == 0 && my_hits && !sweep_warm) atomicAdd(&L.total_hits[qi], (unsigned long long)my_hits);
     if (kStats && tid == 0) {
       atomicAdd(&L.stats[0], 1ull);
       atomicAdd(&L.stats[1], (unsigned long long)(clock64() - t_start));
@@ -948,7 +968,7 @@ __global__ void __launch_bounds__(kThreads, kCtas) posting_probe_kernel(const __
       atomicAdd(&L.stats[7], (unsigned long long)dbg_rounds);
       const unsigned long long cyc = (unsigned long long)(clock64() - t_start);
       atomicMax(&L.stats[8], cyc);
-      if (wflags & 1) { atomicAdd(&L.stats[11], 1ull); atomicAdd(&L.stats[12], cyc); }
+      if (wflags & 5) { atomicAdd(&L.stats[11], 1ull); atomicAdd(&L.stats[12], cyc); }
       atomicAdd(&L.stats[13], (unsigned long long)dbg_tflush); atomicAdd(&L.stats[14], (unsigned long long)dbg_twait);
     }
   }
