@@ -144,3 +144,29 @@ def test_multi_slice_top_scores_and_complete_agree(gpu_ctx):
         assert np.array_equal(got[3][eq], want[3][eq])
         if threshold == INT_MAX:
             assert eq.all()
+
+
+def test_pruned_total_hits_is_a_lower_bound_above_the_threshold(gpu_ctx):
+    """TOP_SCORES with the sweep warm-up (threshold from the rarest list's postings, pruning from the first work item because
+    the longest list already proves totalHits > totalHitsThreshold): the page equals the exhaustive oracle's, and a
+    GREATER_THAN_OR_EQUAL_TO count is what the relation says -- above the threshold, never above the exact count
+    (TopDocs.totalHits contract; LazyQueueTopScoreDocCollector.java:129-143)."""
+    sh = ix.synth_text_shard(700_000, 20_000, min_len=6, poisson_mean=40.0)   # 2 slices; warm-up items are scheduled
+    rng = np.random.default_rng(23)
+    qs = []
+    for i in range(160):
+        n_terms = 2 + i % 3
+        ranks = np.unique(np.floor(10 ** rng.uniform(0.3, 4.0, size=n_terms)).astype(np.int64).clip(1, 19_999))
+        qs.append(disj(ranks))
+    qs.append(disj([3, 15_000]))            # a dense list (known hits >> threshold) + a rare one (swept by the warm-up)
+    qs.append(disj([18_000, 19_000]))       # two rare lists: fewer matching docs than the threshold -> exact count
+    thr = 300
+    got, want = run(gpu_ctx, sh, qs, 40, thr)
+    assert_same_hits(got, want, check_total=False, what="sweep warm-up")
+    total, rel = got[3], got[4]
+    exact = want[3]                         # the oracle ran ScoreMode.COMPLETE
+    gte = rel != 0
+    assert gte.any() and (~gte).any()
+    assert np.array_equal(total[~gte], exact[~gte]), "EQUAL_TO counts must be exact"
+    assert (total[gte] > thr).all(), "a pruned search reports more hits than the threshold"
+    assert (total[gte] <= exact[gte]).all(), "a GREATER_THAN_OR_EQUAL_TO count is a lower bound"
