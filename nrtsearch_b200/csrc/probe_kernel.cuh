@@ -6,9 +6,11 @@
 // behind IndexSearcher.search (reference src/main/java/com/yelp/nrtsearch/server/handler/SearchHandler.java:1412).
 //
 // Design (B200-first, nothing like the per-document iterator chain of the reference):
-//   * work item = (query, doc slice), claimed from an atomic queue by PERSISTENT CTAs (3 per SM, 24 warps): no
-//     per-CTA launch cost, warm-up items first, slice-major so that the CTAs resident together probe the same doc
-//     range of the dense tf planes in L2;
+//   * work item = (query, doc slice, part), claimed from an atomic queue by PERSISTENT CTAs (3 or 4 per SM): no per-CTA
+//     launch cost; slice-major so that the CTAs resident together probe the same doc range of the dense tf planes in
+//     L2; a heavy (query, slice) is split into 2..16 parts so that no item is a large share of the launch; warm-up
+//     items first: a query sweeps the first 32K postings of its highest-bound list over the whole shard (lower-bound
+//     scores, nothing output) and publishes a threshold before any of its other items runs;
 //   * the kernel is data parallel over the DRIVER postings of the item: every thread takes postings of the lists
 //     that lead (the essential lists of a disjunction, the rarest required list of a conjunction), and PROBES every
 //     other list for the doc: a byte gather from the list's dense tf plane (index-time direct-address bytes, L2), or
