@@ -1104,7 +1104,8 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
       if (n_probe > 0) {
         v3::ProbeLaunch P;
         P.ix = L.ix; P.clauses = L.clauses; P.queries = L.queries; P.sbounds = b->sbounds.p;
-        P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr; P.known_hits = b->known_hits.p;
+        P.field_min_norm = b->ix->field_min_norm.p; P.stats = nullptr;
+        P.known_hits = b->ix->live_bits.p ? nullptr : b->known_hits.p;   // (deletes installed after the batch was prepared: list lengths no longer bound the hits)
 #ifdef NRT_PROBE_KNOCK
         { const char* e = getenv("NRTGPU_KNOCK"); P.knock = e ? atoi(e) : 0; }   // profiling builds only (tools/knock.py)
 #else
@@ -1238,7 +1239,7 @@ int nrtgpu_batch_run(nrtgpu_batch* b, void* stream_) {
   M.total_hits = b->total_hits.p; M.pruned = b->pruned.p; M.terminated = b->terminated.p; M.terminate_after = b->ta_scalar;
   M.out_total = b->bound_total; M.out_flags = b->bound_flags;
   M.theta = b->use_probe ? b->theta.p : nullptr;
-  M.known_hits = b->use_probe ? b->known_hits.p : nullptr;
+  M.known_hits = (b->use_probe && !b->ix->live_bits.p) ? b->known_hits.p : nullptr;
   merge_slices_kernel<<<b->nq, kMergeThreads, 0, st>>>(M);
   NRT_CUDA_TRY(cudaGetLastError());
   if (b->sort_kind != NRTGPU_SORT_RELEVANCE) {   // FieldDoc values of the final hits; scores become NaN
@@ -1283,7 +1284,7 @@ static int batch_fetch_impl(nrtgpu_batch* b, void* stream_, int32_t* out_docs, f
     if (out_relation) out_relation[i] = (pr[(size_t)i] || term || to) ? 1 : 0;
     if (out_terminated_early) out_terminated_early[i] = term ? 1 : 0;
     if (out_hit_timeout) out_hit_timeout[i] = to ? 1 : 0;
-    if (out_total_hits && pr[(size_t)i] && !term && !to && (size_t)i < b->h_known.size() && (int64_t)b->h_known[(size_t)i] > out_total_hits[i])
+    if (out_total_hits && pr[(size_t)i] && !term && !to && !b->ix->live_bits.p && (size_t)i < b->h_known.size() && (int64_t)b->h_known[(size_t)i] > out_total_hits[i])
       out_total_hits[i] = (int64_t)b->h_known[(size_t)i];   // pruned search: the count is a lower bound; so is the longest list
     if (term && out_total_hits && b->terminate_after_max_recall > 0 && out_total_hits[i] > b->terminate_after_max_recall)
       out_total_hits[i] = b->terminate_after_max_recall;
